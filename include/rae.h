@@ -1,0 +1,160 @@
+/*
+ * rae.h - C ABI of librae.so: the B200 (sm_100a) implementation of the relation-autoencoder training hot path.
+ *
+ * Drop-in boundary.  The reference touches its model only through the compiled Theano callables stored in
+ * ReconstructInducer.func (learning/OieInduction.py:91):
+ *     func['train'](batch_index, neg1[S,B] int32, neg2[S,B] int32) -> cost      (OieInduction.py:146-149)
+ *     func['label_<split>'](batch_index) -> (labels int64[B], probs[B,K])       (OieInduction.py:151-155)
+ * with the dataset bound once as device-resident "shared" copies sliced by batch_index (make_shared,
+ * OieInduction.py:439-449) and the parameters living in theano.shared variables (OieModel.py:50-63).
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); all tensors are C-contiguous with the reference's
+ * shapes: W[F,K] Wb[K] A[N,d] Ab[N] C[d,d,K] (= R for model A) C1[d,K] C2[d,K]; parameters and AdaGrad accumulators are
+ * fp32 DEVICE buffers owned by the caller and borrowed for the lifetime of the binding; ids are int32; "stream" is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns 0 on success or a negative
+ * RAE_E* code; rae_last_error() gives the message.  No C++ exception crosses this boundary.  A handle is not
+ * thread-safe; work is stream-ordered.
+ */
+#ifndef RAE_H_
+#define RAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAE_ABI_VERSION 1
+
+/* decoder selection: construct_decoder(model_type, ...) learning/models/decoders/Decoder.py:84-93 */
+#define RAE_MODEL_A 0  /* 'rescal'    Bilinear.py               */
+#define RAE_MODEL_C 1  /* 'sp'        SelectionalPreferences.py */
+#define RAE_MODEL_AC 2 /* 'rescal+sp' BilinearPlusSP.py         */
+
+/* optimiser selection: _initialize_optimization_algorithm, OieInduction.py:261-269 */
+#define RAE_OPT_ADAGRAD 0 /* Optimizers.py:6-33  */
+#define RAE_OPT_SGD 1     /* Optimizers.py:36-52 */
+
+/* parameter ids (rae_get_dense_grad) */
+#define RAE_P_W 0
+#define RAE_P_WB 1
+#define RAE_P_A 2
+#define RAE_P_AB 3
+#define RAE_P_C 4
+#define RAE_P_C1 5
+#define RAE_P_C2 6
+#define RAE_NUM_PARAMS 7
+
+/* split ids: settings.py:26 split_labels = ['train', 'valid', 'test'] */
+#define RAE_SPLIT_TRAIN 0
+#define RAE_SPLIT_VALID 1
+#define RAE_SPLIT_TEST 2
+#define RAE_NUM_SPLITS 3
+
+/* error codes */
+#define RAE_OK 0
+#define RAE_EINVAL (-1)      /* bad argument / unsupported shape */
+#define RAE_ECUDA (-2)       /* CUDA runtime error (message holds cudaGetErrorString) */
+#define RAE_ENOTBOUND (-3)   /* parameters / split / negatives not bound yet */
+#define RAE_ENOMEM (-4)
+#define RAE_ENODEVICE (-5)   /* no CUDA device: there is NO CPU fallback */
+
+/* flags for rae_config.flags */
+#define RAE_FLAG_FIX_SP_QUIRK 1u    /* use A[args2] on the right side of model C (SelectionalPreferences.py:35 uses args1) */
+#define RAE_FLAG_DENSE_GRADS 2u     /* also materialise dense gradients every step (parity tests; rae_get_dense_grad) */
+#define RAE_FLAG_FORCE_SIMT 4u      /* never take the tcgen05 contraction path */
+#define RAE_FLAG_FORCE_TENSOR 8u    /* fail instead of falling back when the tcgen05 path does not support the shape */
+#define RAE_FLAG_NO_FEATURE_CACHE 16u /* re-sort the batch's (feature, example) pairs every step instead of once at bind */
+
+typedef struct rae_config {
+    int32_t abi_version; /* RAE_ABI_VERSION */
+    int32_t model;       /* RAE_MODEL_*                                   OieInduction.py:475 --decoder     */
+    int32_t K;           /* relations  m                                  OieInduction.py:469 --relations   */
+    int32_t d;           /* embed size r                                  OieInduction.py:468 --embed-size  */
+    int32_t S;           /* negatives per side s                          OieInduction.py:470 --neg-samples */
+    int32_t B;           /* LOCAL batch size l (rows this handle processes per step)  :467 --batch-size     */
+    int64_t F;           /* feature-space dimensionality (rows of W)      OieData.py:96-98                  */
+    int64_t N;           /* entity vocabulary (rows of A)                 OieData.py:92-94                  */
+    int32_t optimizer;   /* RAE_OPT_*                                     OieInduction.py:473               */
+    int32_t ext_reg;     /* regularise decoder weights too                OieModel.py:60-62                 */
+    uint32_t flags;      /* RAE_FLAG_*                                                                      */
+    int32_t device;      /* CUDA device ordinal                                                              */
+    double lr;           /* learning rate                                 OieInduction.py:466               */
+    double l1, l2;       /* lambda_1, lambda_2                            OieInduction.py:471-472           */
+    double alpha;        /* entropy scale                                 OieModel.py:81                    */
+    double adj;          /* batch_size / N_train                          OieInduction.py:131               */
+    int64_t z_total;     /* denominator of the mean, 4B+2BS of the GLOBAL batch (OieModel.py:90); 0 = derive from B,S */
+} rae_config;
+
+typedef struct rae_engine rae_engine; /* opaque */
+
+typedef struct rae_step_stats {
+    int64_t nnz;            /* feature occurrences in the step's batch                     */
+    int64_t unique_w_rows;  /* U_W: distinct rows of W touched                             */
+    int64_t unique_e_rows;  /* U_E: distinct rows of A/Ab touched                          */
+    int64_t entity_occ;     /* (2+2S)*B                                                    */
+    int32_t kernel_launches;/* kernels launched by the step (ours + CUB passes)            */
+    int32_t tensor_path;    /* 1 if the tcgen05 contraction ran, 0 for the SIMT contraction */
+    double algorithmic_bytes; /* SURVEY 8(d) bytes model evaluated with the step's U_W / U_E */
+} rae_step_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* replaces ReconstructInducer.__init__ + compile_function (OieInduction.py:28-101,118-155): sizes scratch, streams. */
+int rae_create(const rae_config* cfg, rae_engine** out);
+void rae_destroy(rae_engine* h);
+/* message of the last failing call on this handle (h may be NULL: message of the last failing rae_create) */
+const char* rae_last_error(const rae_engine* h);
+int rae_abi_version(void);
+
+/* ---- bindings ------------------------------------------------------------------------------------------- */
+/* theano.shared parameters (RelationClassifier.py:24-25, Bilinear.py:15-17, SelectionalPreferences.py:16-19,
+ * BilinearPlusSP.py:19-23).  Pointers a model does not use may be NULL (C for model C; C1,C2 for model A). */
+int rae_bind_params(rae_engine* h, float* W, float* Wb, float* A, float* Ab, float* C, float* C1, float* C2);
+/* AdaGrad accumulators, one per parameter, same shapes (Optimizers.py:12-15).  Ignored for SGD. */
+int rae_bind_accumulators(rae_engine* h, float* W, float* Wb, float* A, float* Ab, float* C, float* C1, float* C2);
+/* make_shared(DatasetSplit) (OieInduction.py:439-449; OieData.py:72-90): binary CSR (data implied 1.0) + args.
+ * For the train split this also builds the per-batch (feature -> examples) transposed index used by the W update. */
+int rae_bind_split(rae_engine* h, int32_t split_id, const int32_t* indptr, const int32_t* indices, int64_t n_rows,
+                   const int32_t* args1, const int32_t* args2, void* stream);
+/* the epoch's negative ids, row-major [S, n_cols] (NegativeExampleGenerator.py:24; OieInduction.py:183-184);
+ * batch b uses columns [b*B, (b+1)*B) (OieInduction.py:187-188) - read strided in place, no per-batch copy. */
+int rae_bind_epoch_negatives(rae_engine* h, const int32_t* neg1, const int32_t* neg2, int64_t n_cols);
+
+/* ---- func['train'] -------------------------------------------------------------------------------------- */
+/* device-resident form: rows [b*B,(b+1)*B) of the bound train split + bound epoch negatives.  cost_host may be NULL
+ * (fully asynchronous); otherwise the call synchronises the stream and stores the regularised batch cost. */
+int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* stream);
+/* drop-in form of func['train'](batch_index, neg1, neg2): neg1/neg2 are HOST int32[S,B] (what learn() passes,
+ * OieInduction.py:187-189); copies them to the device, runs the step, returns the cost (synchronous). */
+int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, const int32_t* neg2_host,
+                        double* cost_host, void* stream);
+/* fully explicit form for parity tests with injected indices: all DEVICE pointers; indptr has B+1 entries and may
+ * start at any offset into indices (indices is indexed by indptr values); neg_ld = row stride of neg1/neg2. */
+int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, const int32_t* args1,
+                            const int32_t* args2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                            double* cost_host, void* stream);
+
+/* ---- func['label_<split>'] ------------------------------------------------------------------------------ */
+/* labels = argmax of the scores, first max wins (RelationClassifier.py:45-47); probs = softmax.  Device outputs. */
+int rae_label(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels, float* probs, void* stream);
+/* same with HOST outputs (synchronous) */
+int rae_label_host(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels_host, float* probs_host,
+                   void* stream);
+
+/* ---- introspection (parity tests, bench) ---------------------------------------------------------------- */
+/* copy the last step's q(r|x) [B,K] into a device buffer */
+int rae_get_probs(rae_engine* h, float* dst, void* stream);
+/* copy the last step's dense gradient of one parameter (needs RAE_FLAG_DENSE_GRADS) into a device buffer of the
+ * parameter's shape: what T.grad(cost, params) (Optimizers.py:27) would have produced */
+int rae_get_dense_grad(rae_engine* h, int32_t param_id, float* dst, void* stream);
+/* device copy of the last step's sorted entity occurrence keys / permutation and segment starts (bit-exact layout
+ * checks against np.argsort(kind='stable') + np.unique).  Each dst may be NULL.  n_* receive the element counts. */
+int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted_occ, int32_t* seg_start,
+                            int64_t* n_occ, int64_t* n_seg, void* stream);
+int rae_get_step_stats(rae_engine* h, rae_step_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAE_H_ */

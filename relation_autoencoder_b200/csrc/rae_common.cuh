@@ -1,0 +1,46 @@
+// Shared device helpers for the relation-autoencoder kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rae {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// log(sigmoid(x)) = -softplus(-x), stable for both signs (Bilinear.py:38,47 after Theano's own rewrite)
+__device__ __forceinline__ float log_sigmoid(float x) {
+    return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf(float x) {
+    // 1/(1+exp(-x)) without overflow for large |x|
+    float e = expf(-fabsf(x));
+    float s = 1.f / (1.f + e);
+    return x >= 0.f ? s : e * s;
+}
+
+__device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }
+
+// AdaGrad row rule, Optimizers.py:29-32: acc' = acc + g^2 ; p' = p - lr*g/(sqrt(acc') + 1e-6)
+__device__ __forceinline__ void adagrad_apply(float& p, float& acc, float g, float lr) {
+    acc = fmaf(g, g, acc);
+    p = p - lr * g / (sqrtf(acc) + 1e-6f);
+}
+
+}  // namespace rae

@@ -1,0 +1,540 @@
+// C-ABI entry points (include/rae.h) and the per-step kernel schedule.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "rae_internal.h"
+
+namespace rae {
+
+static char g_create_err[512] = "";
+
+int fail(rae_engine* h, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char* dst = h ? h->err : g_create_err;
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+template <typename T>
+static int dev_alloc(rae_engine* h, T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(h, RAE_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return RAE_OK;
+}
+
+static int alloc_segwork(rae_engine* h, SegWork& w, int64_t cap, int key_bits) {
+    int rc;
+    if ((rc = dev_alloc(h, &w.keys, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.vals, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.keys_s, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.vals_s, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.flags, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.pos, cap))) return rc;
+    if ((rc = dev_alloc(h, &w.seg_start, cap + 1))) return rc;
+    if ((rc = dev_alloc(h, &w.n_seg, 1))) return rc;
+    w.capacity = cap;
+    w.key_bits = key_bits;
+    return RAE_OK;
+}
+
+static void free_segwork(SegWork& w) {
+    cudaFree(w.keys); cudaFree(w.vals); cudaFree(w.keys_s); cudaFree(w.vals_s);
+    cudaFree(w.flags); cudaFree(w.pos); cudaFree(w.seg_start); cudaFree(w.n_seg);
+    w = SegWork{};
+}
+
+static int bits_for(int64_t n) {
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+static int ensure_cub(rae_engine* h, int64_t n) {
+    size_t need = segwork_temp_bytes(n);
+    if (need > h->cub_bytes) {
+        if (h->cub_tmp) cudaFree(h->cub_tmp);
+        h->cub_tmp = nullptr;
+        cudaError_t e = cudaMalloc(&h->cub_tmp, need);
+        if (e != cudaSuccess) return fail(h, RAE_ENOMEM, "cudaMalloc(cub temp %zu) failed: %s", need, cudaGetErrorString(e));
+        h->cub_bytes = need;
+    }
+    return RAE_OK;
+}
+
+static int ensure_feat_capacity(rae_engine* h, int64_t nnz) {
+    if (nnz <= h->feat.capacity) return RAE_OK;
+    free_segwork(h->feat);
+    int rc = alloc_segwork(h, h->feat, nnz + nnz / 8 + 1024, bits_for(h->cfg.F));
+    if (rc) return rc;
+    return ensure_cub(h, h->feat.capacity);
+}
+
+static void free_feature_cache(FeatureCache& c) {
+    cudaFree(c.keys_s); cudaFree(c.vals_s); cudaFree(c.seg_start); cudaFree(c.n_seg);
+    delete[] c.batch_off; delete[] c.seg_off;
+    c = FeatureCache{};
+}
+
+// one training step on device-resident inputs.  nnz_hint < 0: unknown (explicit API reads indptr back once).
+static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t nnz, const int32_t* a1,
+                    const int32_t* a2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                    const uint32_t* f_keys_s, const uint32_t* f_vals_s, const int32_t* f_seg_start, const int32_t* f_n_seg,
+                    cudaStream_t st) {
+    int rc;
+    h->launches = 0;
+    const bool emit = h->debug_dense || h->dense_w;
+    // encoder forward: q, log q, entropy
+    if ((rc = launch_encoder_forward(h, indptr, indices, h->B, h->q, h->logq, h->sc + SC_ENT, nullptr, st))) return rc;
+    // entity occurrence keys -> stable sort -> segments (depends on the indices only)
+    const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
+    if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+    if ((rc = sort_and_segment(h, h->ent, n_occ, st))) return rc;
+    if (f_keys_s == nullptr) {
+        if ((rc = ensure_feat_capacity(h, nnz))) return rc;
+        if ((rc = build_feature_keys(h, indptr, indices, st))) return rc;
+        if ((rc = sort_and_segment(h, h->feat, nnz, st))) return rc;
+        f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s; f_seg_start = h->feat.seg_start; f_n_seg = h->feat.n_seg;
+    }
+    // decoder
+    if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
+    if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+    if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
+    if ((rc = launch_grad_dense_simt(h, st))) return rc;
+    if ((rc = launch_dense_finalize(h, st))) return rc;
+    // cost uses the pre-update parameters for the regulariser value
+    if ((rc = launch_cost(h, st))) return rc;
+    if (emit) {
+        if ((rc = launch_zero(h, h->gW_dense, sizeof(float) * (size_t)h->cfg.F * h->K, st))) return rc;
+    }
+    if (h->debug_dense) {
+        if ((rc = launch_zero(h, h->gA_dense, sizeof(float) * (size_t)h->cfg.N * h->d, st))) return rc;
+        if ((rc = launch_zero(h, h->gAb_dense, sizeof(float) * (size_t)h->cfg.N, st))) return rc;
+    }
+    // sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
+    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, h->ent.seg_start, h->ent.n_seg, n_occ, h->debug_dense, true, st))) return rc;
+    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, f_seg_start, f_n_seg, nnz, emit, !h->dense_w, st))) return rc;
+    if ((rc = launch_dense_apply(h, st))) return rc;
+    h->stats.nnz = nnz;
+    h->stats.entity_occ = n_occ;
+    h->stats.kernel_launches = h->launches;
+    h->stats.tensor_path = 0;
+    h->stats.unique_w_rows = -1;
+    h->stats.unique_e_rows = -1;
+    h->last_f_n_seg = f_n_seg;
+    return RAE_OK;
+}
+
+static int finish_cost(rae_engine* h, double* cost_host, cudaStream_t st) {
+    if (cost_host == nullptr) return RAE_OK;
+    RAE_CUDA(h, cudaMemcpyAsync(h->cost_pinned, h->cost_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    *cost_host = *h->cost_pinned;
+    return RAE_OK;
+}
+
+static int check_ready(rae_engine* h, bool need_train_split, bool need_neg) {
+    if (!h) return RAE_EINVAL;
+    if (!h->params_bound) return fail(h, RAE_ENOTBOUND, "parameters are not bound (rae_bind_params)");
+    if (h->adagrad && !h->acc_bound) return fail(h, RAE_ENOTBOUND, "AdaGrad accumulators are not bound (rae_bind_accumulators)");
+    if (need_train_split && !h->split[RAE_SPLIT_TRAIN].bound) return fail(h, RAE_ENOTBOUND, "train split is not bound (rae_bind_split)");
+    if (need_neg && (h->neg1 == nullptr || h->neg2 == nullptr)) return fail(h, RAE_ENOTBOUND, "epoch negatives are not bound (rae_bind_epoch_negatives)");
+    return RAE_OK;
+}
+
+int build_feature_cache(rae_engine* h, cudaStream_t st) {
+    SplitBinding& sp = h->split[RAE_SPLIT_TRAIN];
+    free_feature_cache(h->fcache);
+    const int64_t nb = sp.n_rows / h->B;     // trailing partial batch dropped (OieInduction.py:96-98)
+    if (nb == 0) return RAE_OK;
+    std::vector<int32_t> ip((size_t)nb + 1);
+    RAE_CUDA(h, cudaMemcpy2DAsync(ip.data(), sizeof(int32_t), sp.indptr, sizeof(int32_t) * (size_t)h->B, sizeof(int32_t),
+                                  (size_t)nb + 1, cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    FeatureCache& c = h->fcache;
+    c.n_batches = nb;
+    c.batch_off = new int64_t[nb + 1];
+    c.seg_off = new int64_t[nb + 1];
+    int64_t mx = 0;
+    for (int64_t b = 0; b <= nb; ++b) {
+        c.batch_off[b] = ip[b] - ip[0];
+        c.seg_off[b] = c.batch_off[b] + b;
+        if (b > 0 && ip[b] - ip[b - 1] > mx) mx = ip[b] - ip[b - 1];
+    }
+    sp.max_batch_nnz = mx;
+    const int64_t used = c.batch_off[nb];
+    int rc;
+    if ((rc = dev_alloc(h, &c.keys_s, used))) return rc;
+    if ((rc = dev_alloc(h, &c.vals_s, used))) return rc;
+    if ((rc = dev_alloc(h, &c.seg_start, used + nb + 1))) return rc;
+    if ((rc = dev_alloc(h, &c.n_seg, nb))) return rc;
+    if ((rc = ensure_feat_capacity(h, mx))) return rc;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t n = c.batch_off[b + 1] - c.batch_off[b];
+        const int32_t* ipb = sp.indptr + b * h->B;
+        if ((rc = build_feature_keys(h, ipb, sp.indices, st))) return rc;
+        if ((rc = sort_and_segment(h, h->feat, n, st))) return rc;
+        RAE_CUDA(h, cudaMemcpyAsync(c.keys_s + c.batch_off[b], h->feat.keys_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        RAE_CUDA(h, cudaMemcpyAsync(c.vals_s + c.batch_off[b], h->feat.vals_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        RAE_CUDA(h, cudaMemcpyAsync(c.seg_start + c.seg_off[b], h->feat.seg_start, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToDevice, st));
+        RAE_CUDA(h, cudaMemcpyAsync(c.n_seg + b, h->feat.n_seg, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    c.valid = true;
+    return RAE_OK;
+}
+
+}  // namespace rae
+
+using namespace rae;
+
+extern "C" {
+
+int rae_abi_version(void) { return RAE_ABI_VERSION; }
+
+const char* rae_last_error(const rae_engine* h) { return h ? h->err : g_create_err; }
+
+int rae_create(const rae_config* cfg, rae_engine** out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out) return fail(nullptr, RAE_EINVAL, "rae_create: null argument");
+    if (cfg->abi_version != RAE_ABI_VERSION) return fail(nullptr, RAE_EINVAL, "rae_create: ABI version %d != %d", cfg->abi_version, RAE_ABI_VERSION);
+    if (cfg->model < RAE_MODEL_A || cfg->model > RAE_MODEL_AC) return fail(nullptr, RAE_EINVAL, "rae_create: unknown model %d", cfg->model);
+    if (cfg->optimizer != RAE_OPT_ADAGRAD && cfg->optimizer != RAE_OPT_SGD)
+        return fail(nullptr, RAE_EINVAL, "Optimizer '%d' not implemented", cfg->optimizer);   // OieInduction.py:269
+    if (cfg->K < 1 || cfg->K > 1024 || cfg->d < 1 || cfg->d > 256 || cfg->S < 0 || cfg->B < 1 || cfg->F < 1 || cfg->N < 1)
+        return fail(nullptr, RAE_EINVAL, "rae_create: unsupported sizes K=%d d=%d S=%d B=%d F=%lld N=%lld (need 1<=K<=1024, 1<=d<=256)",
+                    cfg->K, cfg->d, cfg->S, cfg->B, (long long)cfg->F, (long long)cfg->N);
+    if ((int64_t)(2 + 2 * cfg->S) * cfg->B >= ((int64_t)1 << 31)) return fail(nullptr, RAE_EINVAL, "rae_create: (2+2S)*B too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RAE_ENODEVICE, "no CUDA device available: librae has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RAE_EINVAL, "rae_create: device %d out of range (%d devices)", cfg->device, ndev);
+    rae_engine* h = new (std::nothrow) rae_engine();
+    if (!h) return fail(nullptr, RAE_ENOMEM, "out of host memory");
+    memset((void*)h, 0, sizeof(*h));
+    h->ent = SegWork{}; h->feat = SegWork{}; h->fcache = FeatureCache{};
+    for (int i = 0; i < RAE_NUM_SPLITS; ++i) h->split[i] = SplitBinding{};
+    h->cfg = *cfg;
+    h->K = cfg->K; h->d = cfg->d; h->S = cfg->S; h->B = cfg->B;
+    h->dp = (cfg->d + 3) & ~3;
+    h->hasM = cfg->model != RAE_MODEL_C;
+    h->hasSP = cfg->model != RAE_MODEL_A;
+    h->quirk = cfg->model == RAE_MODEL_C && !(cfg->flags & RAE_FLAG_FIX_SP_QUIRK);
+    h->adagrad = cfg->optimizer == RAE_OPT_ADAGRAD;
+    h->dense_w = (cfg->l1 != 0.0 || cfg->l2 != 0.0);
+    h->debug_dense = (cfg->flags & RAE_FLAG_DENSE_GRADS) != 0;
+    h->Z = cfg->z_total > 0 ? (double)cfg->z_total : (double)(4.0 * cfg->B + 2.0 * cfg->B * cfg->S);
+#define RAE_CREATE_CUDA(expr)                                                                                  \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            fail(nullptr, RAE_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                          \
+            rae_destroy(h);                                                                                    \
+            return RAE_ECUDA;                                                                                  \
+        }                                                                                                      \
+    } while (0)
+#define RAE_CREATE_RC(expr)                                                                                    \
+    do {                                                                                                       \
+        int _rc = (expr);                                                                                      \
+        if (_rc) {                                                                                             \
+            strncpy(g_create_err, h->err, sizeof(g_create_err) - 1);                                           \
+            rae_destroy(h);                                                                                    \
+            return _rc;                                                                                        \
+        }                                                                                                      \
+    } while (0)
+    RAE_CREATE_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    RAE_CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        fail(nullptr, RAE_ENODEVICE, "device %d is sm_%d%d: librae is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        rae_destroy(h);
+        return RAE_ENODEVICE;
+    }
+    char why[256];
+    if (!simt_supported(h, why, sizeof(why))) {
+        fail(nullptr, RAE_EINVAL, "%s", why);
+        rae_destroy(h);
+        return RAE_EINVAL;
+    }
+    const size_t BK = (size_t)h->B * h->K;
+    RAE_CREATE_RC(dev_alloc(h, &h->q, BK));
+    RAE_CREATE_RC(dev_alloc(h, &h->logq, BK));
+    RAE_CREATE_RC(dev_alloc(h, &h->dz, BK));
+    RAE_CREATE_RC(dev_alloc(h, &h->ev, (size_t)h->B * E_NV * h->dp));
+    RAE_CREATE_RC(dev_alloc(h, &h->sc, (size_t)h->B * SC_N));
+    RAE_CREATE_RC(dev_alloc(h, &h->gn1, (size_t)h->S * h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->gn2, (size_t)h->S * h->B));
+    RAE_CREATE_CUDA(cudaMemset(h->ev, 0, sizeof(float) * (size_t)h->B * E_NV * h->dp));
+    RAE_CREATE_CUDA(cudaMemset(h->sc, 0, sizeof(float) * (size_t)h->B * SC_N));
+    h->n_loss_part = (h->B + 7) / 8;
+    RAE_CREATE_RC(dev_alloc(h, &h->loss_part, (size_t)h->n_loss_part));
+    h->n_reg_part = 64 * 4;
+    RAE_CREATE_RC(dev_alloc(h, &h->reg_part, (size_t)2 * h->n_reg_part));
+    RAE_CREATE_RC(dev_alloc(h, &h->cost_dev, 1));
+    RAE_CREATE_CUDA(cudaMallocHost((void**)&h->cost_pinned, sizeof(double)));
+    h->n_dz_part = h->B;   // upper bound on CTAs of the backward kernel (>= 8 examples per CTA)
+    RAE_CREATE_RC(dev_alloc(h, &h->dzsum_part, (size_t)h->n_dz_part * h->K));
+    const int64_t dd = h->hasM ? (int64_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (int64_t)h->d * h->K : 0;
+    h->off_gC = 0; h->off_gC1 = dd; h->off_gC2 = dd + dk; h->off_gWb = dd + 2 * dk; h->n_dense = dd + 2 * dk + h->K;
+    RAE_CREATE_RC(dev_alloc(h, &h->dense_grad, (size_t)h->n_dense));
+    {
+        const int nunits = (h->hasM ? h->d : 0) + (h->hasSP ? 2 : 0);
+        int ns = nunits > 0 ? (2 * h->num_sms + nunits - 1) / nunits : 1;
+        const int max_by_batch = (h->B + 63) / 64;
+        if (ns > max_by_batch) ns = max_by_batch;
+        if (ns < 1) ns = 1;
+        h->gC_nsplit = ns;
+        RAE_CREATE_RC(dev_alloc(h, &h->gC_part, (size_t)ns * (size_t)(dd + 2 * dk)));
+    }
+    if (h->dense_w || h->debug_dense) RAE_CREATE_RC(dev_alloc(h, &h->gW_dense, (size_t)cfg->F * h->K));
+    if (h->debug_dense) {
+        RAE_CREATE_RC(dev_alloc(h, &h->gA_dense, (size_t)cfg->N * h->d));
+        RAE_CREATE_RC(dev_alloc(h, &h->gAb_dense, (size_t)cfg->N));
+    }
+    const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
+    RAE_CREATE_RC(alloc_segwork(h, h->ent, n_occ, bits_for(cfg->N)));
+    RAE_CREATE_RC(ensure_cub(h, n_occ));
+    RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
+    RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->label_dev, (size_t)h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->prob_dev, BK));
+#undef RAE_CREATE_CUDA
+#undef RAE_CREATE_RC
+    *out = h;
+    return RAE_OK;
+}
+
+void rae_destroy(rae_engine* h) {
+    if (!h) return;
+    cudaFree(h->q); cudaFree(h->logq); cudaFree(h->dz); cudaFree(h->ev); cudaFree(h->sc); cudaFree(h->gn1); cudaFree(h->gn2);
+    cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->dense_grad);
+    cudaFree(h->gC_part); cudaFree(h->gW_dense); cudaFree(h->gA_dense); cudaFree(h->gAb_dense); cudaFree(h->cub_tmp);
+    cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
+    if (h->cost_pinned) cudaFreeHost(h->cost_pinned);
+    if (h->pinned_neg) cudaFreeHost(h->pinned_neg);
+    free_segwork(h->ent);
+    free_segwork(h->feat);
+    free_feature_cache(h->fcache);
+    cudaGetLastError();
+    delete h;
+}
+
+int rae_bind_params(rae_engine* h, float* W, float* Wb, float* A, float* Ab, float* C, float* C1, float* C2) {
+    if (!h) return RAE_EINVAL;
+    if (!W || !Wb || !A || !Ab) return fail(h, RAE_EINVAL, "rae_bind_params: W, Wb, A, Ab must be non-null");
+    if (h->hasM && !C) return fail(h, RAE_EINVAL, "rae_bind_params: this model needs C (R) [d,d,K]");
+    if (h->hasSP && (!C1 || !C2)) return fail(h, RAE_EINVAL, "rae_bind_params: this model needs C1 and C2 [d,K]");
+    float* v[RAE_NUM_PARAMS] = {W, Wb, A, Ab, C, C1, C2};
+    for (int i = 0; i < RAE_NUM_PARAMS; ++i) h->P[i] = v[i];
+    h->params_bound = true;
+    return RAE_OK;
+}
+
+int rae_bind_accumulators(rae_engine* h, float* W, float* Wb, float* A, float* Ab, float* C, float* C1, float* C2) {
+    if (!h) return RAE_EINVAL;
+    if (!W || !Wb || !A || !Ab) return fail(h, RAE_EINVAL, "rae_bind_accumulators: W, Wb, A, Ab must be non-null");
+    if (h->hasM && !C) return fail(h, RAE_EINVAL, "rae_bind_accumulators: this model needs C (R) [d,d,K]");
+    if (h->hasSP && (!C1 || !C2)) return fail(h, RAE_EINVAL, "rae_bind_accumulators: this model needs C1 and C2 [d,K]");
+    float* v[RAE_NUM_PARAMS] = {W, Wb, A, Ab, C, C1, C2};
+    for (int i = 0; i < RAE_NUM_PARAMS; ++i) h->ACC[i] = v[i];
+    h->acc_bound = true;
+    return RAE_OK;
+}
+
+int rae_bind_split(rae_engine* h, int32_t split_id, const int32_t* indptr, const int32_t* indices, int64_t n_rows,
+                   const int32_t* args1, const int32_t* args2, void* stream) {
+    if (!h) return RAE_EINVAL;
+    if (split_id < 0 || split_id >= RAE_NUM_SPLITS) return fail(h, RAE_EINVAL, "rae_bind_split: bad split id %d", split_id);
+    if (!indptr || !indices || n_rows < 0) return fail(h, RAE_EINVAL, "rae_bind_split: null CSR");
+    if (split_id == RAE_SPLIT_TRAIN && (!args1 || !args2)) return fail(h, RAE_EINVAL, "rae_bind_split: the train split needs args1/args2");
+    cudaStream_t st = (cudaStream_t)stream;
+    SplitBinding& sp = h->split[split_id];
+    sp.indptr = indptr; sp.indices = indices; sp.a1 = args1; sp.a2 = args2; sp.n_rows = n_rows;
+    int32_t ends[2] = {0, 0};
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[0], indptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[1], indptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    sp.nnz = (int64_t)ends[1] - ends[0];
+    sp.bound = true;
+    if (split_id == RAE_SPLIT_TRAIN) {
+        if (!(h->cfg.flags & RAE_FLAG_NO_FEATURE_CACHE)) {
+            int rc = build_feature_cache(h, st);
+            if (rc) return rc;
+        } else {
+            free_feature_cache(h->fcache);
+        }
+    }
+    return RAE_OK;
+}
+
+int rae_bind_epoch_negatives(rae_engine* h, const int32_t* neg1, const int32_t* neg2, int64_t n_cols) {
+    if (!h) return RAE_EINVAL;
+    if ((!neg1 || !neg2) && h->S > 0) return fail(h, RAE_EINVAL, "rae_bind_epoch_negatives: null pointer");
+    h->neg1 = neg1; h->neg2 = neg2; h->neg_cols = n_cols;
+    return RAE_OK;
+}
+
+static int train_batch(rae_engine* h, int64_t batch_index, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                       cudaStream_t st) {
+    SplitBinding& sp = h->split[RAE_SPLIT_TRAIN];
+    const int64_t nb = sp.n_rows / h->B;
+    if (batch_index < 0 || batch_index >= nb) return fail(h, RAE_EINVAL, "batch_index %lld out of range [0,%lld)", (long long)batch_index, (long long)nb);
+    const int64_t r0 = batch_index * h->B;
+    if (h->fcache.valid) {
+        const FeatureCache& c = h->fcache;
+        const int64_t nnz = c.batch_off[batch_index + 1] - c.batch_off[batch_index];
+        return run_step(h, sp.indptr + r0, sp.indices, nnz, sp.a1 + r0, sp.a2 + r0, neg1, neg2, neg_ld,
+                        c.keys_s + c.batch_off[batch_index], c.vals_s + c.batch_off[batch_index],
+                        c.seg_start + c.seg_off[batch_index], c.n_seg + batch_index, st);
+    }
+    int32_t ends[2];
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[0], sp.indptr + r0, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[1], sp.indptr + r0 + h->B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    return run_step(h, sp.indptr + r0, sp.indices, (int64_t)ends[1] - ends[0], sp.a1 + r0, sp.a2 + r0, neg1, neg2, neg_ld,
+                    nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* stream) {
+    int rc = check_ready(h, true, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((batch_index + 1) * h->B > h->neg_cols) return fail(h, RAE_EINVAL, "batch %lld exceeds the bound negatives (%lld columns)", (long long)batch_index, (long long)h->neg_cols);
+    const int64_t c0 = batch_index * h->B;
+    if ((rc = train_batch(h, batch_index, h->neg1 + c0, h->neg2 + c0, h->neg_cols, st))) return rc;
+    return finish_cost(h, cost_host, st);
+}
+
+int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, const int32_t* neg2_host,
+                        double* cost_host, void* stream) {
+    int rc = check_ready(h, true, false);
+    if (rc) return rc;
+    if ((!neg1_host || !neg2_host) && h->S > 0) return fail(h, RAE_EINVAL, "rae_train_step_host: null negatives");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->S * h->B;
+    // the pinned staging buffer is reused: wait until the previous step's copy has been consumed
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    memcpy(h->pinned_neg, neg1_host, n * sizeof(int32_t));
+    memcpy(h->pinned_neg + n, neg2_host, n * sizeof(int32_t));
+    RAE_CUDA(h, cudaMemcpyAsync(h->stage_neg1, h->pinned_neg, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    RAE_CUDA(h, cudaMemcpyAsync(h->stage_neg2, h->pinned_neg + n, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if ((rc = train_batch(h, batch_index, h->stage_neg1, h->stage_neg2, h->B, st))) return rc;
+    return finish_cost(h, cost_host, st);
+}
+
+int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, const int32_t* args1,
+                            const int32_t* args2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                            double* cost_host, void* stream) {
+    int rc = check_ready(h, false, false);
+    if (rc) return rc;
+    if (!indptr || !indices || !args1 || !args2) return fail(h, RAE_EINVAL, "rae_train_step_explicit: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t ends[2];
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[0], indptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaMemcpyAsync(&ends[1], indptr + h->B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    if ((rc = run_step(h, indptr, indices, (int64_t)ends[1] - ends[0], args1, args2, neg1, neg2, neg_ld, nullptr, nullptr,
+                       nullptr, nullptr, st)))
+        return rc;
+    return finish_cost(h, cost_host, st);
+}
+
+int rae_label(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels, float* probs, void* stream) {
+    if (!h) return RAE_EINVAL;
+    if (!h->params_bound) return fail(h, RAE_ENOTBOUND, "parameters are not bound (rae_bind_params)");
+    if (split_id < 0 || split_id >= RAE_NUM_SPLITS || !h->split[split_id].bound) return fail(h, RAE_ENOTBOUND, "split %d is not bound", split_id);
+    if (!labels || !probs) return fail(h, RAE_EINVAL, "rae_label: null output");
+    SplitBinding& sp = h->split[split_id];
+    const int64_t nb = sp.n_rows / h->B;
+    if (batch_index < 0 || batch_index >= nb) return fail(h, RAE_EINVAL, "batch_index %lld out of range [0,%lld)", (long long)batch_index, (long long)nb);
+    h->launches = 0;
+    return launch_encoder_forward(h, sp.indptr + batch_index * h->B, sp.indices, h->B, probs, nullptr, nullptr, labels,
+                                  (cudaStream_t)stream);
+}
+
+int rae_label_host(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels_host, float* probs_host,
+                   void* stream) {
+    if (!h) return RAE_EINVAL;
+    if (!labels_host || !probs_host) return fail(h, RAE_EINVAL, "rae_label_host: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rae_label(h, split_id, batch_index, h->label_dev, h->prob_dev, stream);
+    if (rc) return rc;
+    RAE_CUDA(h, cudaMemcpyAsync(labels_host, h->label_dev, sizeof(int64_t) * h->B, cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaMemcpyAsync(probs_host, h->prob_dev, sizeof(float) * (size_t)h->B * h->K, cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    return RAE_OK;
+}
+
+int rae_get_probs(rae_engine* h, float* dst, void* stream) {
+    if (!h || !dst) return RAE_EINVAL;
+    RAE_CUDA(h, cudaMemcpyAsync(dst, h->q, sizeof(float) * (size_t)h->B * h->K, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return RAE_OK;
+}
+
+int rae_get_dense_grad(rae_engine* h, int32_t param_id, float* dst, void* stream) {
+    if (!h || !dst) return RAE_EINVAL;
+    if (!h->debug_dense) return fail(h, RAE_EINVAL, "rae_get_dense_grad needs RAE_FLAG_DENSE_GRADS");
+    const float* src = nullptr;
+    size_t n = 0;
+    switch (param_id) {
+        case RAE_P_W: src = h->gW_dense; n = (size_t)h->cfg.F * h->K; break;
+        case RAE_P_WB: src = h->dense_grad + h->off_gWb; n = (size_t)h->K; break;
+        case RAE_P_A: src = h->gA_dense; n = (size_t)h->cfg.N * h->d; break;
+        case RAE_P_AB: src = h->gAb_dense; n = (size_t)h->cfg.N; break;
+        case RAE_P_C: if (h->hasM) { src = h->dense_grad + h->off_gC; n = (size_t)h->d * h->d * h->K; } break;
+        case RAE_P_C1: if (h->hasSP) { src = h->dense_grad + h->off_gC1; n = (size_t)h->d * h->K; } break;
+        case RAE_P_C2: if (h->hasSP) { src = h->dense_grad + h->off_gC2; n = (size_t)h->d * h->K; } break;
+        default: break;
+    }
+    if (!src) return fail(h, RAE_EINVAL, "rae_get_dense_grad: parameter %d is not part of this model", param_id);
+    RAE_CUDA(h, cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return RAE_OK;
+}
+
+int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted_occ, int32_t* seg_start, int64_t* n_occ,
+                            int64_t* n_seg, void* stream) {
+    if (!h) return RAE_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)(2 + 2 * h->S) * h->B;
+    int32_t ns = 0;
+    RAE_CUDA(h, cudaMemcpyAsync(&ns, h->ent.n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RAE_CUDA(h, cudaStreamSynchronize(st));
+    if (sorted_rows) RAE_CUDA(h, cudaMemcpyAsync(sorted_rows, h->ent.keys_s, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+    if (sorted_occ) RAE_CUDA(h, cudaMemcpyAsync(sorted_occ, h->ent.vals_s, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+    if (seg_start) RAE_CUDA(h, cudaMemcpyAsync(seg_start, h->ent.seg_start, sizeof(int32_t) * ((size_t)ns + 1), cudaMemcpyDeviceToDevice, st));
+    if (n_occ) *n_occ = n;
+    if (n_seg) *n_seg = ns;
+    return RAE_OK;
+}
+
+int rae_get_step_stats(rae_engine* h, rae_step_stats* out) {
+    if (!h || !out) return RAE_EINVAL;
+    // unique-row counts live on the device; reading them synchronises, so it happens only here
+    int32_t ue = 0, uw = 0;
+    cudaMemcpy(&ue, h->ent.n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (h->last_f_n_seg) cudaMemcpy(&uw, h->last_f_n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    h->stats.unique_e_rows = ue;
+    h->stats.unique_w_rows = uw;
+    // fp32 params + fp32 accumulators, int32 ids
+    const double rmw = h->adagrad ? 16.0 : 8.0;
+    const double B = h->B, S = h->S, K = h->K, d = h->d, nnz = (double)h->stats.nnz;
+    const double p_dense = (h->hasM ? d * d * K : 0.0) + (h->hasSP ? 2.0 * d * K : 0.0) + K;
+    const double gath = h->hasM ? 4.0 * (2 + 2 * S) * B * (d + 1) : 4.0 * ((1 + 2 * S) * B * (d + 1) + B);
+    h->stats.algorithmic_bytes = 4.0 * nnz * K + rmw * uw * K + gath + rmw * ue * (d + 1) + (4.0 + rmw) * p_dense +
+                                 4.0 * (nnz + 2 * B + 2 * S * B);
+    *out = h->stats;
+    return RAE_OK;
+}
+
+}  // extern "C"

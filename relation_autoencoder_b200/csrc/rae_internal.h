@@ -1,0 +1,156 @@
+// Internal engine state and kernel-launcher declarations (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rae.h"
+
+namespace rae {
+
+// per-example vector slots in ev[b][slot][dp]
+enum EvSlot {
+    E_L = 0,    // A[a1]
+    E_R = 1,    // A[a2]  (A[a1] for model C with the reference's quirk, SelectionalPreferences.py:35)
+    E_V1 = 2,   // fwd: v = M R ; after scoring: v + c1   (gradient direction of neg1 rows)
+    E_V2 = 3,   // fwd: w = M^T L ; after scoring: w + c2 (gradient direction of neg2 rows)
+    E_C1 = 4,   // c1 = C1 q
+    E_C2 = 5,   // c2 = C2 q
+    E_A = 6,    // a = gp L + X1
+    E_CV = 7,   // c = gp R + Y2
+    E_Y2 = 8,   // Y2 = sum_s gn2_s y_s
+    E_GA1 = 9,  // d cost / d L
+    E_GA2 = 10, // d cost / d R
+    E_NV = 11
+};
+// per-example scalars sc[b][SC_N]
+enum ScSlot { SC_GU1 = 0, SC_GU2 = 1, SC_GP = 2, SC_G1 = 3, SC_G2 = 4, SC_ENT = 5, SC_N = 8 };
+
+struct SplitBinding {
+    const int32_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const int32_t* a1 = nullptr;
+    const int32_t* a2 = nullptr;
+    int64_t n_rows = 0;
+    int64_t nnz = 0;
+    int64_t max_batch_nnz = 0;
+    bool bound = false;
+};
+
+// sorted-occurrence workspace (one for entity rows, one for feature rows)
+struct SegWork {
+    uint32_t* keys = nullptr;      // unsorted keys (row ids)
+    uint32_t* vals = nullptr;      // unsorted values (occurrence ids)
+    uint32_t* keys_s = nullptr;    // sorted keys
+    uint32_t* vals_s = nullptr;    // sorted values (stable)
+    int32_t* flags = nullptr;      // segment-head flags
+    int32_t* pos = nullptr;        // exclusive scan of flags
+    int32_t* seg_start = nullptr;  // [n_seg + 1]
+    int32_t* n_seg = nullptr;      // device scalar
+    int64_t capacity = 0;
+    int key_bits = 32;
+};
+
+// feature-side transposed index cached for every batch of the train split
+struct FeatureCache {
+    uint32_t* keys_s = nullptr;   // [nnz_used] feature ids, sorted within each batch
+    uint32_t* vals_s = nullptr;   // [nnz_used] example index within the batch
+    int32_t* seg_start = nullptr; // [nnz_used + n_batches] segment starts, batch-local positions
+    int32_t* n_seg = nullptr;     // [n_batches]
+    int64_t* batch_off = nullptr; // host copy: offset of each batch into keys_s / vals_s (= indptr[b*B])
+    int64_t* seg_off = nullptr;   // host: offset of each batch into seg_start
+    int64_t n_batches = 0;
+    bool valid = false;
+};
+
+}  // namespace rae
+
+struct rae_engine {
+    rae_config cfg;
+    int K, d, S, B;
+    int dp;          // d rounded up to a multiple of 4 (row stride of ev)
+    bool hasM, hasSP, quirk, adagrad, dense_w, debug_dense;
+    double Z;        // denominator of the mean
+    float* P[RAE_NUM_PARAMS];
+    float* ACC[RAE_NUM_PARAMS];
+    bool params_bound, acc_bound;
+    rae::SplitBinding split[RAE_NUM_SPLITS];
+    const int32_t* neg1;
+    const int32_t* neg2;
+    int64_t neg_cols;
+
+    // scratch (device)
+    float* q;        // [B,K]
+    float* logq;     // [B,K]
+    float* dz;       // [B,K]
+    float* ev;       // [B,E_NV,dp]
+    float* sc;       // [B,SC_N]
+    float* gn1;      // [S,B]
+    float* gn2;      // [S,B]
+    double* loss_part; int n_loss_part;
+    double* reg_part;  int n_reg_part;
+    double* cost_dev;  // [1]
+    double* cost_pinned;
+    float* dzsum_part; int n_dz_part; int dz_part_used;   // [n_dz_part, K]; rows written by the last backward
+    float* dense_grad;  // flat [C | C1 | C2 | Wb]
+    int64_t off_gC, off_gC1, off_gC2, off_gWb, n_dense;
+    float* gC_part; int gC_nsplit;       // [nsplit, units*d*K]
+    // debug / regularised dense gradients of the sparse tables
+    float* gW_dense; float* gA_dense; float* gAb_dense;
+    rae::SegWork ent, feat;
+    rae::FeatureCache fcache;
+    void* cub_tmp; size_t cub_bytes;
+    // explicit-step staging
+    int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
+    int32_t* pinned_neg;                         // host pinned [2,S,B]
+    int64_t* label_dev; float* prob_dev;         // label_host staging
+    // bookkeeping
+    rae_step_stats stats;
+    const int32_t* last_f_n_seg;   // device scalar: unique W rows of the last step
+    int launches;
+    int num_sms;
+    int max_smem_optin;
+    char err[512];
+};
+
+namespace rae {
+
+// ---- error helpers ----
+int fail(rae_engine* h, int code, const char* fmt, ...);
+#define RAE_CUDA(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return rae::fail((h), RAE_ECUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                             cudaGetErrorString(_e));                                              \
+    } while (0)
+
+// ---- encoder (rae_encoder.cu) ----
+int launch_encoder_forward(rae_engine* h, const int32_t* indptr, const int32_t* indices, int B, float* q, float* logq,
+                           float* sc_ent /* sc + SC_ENT, stride SC_N, may be null */, int64_t* labels, cudaStream_t st);
+
+// ---- decoder, SIMT contraction (rae_decoder_simt.cu) ----
+int simt_supported(const rae_engine* h, char* why, size_t n);
+int launch_bilinear_forward_simt(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);
+int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
+                 int64_t neg_ld, cudaStream_t st);
+int launch_bilinear_backward_simt(rae_engine* h, cudaStream_t st);
+int launch_grad_dense_simt(rae_engine* h, cudaStream_t st);
+
+// ---- sort / segment / updates (rae_update.cu) ----
+size_t segwork_temp_bytes(int64_t n);
+int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
+                      int64_t neg_ld, cudaStream_t st);
+int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indices, cudaStream_t st);
+int sort_and_segment(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st);
+int build_feature_cache(rae_engine* h, cudaStream_t st);
+int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, const int32_t* seg_start,
+                         const int32_t* n_seg, int64_t n_occ, bool emit_dense, bool apply, cudaStream_t st);
+int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, const int32_t* seg_start,
+                    const int32_t* n_seg, int64_t nnz, bool emit_dense, bool apply, cudaStream_t st);
+int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
+int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
+int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser
+int launch_zero(rae_engine* h, void* p, size_t bytes, cudaStream_t st);
+
+}  // namespace rae
