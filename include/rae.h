@@ -154,6 +154,15 @@ int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted
                             int64_t* n_occ, int64_t* n_seg, void* stream);
 int rae_get_step_stats(rae_engine* h, rae_step_stats* out);
 
+/* per-phase device timing of a step (CUDA events on the step's stream; bench.py's roofline leg).  Phases:
+ * 0 encoder_forward 1 entity_sort 2 feature_sort 3 decoder_forward 4 score 5 decoder_backward 6 grad_dense 7 cost
+ * 8 entity_update 9 w_update 10 dense_apply.  Profiling adds event records between kernels: never on for a timed run. */
+#define RAE_NUM_PHASES 11
+int rae_set_profiling(rae_engine* h, int32_t on);
+/* milliseconds of each phase of the last profiled step (synchronises); ms must hold RAE_NUM_PHASES floats */
+int rae_get_phase_times(rae_engine* h, float* ms);
+const char* rae_phase_name(int32_t phase);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,38 +77,47 @@ static int ensure_feat_capacity(rae_engine* h, int64_t nnz) {
 }
 
 static void free_feature_cache(FeatureCache& c) {
-    cudaFree(c.keys_s); cudaFree(c.vals_s); cudaFree(c.seg_start); cudaFree(c.n_seg);
-    delete[] c.batch_off; delete[] c.seg_off;
+    cudaFree(c.keys_s); cudaFree(c.vals_s);
+    delete[] c.batch_off;
     c = FeatureCache{};
 }
 
 // one training step on device-resident inputs.  nnz_hint < 0: unknown (explicit API reads indptr back once).
 static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t nnz, const int32_t* a1,
                     const int32_t* a2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
-                    const uint32_t* f_keys_s, const uint32_t* f_vals_s, const int32_t* f_seg_start, const int32_t* f_n_seg,
-                    cudaStream_t st) {
+                    const uint32_t* f_keys_s, const uint32_t* f_vals_s, cudaStream_t st) {
     int rc;
     h->launches = 0;
     const bool emit = h->debug_dense || h->dense_w;
-    // encoder forward: q, log q, entropy
+    int phase = 0;
+#define RAE_PHASE()                                                                    \
+    do {                                                                               \
+        if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_phase[phase], st));        \
+        ++phase;                                                                       \
+    } while (0)
+    RAE_PHASE();   // 0 encoder forward: q, log q, entropy
     if ((rc = launch_encoder_forward(h, indptr, indices, h->B, h->q, h->logq, h->sc + SC_ENT, nullptr, st))) return rc;
-    // entity occurrence keys -> stable sort -> segments (depends on the indices only)
+    RAE_PHASE();   // 1 entity occurrence keys -> stable sort -> segments (depends on the indices only)
     const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
     if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
-    if ((rc = sort_and_segment(h, h->ent, n_occ, st))) return rc;
+    if ((rc = sort_pairs(h, h->ent, n_occ, st))) return rc;
+    RAE_PHASE();   // 2 feature sort (skipped when the per-batch transposed index was cached at bind time)
     if (f_keys_s == nullptr) {
         if ((rc = ensure_feat_capacity(h, nnz))) return rc;
         if ((rc = build_feature_keys(h, indptr, indices, st))) return rc;
-        if ((rc = sort_and_segment(h, h->feat, nnz, st))) return rc;
-        f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s; f_seg_start = h->feat.seg_start; f_n_seg = h->feat.n_seg;
+        if ((rc = sort_pairs(h, h->feat, nnz, st))) return rc;
+        f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s;
     }
-    // decoder
+    RAE_PHASE();   // 3 decoder forward
     if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
+    RAE_PHASE();   // 4 scoring / loss / d cost / d score
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+    RAE_PHASE();   // 5 decoder backward
     if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
+    RAE_PHASE();   // 6 dense-parameter gradients
     if ((rc = launch_grad_dense_simt(h, st))) return rc;
     if ((rc = launch_dense_finalize(h, st))) return rc;
-    // cost uses the pre-update parameters for the regulariser value
+    RAE_PHASE();   // 7 cost (uses the pre-update parameters for the regulariser value)
     if ((rc = launch_cost(h, st))) return rc;
     if (emit) {
         if ((rc = launch_zero(h, h->gW_dense, sizeof(float) * (size_t)h->cfg.F * h->K, st))) return rc;
@@ -117,17 +126,22 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = launch_zero(h, h->gA_dense, sizeof(float) * (size_t)h->cfg.N * h->d, st))) return rc;
         if ((rc = launch_zero(h, h->gAb_dense, sizeof(float) * (size_t)h->cfg.N, st))) return rc;
     }
-    // sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
-    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, h->ent.seg_start, h->ent.n_seg, n_occ, h->debug_dense, true, st))) return rc;
-    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, f_seg_start, f_n_seg, nnz, emit, !h->dense_w, st))) return rc;
+    RAE_PHASE();   // 8 sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
+    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense, true, st))) return rc;
+    RAE_PHASE();   // 9
+    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w, st))) return rc;
+    RAE_PHASE();   // 10
     if ((rc = launch_dense_apply(h, st))) return rc;
+    RAE_PHASE();   // end
+#undef RAE_PHASE
     h->stats.nnz = nnz;
     h->stats.entity_occ = n_occ;
     h->stats.kernel_launches = h->launches;
     h->stats.tensor_path = 0;
     h->stats.unique_w_rows = -1;
     h->stats.unique_e_rows = -1;
-    h->last_f_n_seg = f_n_seg;
+    h->last_f_keys_s = f_keys_s;
+    h->last_f_n = nnz;
     return RAE_OK;
 }
 
@@ -160,11 +174,9 @@ int build_feature_cache(rae_engine* h, cudaStream_t st) {
     FeatureCache& c = h->fcache;
     c.n_batches = nb;
     c.batch_off = new int64_t[nb + 1];
-    c.seg_off = new int64_t[nb + 1];
     int64_t mx = 0;
     for (int64_t b = 0; b <= nb; ++b) {
         c.batch_off[b] = ip[b] - ip[0];
-        c.seg_off[b] = c.batch_off[b] + b;
         if (b > 0 && ip[b] - ip[b - 1] > mx) mx = ip[b] - ip[b - 1];
     }
     sp.max_batch_nnz = mx;
@@ -172,18 +184,14 @@ int build_feature_cache(rae_engine* h, cudaStream_t st) {
     int rc;
     if ((rc = dev_alloc(h, &c.keys_s, used))) return rc;
     if ((rc = dev_alloc(h, &c.vals_s, used))) return rc;
-    if ((rc = dev_alloc(h, &c.seg_start, used + nb + 1))) return rc;
-    if ((rc = dev_alloc(h, &c.n_seg, nb))) return rc;
     if ((rc = ensure_feat_capacity(h, mx))) return rc;
     for (int64_t b = 0; b < nb; ++b) {
         const int64_t n = c.batch_off[b + 1] - c.batch_off[b];
         const int32_t* ipb = sp.indptr + b * h->B;
         if ((rc = build_feature_keys(h, ipb, sp.indices, st))) return rc;
-        if ((rc = sort_and_segment(h, h->feat, n, st))) return rc;
+        if ((rc = sort_pairs(h, h->feat, n, st))) return rc;
         RAE_CUDA(h, cudaMemcpyAsync(c.keys_s + c.batch_off[b], h->feat.keys_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
         RAE_CUDA(h, cudaMemcpyAsync(c.vals_s + c.batch_off[b], h->feat.vals_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
-        RAE_CUDA(h, cudaMemcpyAsync(c.seg_start + c.seg_off[b], h->feat.seg_start, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToDevice, st));
-        RAE_CUDA(h, cudaMemcpyAsync(c.n_seg + b, h->feat.n_seg, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
     RAE_CUDA(h, cudaStreamSynchronize(st));
     c.valid = true;
@@ -307,6 +315,8 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->stat_dev, 2));
+    RAE_CREATE_CUDA(cudaMemset(h->stat_dev, 0, 2 * sizeof(int32_t)));
     RAE_CREATE_RC(dev_alloc(h, &h->label_dev, (size_t)h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->prob_dev, BK));
 #undef RAE_CREATE_CUDA
@@ -320,7 +330,9 @@ void rae_destroy(rae_engine* h) {
     cudaFree(h->q); cudaFree(h->logq); cudaFree(h->dz); cudaFree(h->ev); cudaFree(h->sc); cudaFree(h->gn1); cudaFree(h->gn2);
     cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->dense_grad);
     cudaFree(h->gC_part); cudaFree(h->gW_dense); cudaFree(h->gA_dense); cudaFree(h->gAb_dense); cudaFree(h->cub_tmp);
+    cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev);
     cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
+    if (h->ev_created) for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
     if (h->cost_pinned) cudaFreeHost(h->cost_pinned);
     if (h->pinned_neg) cudaFreeHost(h->pinned_neg);
     free_segwork(h->ent);
@@ -395,15 +407,14 @@ static int train_batch(rae_engine* h, int64_t batch_index, const int32_t* neg1, 
         const FeatureCache& c = h->fcache;
         const int64_t nnz = c.batch_off[batch_index + 1] - c.batch_off[batch_index];
         return run_step(h, sp.indptr + r0, sp.indices, nnz, sp.a1 + r0, sp.a2 + r0, neg1, neg2, neg_ld,
-                        c.keys_s + c.batch_off[batch_index], c.vals_s + c.batch_off[batch_index],
-                        c.seg_start + c.seg_off[batch_index], c.n_seg + batch_index, st);
+                        c.keys_s + c.batch_off[batch_index], c.vals_s + c.batch_off[batch_index], st);
     }
     int32_t ends[2];
     RAE_CUDA(h, cudaMemcpyAsync(&ends[0], sp.indptr + r0, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaMemcpyAsync(&ends[1], sp.indptr + r0 + h->B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaStreamSynchronize(st));
     return run_step(h, sp.indptr + r0, sp.indices, (int64_t)ends[1] - ends[0], sp.a1 + r0, sp.a2 + r0, neg1, neg2, neg_ld,
-                    nullptr, nullptr, nullptr, nullptr, st);
+                    nullptr, nullptr, st);
 }
 
 int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* stream) {
@@ -444,8 +455,7 @@ int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t*
     RAE_CUDA(h, cudaMemcpyAsync(&ends[0], indptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaMemcpyAsync(&ends[1], indptr + h->B, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaStreamSynchronize(st));
-    if ((rc = run_step(h, indptr, indices, (int64_t)ends[1] - ends[0], args1, args2, neg1, neg2, neg_ld, nullptr, nullptr,
-                       nullptr, nullptr, st)))
+    if ((rc = run_step(h, indptr, indices, (int64_t)ends[1] - ends[0], args1, args2, neg1, neg2, neg_ld, nullptr, nullptr, st)))
         return rc;
     return finish_cost(h, cost_host, st);
 }
@@ -508,6 +518,10 @@ int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)(2 + 2 * h->S) * h->B;
     int32_t ns = 0;
+    {
+        int rc = segment_heads(h, h->ent.keys_s, n, h->ent, st);
+        if (rc) return rc;
+    }
     RAE_CUDA(h, cudaMemcpyAsync(&ns, h->ent.n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaStreamSynchronize(st));
     if (sorted_rows) RAE_CUDA(h, cudaMemcpyAsync(sorted_rows, h->ent.keys_s, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
@@ -518,12 +532,41 @@ int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted
     return RAE_OK;
 }
 
+static const char* kPhaseNames[RAE_NUM_PHASES] = {"encoder_forward", "entity_sort", "feature_sort", "decoder_forward", "score",
+                                                   "decoder_backward", "grad_dense", "cost", "entity_update", "w_update",
+                                                   "dense_apply"};
+
+const char* rae_phase_name(int32_t phase) { return (phase >= 0 && phase < RAE_NUM_PHASES) ? kPhaseNames[phase] : ""; }
+
+int rae_set_profiling(rae_engine* h, int32_t on) {
+    if (!h) return RAE_EINVAL;
+    if (on && !h->ev_created) {
+        for (int i = 0; i <= RAE_NUM_PHASES; ++i) RAE_CUDA(h, cudaEventCreate(&h->ev_phase[i]));
+        h->ev_created = true;
+    }
+    h->profiling = on != 0;
+    return RAE_OK;
+}
+
+int rae_get_phase_times(rae_engine* h, float* ms) {
+    if (!h || !ms) return RAE_EINVAL;
+    if (!h->ev_created) return fail(h, RAE_EINVAL, "rae_get_phase_times: profiling was never enabled");
+    RAE_CUDA(h, cudaEventSynchronize(h->ev_phase[RAE_NUM_PHASES]));
+    for (int i = 0; i < RAE_NUM_PHASES; ++i) RAE_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev_phase[i], h->ev_phase[i + 1]));
+    return RAE_OK;
+}
+
 int rae_get_step_stats(rae_engine* h, rae_step_stats* out) {
     if (!h || !out) return RAE_EINVAL;
     // unique-row counts live on the device; reading them synchronises, so it happens only here
-    int32_t ue = 0, uw = 0;
-    cudaMemcpy(&ue, h->ent.n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost);
-    if (h->last_f_n_seg) cudaMemcpy(&uw, h->last_f_n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    int32_t cnt[2] = {0, 0};
+    {
+        int rc = count_unique(h, h->ent.keys_s, h->stats.entity_occ, h->stat_dev, 0);
+        if (rc) return rc;
+        if (h->last_f_keys_s && (rc = count_unique(h, h->last_f_keys_s, h->last_f_n, h->stat_dev + 1, 0))) return rc;
+        RAE_CUDA(h, cudaMemcpy(cnt, h->stat_dev, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    const int32_t ue = cnt[0], uw = h->last_f_keys_s ? cnt[1] : 0;
     h->stats.unique_e_rows = ue;
     h->stats.unique_w_rows = uw;
     // fp32 params + fp32 accumulators, int32 ids

@@ -54,11 +54,8 @@ struct SegWork {
 // feature-side transposed index cached for every batch of the train split
 struct FeatureCache {
     uint32_t* keys_s = nullptr;   // [nnz_used] feature ids, sorted within each batch
-    uint32_t* vals_s = nullptr;   // [nnz_used] example index within the batch
-    int32_t* seg_start = nullptr; // [nnz_used + n_batches] segment starts, batch-local positions
-    int32_t* n_seg = nullptr;     // [n_batches]
-    int64_t* batch_off = nullptr; // host copy: offset of each batch into keys_s / vals_s (= indptr[b*B])
-    int64_t* seg_off = nullptr;   // host: offset of each batch into seg_start
+    uint32_t* vals_s = nullptr;   // [nnz_used] example index within the batch (stable order)
+    int64_t* batch_off = nullptr; // host copy: offset of each batch into keys_s / vals_s (= indptr[b*B] - indptr[0])
     int64_t n_batches = 0;
     bool valid = false;
 };
@@ -98,6 +95,8 @@ struct rae_engine {
     // debug / regularised dense gradients of the sparse tables
     float* gW_dense; float* gA_dense; float* gAb_dense;
     rae::SegWork ent, feat;
+    float* ent_part; size_t ent_part_cap;     // level-1 partial rows of multi-chunk segments
+    float* feat_part; size_t feat_part_cap;
     rae::FeatureCache fcache;
     void* cub_tmp; size_t cub_bytes;
     // explicit-step staging
@@ -106,7 +105,9 @@ struct rae_engine {
     int64_t* label_dev; float* prob_dev;         // label_host staging
     // bookkeeping
     rae_step_stats stats;
-    const int32_t* last_f_n_seg;   // device scalar: unique W rows of the last step
+    bool profiling; cudaEvent_t ev_phase[RAE_NUM_PHASES + 1]; bool ev_created;
+    const uint32_t* last_f_keys_s; int64_t last_f_n;   // sorted feature keys of the last step (statistics)
+    int32_t* stat_dev;   // [2] device scratch for unique-row counts
     int launches;
     int num_sms;
     int max_smem_optin;
@@ -142,12 +143,14 @@ size_t segwork_temp_bytes(int64_t n);
 int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
                       int64_t neg_ld, cudaStream_t st);
 int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indices, cudaStream_t st);
-int sort_and_segment(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st);
+int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st);                 // stable radix sort by row
+int segment_heads(rae_engine* h, const uint32_t* keys_s, int64_t n, SegWork& w, cudaStream_t st);   // introspection
+int count_unique(rae_engine* h, const uint32_t* keys_s, int64_t n, int32_t* out_dev, cudaStream_t st);
 int build_feature_cache(rae_engine* h, cudaStream_t st);
-int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, const int32_t* seg_start,
-                         const int32_t* n_seg, int64_t n_occ, bool emit_dense, bool apply, cudaStream_t st);
-int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, const int32_t* seg_start,
-                    const int32_t* n_seg, int64_t nnz, bool emit_dense, bool apply, cudaStream_t st);
+int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t n_occ, bool emit_dense,
+                         bool apply, cudaStream_t st);
+int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t nnz, bool emit_dense,
+                    bool apply, cudaStream_t st);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser

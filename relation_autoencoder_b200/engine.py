@@ -224,6 +224,14 @@ class Engine:
         torch.cuda.synchronize(self.device)
         return rows.cpu().numpy(), occ.cpu().numpy(), seg.cpu().numpy()[: b.value + 1]
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.rae_set_profiling(self._h, 1 if on else 0), "rae_set_profiling")
+
+    def phase_times_ms(self) -> Dict[str, float]:
+        buf = (C.c_float * L.RAE_NUM_PHASES)()
+        self._check(self.lib.rae_get_phase_times(self._h, buf), "rae_get_phase_times")
+        return {self.lib.rae_phase_name(i).decode(): float(buf[i]) for i in range(L.RAE_NUM_PHASES)}
+
     def stats(self) -> dict:
         st = L.RaeStepStats()
         self._check(self.lib.rae_get_step_stats(self._h, C.byref(st)), "rae_get_step_stats")
