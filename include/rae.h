@@ -66,6 +66,7 @@ extern "C" {
 #define RAE_FLAG_FORCE_SIMT 4u      /* never take the tcgen05 contraction path */
 #define RAE_FLAG_FORCE_TENSOR 8u    /* fail instead of falling back when the tcgen05 path does not support the shape */
 #define RAE_FLAG_NO_FEATURE_CACHE 16u /* re-sort the batch's (feature, example) pairs every step instead of once at bind */
+#define RAE_FLAG_EMIT_ONLY 32u      /* row-sharded multi-GPU: W/A/Ab are per-step compact copies; emit per-row gradients, apply nothing */
 
 typedef struct rae_config {
     int32_t abi_version; /* RAE_ABI_VERSION */
@@ -134,6 +135,32 @@ int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_
 int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, const int32_t* args1,
                             const int32_t* args2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
                             double* cost_host, void* stream);
+
+/* ---- multi-GPU building blocks: the reference has no counterpart (single process, no device) ----------
+ * Data parallel over examples; dense parameters (C, C1, C2, Wb) replicated and their gradients all-reduced by the caller
+ * (NCCL) between _begin and _end; W / A / Ab row-sharded by owner = row mod world.  A rank fetches the rows its batch
+ * touches into compact tables (rae_gather_rows on the owner + all-to-all), runs the step with RAE_FLAG_EMIT_ONLY so the
+ * kernels emit one reduced gradient row per compact row, returns those rows to the owners, and each owner applies them
+ * with rae_sparse_rows_apply: stable sort by (row, source rank order), segment-reduce, one optimiser RMW per row. */
+/* caller-owned output buffers for the emitted gradients: gW[F,K], gA[N,d], gAb[N] (F, N = compact capacities) and the
+ * flat dense gradient [C | C1 | C2 | Wb] (rae_dense_grad_size floats).  NULL keeps the internal buffer. */
+int rae_bind_grad_buffers(rae_engine* h, float* gW, float* gA, float* gAb, float* dense);
+int64_t rae_dense_grad_size(const rae_engine* h);
+/* first part of a step on explicit device inputs: everything except the dense-parameter optimiser update; the flat
+ * dense gradient is complete when the stream reaches this point (all-reduce it, then call _end). */
+int rae_train_step_begin_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t nnz,
+                                  const int32_t* args1, const int32_t* args2, const int32_t* neg1, const int32_t* neg2,
+                                  int64_t neg_ld, void* stream);
+int rae_train_step_end(rae_engine* h, void* stream);
+/* synchronise and read the last step's (local) cost */
+int rae_read_cost(rae_engine* h, double* cost_host, void* stream);
+/* out[i, :] = table[rows[i], :]  (owner-side fetch of requested rows; width floats per row) */
+int rae_gather_rows(rae_engine* h, const float* table, int64_t width, const int32_t* rows, int64_t n, float* out,
+                    void* stream);
+/* owner-side update: for every distinct r in rows[0..n): g = sum (in input order) of grads[i,:] with rows[i] == r, then the
+ * handle's optimiser rule on table[r,:] / acc[r,:] (Optimizers.py:29-32 / :51).  n_table_rows bounds the row ids. */
+int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows, const float* grads,
+                          int64_t n, int64_t n_table_rows, void* stream);
 
 /* ---- func['label_<split>'] ------------------------------------------------------------------------------ */
 /* labels = argmax of the scores, first max wins (RelationClassifier.py:45-47); probs = softmax.  Device outputs. */

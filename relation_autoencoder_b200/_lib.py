@@ -24,6 +24,7 @@ RAE_FLAG_DENSE_GRADS = 2
 RAE_FLAG_FORCE_SIMT = 4
 RAE_FLAG_FORCE_TENSOR = 8
 RAE_FLAG_NO_FEATURE_CACHE = 16
+RAE_FLAG_EMIT_ONLY = 32
 RAE_ENODEVICE = -5
 RAE_NUM_PHASES = 11
 
@@ -63,6 +64,13 @@ _SIGNATURES = {
     "rae_get_dense_grad": (C.c_int, [_P, C.c_int32, _P, _P]),
     "rae_get_entity_segments": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
     "rae_get_step_stats": (C.c_int, [_P, C.POINTER(RaeStepStats)]),
+    "rae_bind_grad_buffers": (C.c_int, [_P, _P, _P, _P, _P]),
+    "rae_dense_grad_size": (C.c_int64, [_P]),
+    "rae_train_step_begin_explicit": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
+    "rae_train_step_end": (C.c_int, [_P, _P]),
+    "rae_read_cost": (C.c_int, [_P, C.POINTER(C.c_double), _P]),
+    "rae_gather_rows": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
+    "rae_sparse_rows_apply": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P]),
     "rae_set_profiling": (C.c_int, [_P, C.c_int32]),
     "rae_get_phase_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rae_phase_name": (C.c_char_p, [C.c_int32]),

@@ -85,10 +85,10 @@ static void free_feature_cache(FeatureCache& c) {
 // one training step on device-resident inputs.  nnz_hint < 0: unknown (explicit API reads indptr back once).
 static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t nnz, const int32_t* a1,
                     const int32_t* a2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
-                    const uint32_t* f_keys_s, const uint32_t* f_vals_s, cudaStream_t st) {
+                    const uint32_t* f_keys_s, const uint32_t* f_vals_s, cudaStream_t st, bool finish_dense = true) {
     int rc;
     h->launches = 0;
-    const bool emit = h->debug_dense || h->dense_w;
+    const bool emit = h->debug_dense || h->dense_w || h->emit_only;
     int phase = 0;
 #define RAE_PHASE()                                                                    \
     do {                                                                               \
@@ -119,19 +119,21 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     if ((rc = launch_dense_finalize(h, st))) return rc;
     RAE_PHASE();   // 7 cost (uses the pre-update parameters for the regulariser value)
     if ((rc = launch_cost(h, st))) return rc;
-    if (emit) {
+    // emit-only (row-sharded multi-GPU): the tables are per-step compact copies whose every row is touched, so the
+    // emitted gradient buffers need no clearing and nothing is applied here (the owner shard applies, rae_sparse_rows_apply)
+    if (emit && !h->emit_only) {
         if ((rc = launch_zero(h, h->gW_dense, sizeof(float) * (size_t)h->cfg.F * h->K, st))) return rc;
     }
-    if (h->debug_dense) {
+    if (h->debug_dense && !h->emit_only) {
         if ((rc = launch_zero(h, h->gA_dense, sizeof(float) * (size_t)h->cfg.N * h->d, st))) return rc;
         if ((rc = launch_zero(h, h->gAb_dense, sizeof(float) * (size_t)h->cfg.N, st))) return rc;
     }
     RAE_PHASE();   // 8 sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
-    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense, true, st))) return rc;
+    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense || h->emit_only, !h->emit_only, st))) return rc;
     RAE_PHASE();   // 9
-    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w, st))) return rc;
+    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w && !h->emit_only, st))) return rc;
     RAE_PHASE();   // 10
-    if ((rc = launch_dense_apply(h, st))) return rc;
+    if (finish_dense && (rc = launch_dense_apply(h, st))) return rc;
     RAE_PHASE();   // end
 #undef RAE_PHASE
     h->stats.nnz = nnz;
@@ -239,6 +241,11 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     h->adagrad = cfg->optimizer == RAE_OPT_ADAGRAD;
     h->dense_w = (cfg->l1 != 0.0 || cfg->l2 != 0.0);
     h->debug_dense = (cfg->flags & RAE_FLAG_DENSE_GRADS) != 0;
+    h->emit_only = (cfg->flags & RAE_FLAG_EMIT_ONLY) != 0;
+    if (h->emit_only && h->dense_w) {
+        delete h;
+        return fail(nullptr, RAE_EINVAL, "RAE_FLAG_EMIT_ONLY (row-sharded tables) does not support l1/l2 != 0 yet");
+    }
     h->Z = cfg->z_total > 0 ? (double)cfg->z_total : (double)(4.0 * cfg->B + 2.0 * cfg->B * cfg->S);
 #define RAE_CREATE_CUDA(expr)                                                                                  \
     do {                                                                                                       \
@@ -304,11 +311,12 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
         h->gC_nsplit = ns;
         RAE_CREATE_RC(dev_alloc(h, &h->gC_part, (size_t)ns * (size_t)(dd + 2 * dk)));
     }
-    if (h->dense_w || h->debug_dense) RAE_CREATE_RC(dev_alloc(h, &h->gW_dense, (size_t)cfg->F * h->K));
-    if (h->debug_dense) {
+    if (h->dense_w || h->debug_dense || h->emit_only) RAE_CREATE_RC(dev_alloc(h, &h->gW_dense, (size_t)cfg->F * h->K));
+    if (h->debug_dense || h->emit_only) {
         RAE_CREATE_RC(dev_alloc(h, &h->gA_dense, (size_t)cfg->N * h->d));
         RAE_CREATE_RC(dev_alloc(h, &h->gAb_dense, (size_t)cfg->N));
     }
+    h->own_gW = h->gW_dense; h->own_gA = h->gA_dense; h->own_gAb = h->gAb_dense; h->own_dense = h->dense_grad;
     const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
     RAE_CREATE_RC(alloc_segwork(h, h->ent, n_occ, bits_for(cfg->N)));
     RAE_CREATE_RC(ensure_cub(h, n_occ));
@@ -328,8 +336,8 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
 void rae_destroy(rae_engine* h) {
     if (!h) return;
     cudaFree(h->q); cudaFree(h->logq); cudaFree(h->dz); cudaFree(h->ev); cudaFree(h->sc); cudaFree(h->gn1); cudaFree(h->gn2);
-    cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->dense_grad);
-    cudaFree(h->gC_part); cudaFree(h->gW_dense); cudaFree(h->gA_dense); cudaFree(h->gAb_dense); cudaFree(h->cub_tmp);
+    cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->own_dense);
+    cudaFree(h->gC_part); cudaFree(h->own_gW); cudaFree(h->own_gA); cudaFree(h->own_gAb); cudaFree(h->cub_tmp);
     cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev);
     cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
     if (h->ev_created) for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
@@ -355,7 +363,8 @@ int rae_bind_params(rae_engine* h, float* W, float* Wb, float* A, float* Ab, flo
 
 int rae_bind_accumulators(rae_engine* h, float* W, float* Wb, float* A, float* Ab, float* C, float* C1, float* C2) {
     if (!h) return RAE_EINVAL;
-    if (!W || !Wb || !A || !Ab) return fail(h, RAE_EINVAL, "rae_bind_accumulators: W, Wb, A, Ab must be non-null");
+    if (!Wb || (!h->emit_only && (!W || !A || !Ab)))
+        return fail(h, RAE_EINVAL, "rae_bind_accumulators: W, Wb, A, Ab must be non-null (W, A, Ab may be NULL with RAE_FLAG_EMIT_ONLY)");
     if (h->hasM && !C) return fail(h, RAE_EINVAL, "rae_bind_accumulators: this model needs C (R) [d,d,K]");
     if (h->hasSP && (!C1 || !C2)) return fail(h, RAE_EINVAL, "rae_bind_accumulators: this model needs C1 and C2 [d,K]");
     float* v[RAE_NUM_PARAMS] = {W, Wb, A, Ab, C, C1, C2};
@@ -484,6 +493,61 @@ int rae_label_host(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t
     RAE_CUDA(h, cudaMemcpyAsync(probs_host, h->prob_dev, sizeof(float) * (size_t)h->B * h->K, cudaMemcpyDeviceToHost, st));
     RAE_CUDA(h, cudaStreamSynchronize(st));
     return RAE_OK;
+}
+
+int rae_bind_grad_buffers(rae_engine* h, float* gW, float* gA, float* gAb, float* dense) {
+    if (!h) return RAE_EINVAL;
+    h->gW_dense = gW ? gW : h->own_gW;
+    h->gA_dense = gA ? gA : h->own_gA;
+    h->gAb_dense = gAb ? gAb : h->own_gAb;
+    h->dense_grad = dense ? dense : h->own_dense;
+    return RAE_OK;
+}
+
+int64_t rae_dense_grad_size(const rae_engine* h) { return h ? h->n_dense : 0; }
+
+int rae_train_step_begin_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t nnz,
+                                  const int32_t* args1, const int32_t* args2, const int32_t* neg1, const int32_t* neg2,
+                                  int64_t neg_ld, void* stream) {
+    int rc = check_ready(h, false, false);
+    if (rc) return rc;
+    if (!indptr || !indices || !args1 || !args2 || nnz < 0) return fail(h, RAE_EINVAL, "rae_train_step_begin_explicit: bad argument");
+    return run_step(h, indptr, indices, nnz, args1, args2, neg1, neg2, neg_ld, nullptr, nullptr, (cudaStream_t)stream, false);
+}
+
+int rae_train_step_end(rae_engine* h, void* stream) {
+    int rc = check_ready(h, false, false);
+    if (rc) return rc;
+    return launch_dense_apply(h, (cudaStream_t)stream);
+}
+
+int rae_read_cost(rae_engine* h, double* cost_host, void* stream) {
+    if (!h || !cost_host) return RAE_EINVAL;
+    return finish_cost(h, cost_host, (cudaStream_t)stream);
+}
+
+int rae_gather_rows(rae_engine* h, const float* table, int64_t width, const int32_t* rows, int64_t n, float* out,
+                    void* stream) {
+    if (!h || !table || (!rows && n > 0) || (!out && n > 0) || width < 1 || n < 0) return rae::fail(h, RAE_EINVAL, "rae_gather_rows: bad argument");
+    return launch_gather_rows(h, table, width, rows, n, out, (cudaStream_t)stream);
+}
+
+int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows, const float* grads,
+                          int64_t n, int64_t n_table_rows, void* stream) {
+    if (!h || !table || width < 1 || n < 0 || n_table_rows < 1) return rae::fail(h, RAE_EINVAL, "rae_sparse_rows_apply: bad argument");
+    if (h->adagrad && !acc) return rae::fail(h, RAE_EINVAL, "rae_sparse_rows_apply: AdaGrad needs the accumulator table");
+    if (n == 0) return RAE_OK;
+    if (!rows || !grads) return rae::fail(h, RAE_EINVAL, "rae_sparse_rows_apply: null rows/grads");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_feat_capacity(h, n);
+    if (rc) return rc;
+    if ((rc = build_row_keys(h, rows, n, st))) return rc;
+    const int saved_bits = h->feat.key_bits;
+    h->feat.key_bits = bits_for(n_table_rows);
+    rc = sort_pairs(h, h->feat, n, st);
+    h->feat.key_bits = saved_bits;
+    if (rc) return rc;
+    return launch_rows_apply(h, table, acc, (int)width, h->feat.keys_s, h->feat.vals_s, grads, n, st);
 }
 
 int rae_get_probs(rae_engine* h, float* dst, void* stream) {

@@ -66,7 +66,7 @@ struct rae_engine {
     rae_config cfg;
     int K, d, S, B;
     int dp;          // d rounded up to a multiple of 4 (row stride of ev)
-    bool hasM, hasSP, quirk, adagrad, dense_w, debug_dense;
+    bool hasM, hasSP, quirk, adagrad, dense_w, debug_dense, emit_only;
     double Z;        // denominator of the mean
     float* P[RAE_NUM_PARAMS];
     float* ACC[RAE_NUM_PARAMS];
@@ -94,6 +94,7 @@ struct rae_engine {
     float* gC_part; int gC_nsplit;       // [nsplit, units*d*K]
     // debug / regularised dense gradients of the sparse tables
     float* gW_dense; float* gA_dense; float* gAb_dense;
+    float* own_gW; float* own_gA; float* own_gAb; float* own_dense;   // internally allocated versions (freed at destroy)
     rae::SegWork ent, feat;
     float* ent_part; size_t ent_part_cap;     // level-1 partial rows of multi-chunk segments
     float* feat_part; size_t feat_part_cap;
@@ -151,6 +152,11 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
                          bool apply, cudaStream_t st);
 int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t nnz, bool emit_dense,
                     bool apply, cudaStream_t st);
+int build_row_keys(rae_engine* h, const int32_t* rows, int64_t n, cudaStream_t st);      // keys = rows, vals = 0..n-1
+int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const uint32_t* keys_s, const uint32_t* vals_s,
+                      const float* grads, int64_t n, cudaStream_t st);
+int launch_gather_rows(rae_engine* h, const float* table, int64_t width, const int32_t* rows, int64_t n, float* out,
+                       cudaStream_t st);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser

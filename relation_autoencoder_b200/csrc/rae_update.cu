@@ -48,6 +48,32 @@ __global__ void k_feature_keys(const int32_t* __restrict__ indptr, const int32_t
     }
 }
 
+__global__ void k_row_keys(const int32_t* __restrict__ rows, int n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        keys[i] = (uint32_t)rows[i];
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// out[i,:] = table[rows[i],:]; one warp per row, 16-byte vectors when the row pitch allows it
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ table, int width, const int32_t* __restrict__ rows,
+                                                     int n, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = gw; i < n; i += nw) {
+        const float* src = table + (size_t)rows[i] * width;
+        float* dst = out + (size_t)i * width;
+        if ((width & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int q = lane; q < (width >> 2); q += 32) d4[q] = s4[q];
+        } else {
+            for (int k = lane; k < width; k += 32) dst[k] = src[k];
+        }
+    }
+}
+
 // ---- segment boundaries (introspection / parity tests only: the update kernels work from the sorted keys) ----
 __global__ void k_flag_heads(const uint32_t* __restrict__ keys_s, int n, int32_t* __restrict__ flags) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -985,6 +1011,62 @@ int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_
     else if (kt <= 16) RAE_WU(16);
     else RAE_WU(32);
 #undef RAE_WU
+    h->launches += 2;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+int build_row_keys(rae_engine* h, const int32_t* rows, int64_t n, cudaStream_t st) {
+    if (n > h->feat.capacity) return fail(h, RAE_EINVAL, "internal: row-key workspace too small");
+    const int blocks = std::min((int)((n + 255) / 256), 4 * h->num_sms);
+    k_row_keys<<<blocks, 256, 0, st>>>(rows, (int)n, h->feat.keys, h->feat.vals);
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+int launch_gather_rows(rae_engine* h, const float* table, int64_t width, const int32_t* rows, int64_t n, float* out,
+                       cudaStream_t st) {
+    if (n <= 0) return RAE_OK;
+    const int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)h->num_sms * 8);
+    k_gather_rows<<<blocks, 256, 0, st>>>(table, (int)width, rows, (int)n, out);
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+// generic owner-side sparse-row optimiser step: table[row,:] updated with the sum of grads[val,:] over the row's
+// sorted occurrences (the same kernels as the W update with dz := grads, K := width)
+int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const uint32_t* keys_s, const uint32_t* vals_s,
+                      const float* grads, int64_t n, cudaStream_t st) {
+    if (n <= 0) return RAE_OK;
+    WArgs p{};
+    p.keys_s = keys_s; p.vals_s = vals_s;
+    p.dz = grads; p.W = table; p.accW = acc; p.gW_dense = nullptr;
+    p.K = width; p.n = (int)n; p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = 0; p.apply = 1;
+    const int64_t nchunks = (n + 31) / 32;
+    int rc = ensure_part(h, &h->feat_part, &h->feat_part_cap, (size_t)(2 * nchunks) * width);
+    if (rc) return rc;
+    p.part = h->feat_part;
+    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
+    const int kt = (width + 31) / 32;
+#define RAE_RA(KT)                                     \
+    do {                                               \
+        k_w_chunks<KT><<<blocks, 256, 0, st>>>(p);     \
+        k_w_long<KT><<<blocks, 256, 0, st>>>(p);       \
+    } while (0)
+    if ((width & 3) == 0) {
+        const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
+        k_w_scan<<<blocks, 256, 0, st>>>(p);
+        k_w_long2<<<blocks2, 256, sizeof(float) * 8 * width, st>>>(p);
+    }
+    else if (kt <= 1) RAE_RA(1);
+    else if (kt <= 2) RAE_RA(2);
+    else if (kt <= 4) RAE_RA(4);
+    else if (kt <= 8) RAE_RA(8);
+    else if (kt <= 16) RAE_RA(16);
+    else RAE_RA(32);
+#undef RAE_RA
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
