@@ -109,7 +109,14 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s;
     }
     RAE_PHASE();   // 3 decoder forward
-    if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
+    if (h->use_tc) {
+        if ((rc = tc_prepare_c(h, st))) return rc;
+        if ((rc = tc_prepare_p(h, st))) return rc;
+        if ((rc = tc_gather_lr(h, a1, a2, st))) return rc;
+        if ((rc = tc_contract(h, E_L, E_R, E_V1, E_V2, true, st))) return rc;
+    } else {
+        if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
+    }
     RAE_PHASE();   // 4 scoring / loss / d cost / d score
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
     RAE_PHASE();   // 5 decoder backward
@@ -139,7 +146,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     h->stats.nnz = nnz;
     h->stats.entity_occ = n_occ;
     h->stats.kernel_launches = h->launches;
-    h->stats.tensor_path = 0;
+    h->stats.tensor_path = h->use_tc ? 1 : 0;
     h->stats.unique_w_rows = -1;
     h->stats.unique_e_rows = -1;
     h->last_f_keys_s = f_keys_s;
@@ -281,6 +288,16 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
         rae_destroy(h);
         return RAE_EINVAL;
     }
+    h->tc = TcState{};
+    h->use_tc = false;
+    if (!(cfg->flags & RAE_FLAG_FORCE_SIMT) && tc_supported(h)) {
+        RAE_CREATE_RC(tc_init(h));
+        h->use_tc = true;
+    } else if (cfg->flags & RAE_FLAG_FORCE_TENSOR) {
+        fail(nullptr, RAE_EINVAL, "RAE_FLAG_FORCE_TENSOR: the tcgen05 path needs a bilinear model with 16 < d <= 128 and K <= 104 (K=%d d=%d)", cfg->K, cfg->d);
+        rae_destroy(h);
+        return RAE_EINVAL;
+    }
     const size_t BK = (size_t)h->B * h->K;
     RAE_CREATE_RC(dev_alloc(h, &h->q, BK));
     RAE_CREATE_RC(dev_alloc(h, &h->logq, BK));
@@ -346,6 +363,7 @@ void rae_destroy(rae_engine* h) {
     free_segwork(h->ent);
     free_segwork(h->feat);
     free_feature_cache(h->fcache);
+    tc_free(h);
     cudaGetLastError();
     delete h;
 }

@@ -60,6 +60,20 @@ struct FeatureCache {
     bool valid = false;
 };
 
+// tensor-core (tcgen05) contraction path state (rae_decoder_tc.cu)
+struct TcState {
+    bool ready = false;
+    int DP = 0;            // columns per row of M, padded: 32 / 64 / 128
+    int KQ = 0;            // float4 planes along the relation axis (K padded to a multiple of 8, / 4)
+    int n_bil_rows = 0, n_bil_chunks = 0, n_sp_chunks = 0, n_rows_total = 0;
+    int ntile = 0, NS = 0;
+    size_t smem = 0;
+    float4* pop = nullptr; // P operand tiles  [tile][hi/lo][KQ][128]
+    float4* bop = nullptr; // B operand chunks [chunk][hi/lo][KQ][64]
+    float* vg = nullptr;   // [2][B][dp]
+    float* wp = nullptr;   // [NS][2][B][dp]
+};
+
 }  // namespace rae
 
 struct rae_engine {
@@ -99,6 +113,7 @@ struct rae_engine {
     float* ent_part; size_t ent_part_cap;     // level-1 partial rows of multi-chunk segments
     float* feat_part; size_t feat_part_cap;
     rae::FeatureCache fcache;
+    rae::TcState tc; bool use_tc;
     void* cub_tmp; size_t cub_bytes;
     // explicit-step staging
     int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
@@ -138,6 +153,15 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
                  int64_t neg_ld, cudaStream_t st);
 int launch_bilinear_backward_simt(rae_engine* h, cudaStream_t st);
 int launch_grad_dense_simt(rae_engine* h, cudaStream_t st);
+
+// ---- decoder, tcgen05 contraction (rae_decoder_tc.cu) ----
+int tc_supported(const rae_engine* h);
+int tc_init(rae_engine* h);
+void tc_free(rae_engine* h);
+int tc_prepare_c(rae_engine* h, cudaStream_t st);
+int tc_prepare_p(rae_engine* h, cudaStream_t st);
+int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);
+int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
 
 // ---- sort / segment / updates (rae_update.cu) ----
 size_t segwork_temp_bytes(int64_t n);
