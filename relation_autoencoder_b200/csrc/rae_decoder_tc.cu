@@ -420,6 +420,455 @@ __global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// backward, dq[b,k] = sum_n G[b,n] Cf[n,k]  with the generated operand
+//   bilinear row n=(i,j): G = a_bi R_bj + L_bi Y2_bj   (dM_b = a R^T + L Y2^T, rank 2)
+//   C1 row j            : G = a_bj + G2_b L_bj         (d cost / d c1)
+//   C2 row j            : G = c_bj + G1_b R_bj         (d cost / d c2)
+// UMMA: M = 128 examples, N = NK (relations padded to 16), reduction over n in chunks of 32 rows.  The A operand is
+// produced by 8 generator warps straight into the canonical smem image (hi/lo split, fence.proxy.async, mbarrier), the B
+// operand (Cf transposed: K-major along n) is pre-arranged in HBM and bulk-copied.  One TMEM accumulator [128 x NK].
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TC_NC = 32;          // reduction rows per chunk (8 float4 planes)
+
+__global__ void __launch_bounds__(256) k_tc_prep_ct(const float* __restrict__ C, const float* __restrict__ C1,
+                                                    const float* __restrict__ C2, int d, int K, int NK, int DP, int n_bil_rows,
+                                                    int n_rows_total, float4* __restrict__ out) {
+    // out[c32][split][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
+    const size_t total = (size_t)(n_rows_total / 4) * NK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int krow = (int)(idx % NK);
+        const int nq_g = (int)(idx / NK);            // global quad index along n
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = 4 * nq_g + u;
+            const float* src = nullptr;
+            if (n < n_bil_rows) {
+                const int i = n / DP, j = n - i * DP;
+                if (i < d && j < d && C != nullptr) src = C + ((size_t)i * d + j) * K;
+            } else {
+                const int m = n - n_bil_rows;
+                const int which = m / DP, j = m - which * DP;
+                if (j < d) src = (which == 0 ? C1 : C2);
+                if (src != nullptr) src += (size_t)j * K;
+            }
+            x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
+        }
+        float4 hi, lo;
+        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
+        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
+        const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
+        float4* base = out + (size_t)c32 * 2 * 8 * NK;
+        base[(size_t)nq * NK + krow] = hi;
+        base[(size_t)(8 + nq) * NK + krow] = lo;
+    }
+}
+
+struct TcDqArgs {
+    const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
+    const float* ev; const float* sc;
+    float* dqp;             // [NS][B][NK]
+    int B, d, dp, K, NK, DP;
+    int n_bil_rows, n_chunks32, NS;
+};
+
+// the generated operand for 4 consecutive rows n = base..base+3 of chunk c32 and example row evb (zero beyond dp)
+__device__ __forceinline__ float4 gen_g4(const float* __restrict__ evb, const float* __restrict__ scb, int dp, int DP,
+                                         int n_bil_rows, int n, bool ok) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!ok) return g;
+    float s1, s2;
+    int sx, sy, j;
+    if (n < n_bil_rows) {
+        const int i = n / DP;
+        j = n - i * DP;
+        if (i >= dp) return g;
+        s1 = evb[E_A * dp + i]; s2 = evb[E_L * dp + i]; sx = E_R; sy = E_Y2;
+    } else {
+        const int m = n - n_bil_rows;
+        const int which = m / DP;
+        j = m - which * DP;
+        s1 = 1.f;
+        if (which == 0) { sx = E_A; s2 = scb[SC_G2]; sy = E_L; }
+        else { sx = E_CV; s2 = scb[SC_G1]; sy = E_R; }
+    }
+    if (j >= dp) return g;
+    const float4 x = *reinterpret_cast<const float4*>(evb + sx * dp + j);
+    const float4 y = *reinterpret_cast<const float4*>(evb + sy * dp + j);
+    g.x = fmaf(s1, x.x, s2 * y.x); g.y = fmaf(s1, x.y, s2 * y.y); g.z = fmaf(s1, x.z, s2 * y.z); g.w = fmaf(s1, x.w, s2 * y.w);
+    return g;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dq(TcDqArgs p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
+    const uint32_t A_BYTES = 2u * 8u * TC_M * 16u;          // hi/lo x 8 planes x 128 rows
+    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
+    uint8_t* smA = smem_raw;
+    uint8_t* smB = smem_raw + 2 * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_BYTES + 2 * B_BYTES);
+    uint64_t* a_full = bars;            // [2] 256 generator arrivals
+    uint64_t* a_empty = bars + 2;       // [2] tcgen05.commit
+    uint64_t* b_full = bars + 4;        // [2] bulk-copy tx
+    uint64_t* b_empty = bars + 6;       // [2] tcgen05.commit
+    uint64_t* acc_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int per = (p.n_chunks32 + p.NS - 1) / p.NS;
+    const int c_begin = min(per * split, p.n_chunks32), c_end = min(per * (split + 1), p.n_chunks32);
+    const int nit = c_end - c_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nit; ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&b_empty[s], ph ^ 1);
+                mbar_expect_tx(&b_full[s], B_BYTES);
+                bulk_g2s(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop2) + (size_t)(c_begin + it) * B_BYTES,
+                         B_BYTES, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nit > 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, p.NK);
+            for (int it = 0; it < nit; ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&a_full[s], ph);
+                mbar_wait(&b_full[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smA + (size_t)s * A_BYTES), a_lo = a_hi + 8u * TC_M * 16u;
+                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES), b_lo = b_hi + 8u * (uint32_t)p.NK * 16u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ao = (uint32_t)(2 * ks) * TC_M * 16u, bo = (uint32_t)(2 * ks) * (uint32_t)p.NK * 16u;
+                    const uint64_t dah = make_desc(a_hi + ao, TC_M * 16u, 128u), dal = make_desc(a_lo + ao, TC_M * 16u, 128u);
+                    const uint64_t dbh = make_desc(b_hi + bo, (uint32_t)p.NK * 16u, 128u), dbl = make_desc(b_lo + bo, (uint32_t)p.NK * 16u, 128u);
+                    tc_mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    tc_mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                }
+                tc_commit(&a_empty[s]);
+                tc_commit(&b_empty[s]);
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // ===== generators (8 warps): thread = (row, half of the chunk's 8 planes) =====
+        const int gt = threadIdx.x - 128;
+        const int row = gt & 127, half = gt >> 7;
+        const int b = tile * TC_M + row;
+        const bool ok = b < p.B;
+        const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
+        const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
+        for (int it = 0; it < nit; ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int n0 = (c_begin + it) * TC_NC + 16 * half;
+            float4 g[4];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) g[qd] = gen_g4(evb, scb, p.dp, p.DP, p.n_bil_rows, n0 + 4 * qd, ok);
+            mbar_wait(&a_empty[s], ph ^ 1);
+            float4* ah = reinterpret_cast<float4*>(smA + (size_t)s * A_BYTES);
+            float4* al = ah + 8 * TC_M;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                float4 hi, lo;
+                hi.x = tf32_hi(g[qd].x); hi.y = tf32_hi(g[qd].y); hi.z = tf32_hi(g[qd].z); hi.w = tf32_hi(g[qd].w);
+                lo.x = tf32_hi(g[qd].x - hi.x); lo.y = tf32_hi(g[qd].y - hi.y); lo.z = tf32_hi(g[qd].z - hi.z); lo.w = tf32_hi(g[qd].w - hi.w);
+                ah[(4 * half + qd) * TC_M + row] = hi;
+                al[(4 * half + qd) * TC_M + row] = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA (async proxy)
+            mbar_arrive(&a_full[s]);
+        }
+        if (warp < 8) {
+            // ===== epilogue: accumulator row -> dq partial =====
+            if (nit > 0) {
+                mbar_wait(acc_full, 0);
+                tc_fence_after();
+            }
+            const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            float* o = p.dqp + ((size_t)split * p.B + (ok ? b : 0)) * p.NK;
+            for (int c0 = 0; c0 < p.NK; c0 += 32) {
+                float t[32];
+                if (nit > 0) {
+                    tc_ld32(lane_base + (uint32_t)c0, t);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) t[x] = 0.f;
+                }
+                if (ok) {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x)
+                        if (c0 + x < p.NK) o[c0 + x] = t[x];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, dense-parameter gradients: dCf[n,k] = sum_b G[b,n] q[b,k]   (dC, dC1, dC2 in one operand)
+// UMMA: M = 128 rows n (one CTA owns an n-tile), N = NK, reduction over the examples in chunks of 32.  The A operand is
+// G^T generated in shared memory (planes over 4 consecutive examples), the B operand q^T is pre-arranged and bulk-copied.
+// The batch range can be split over CTAs (split-K); partial tiles land in gC_part[split] and are summed in fixed order
+// by k_dense_finalize.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out) {
+    // out[bc][split][bq 0..7][krow 0..NK-1] = (q[32bc+4bq+0..3][krow])
+    const int nbc = (B + TC_NC - 1) / TC_NC;
+    const size_t total = (size_t)nbc * 8 * NK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int krow = (int)(idx % NK);
+        const int bq = (int)((idx / NK) % 8);
+        const int bc = (int)(idx / ((size_t)8 * NK));
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = bc * TC_NC + 4 * bq + u;
+            x[u] = (b < B && krow < K) ? q[(size_t)b * K + krow] : 0.f;
+        }
+        float4 hi, lo;
+        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
+        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
+        float4* base = out + (size_t)bc * 2 * 8 * NK;
+        base[(size_t)bq * NK + krow] = hi;
+        base[(size_t)(8 + bq) * NK + krow] = lo;
+    }
+}
+
+struct TcDcArgs {
+    const float4* pop3;     // q^T chunks [bc][hi/lo][8][NK]
+    const float* ev; const float* sc;
+    float* out;             // gC_part [NSb][units*d*K]
+    int B, d, dp, K, NK, DP;
+    int n_bil_rows, n_rows_total, n_bchunks, NSb, hasM;
+    size_t split_stride;    // units*d*K
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dc(TcDcArgs p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile = blockIdx.x / p.NSb, split = blockIdx.x - ntile * p.NSb;
+    const uint32_t A_BYTES = 2u * 8u * TC_M * 16u;
+    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
+    uint8_t* smA = smem_raw;
+    uint8_t* smB = smem_raw + 2 * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_BYTES + 2 * B_BYTES);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + 2;
+    uint64_t* b_full = bars + 4;
+    uint64_t* b_empty = bars + 6;
+    uint64_t* acc_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int per = (p.n_bchunks + p.NSb - 1) / p.NSb;
+    const int c_begin = min(per * split, p.n_bchunks), c_end = min(per * (split + 1), p.n_bchunks);
+    const int nit = c_end - c_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nit; ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&b_empty[s], ph ^ 1);
+                mbar_expect_tx(&b_full[s], B_BYTES);
+                bulk_g2s(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.pop3) + (size_t)(c_begin + it) * B_BYTES,
+                         B_BYTES, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nit > 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, p.NK);
+            for (int it = 0; it < nit; ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&a_full[s], ph);
+                mbar_wait(&b_full[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smA + (size_t)s * A_BYTES), a_lo = a_hi + 8u * TC_M * 16u;
+                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES), b_lo = b_hi + 8u * (uint32_t)p.NK * 16u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ao = (uint32_t)(2 * ks) * TC_M * 16u, bo = (uint32_t)(2 * ks) * (uint32_t)p.NK * 16u;
+                    const uint64_t dah = make_desc(a_hi + ao, TC_M * 16u, 128u), dal = make_desc(a_lo + ao, TC_M * 16u, 128u);
+                    const uint64_t dbh = make_desc(b_hi + bo, (uint32_t)p.NK * 16u, 128u), dbl = make_desc(b_lo + bo, (uint32_t)p.NK * 16u, 128u);
+                    tc_mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    tc_mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                }
+                tc_commit(&a_empty[s]);
+                tc_commit(&b_empty[s]);
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // ===== generators: thread = (row n of the tile, half of the chunk's examples) =====
+        const int gt = threadIdx.x - 128;
+        const int row = gt & 127, half = gt >> 7;
+        const int n = ntile * TC_M + row;
+        // decode the row once: g(b) = P1(b) * X(b) + P2(b) * Y(b)
+        int type = -1, i = 0, j = 0;          // -1: padding row (zero)
+        if (n < p.n_bil_rows) {
+            i = n / p.DP; j = n - i * p.DP;
+            if (i < p.d && j < p.d) type = 0;
+        } else if (n < p.n_rows_total) {
+            const int m = n - p.n_bil_rows;
+            const int which = m / p.DP;
+            j = m - which * p.DP;
+            if (j < p.d) type = 1 + which;
+        }
+        const size_t estride = (size_t)E_NV * p.dp;
+        int oP1, oX, oP2, oY;                 // float offsets inside an example's ev block (type 0) ...
+        if (type == 0) { oP1 = E_A * p.dp + i; oX = E_R * p.dp + j; oP2 = E_L * p.dp + i; oY = E_Y2 * p.dp + j; }
+        else if (type == 1) { oP1 = -1; oX = E_A * p.dp + j; oP2 = SC_G2; oY = E_L * p.dp + j; }
+        else { oP1 = -1; oX = E_CV * p.dp + j; oP2 = SC_G1; oY = E_R * p.dp + j; }
+        for (int it = 0; it < nit; ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int b0 = (c_begin + it) * TC_NC + 16 * half;
+            float g[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int b = b0 + e;
+                float v = 0.f;
+                if (type >= 0 && b < p.B) {
+                    const float* evb = p.ev + (size_t)b * estride;
+                    const float p1 = (type == 0) ? evb[oP1] : 1.f;
+                    const float p2 = (type == 0) ? evb[oP2] : p.sc[(size_t)b * SC_N + oP2];
+                    v = fmaf(p1, evb[oX], p2 * evb[oY]);
+                }
+                g[e] = v;
+            }
+            mbar_wait(&a_empty[s], ph ^ 1);
+            float4* ah = reinterpret_cast<float4*>(smA + (size_t)s * A_BYTES);
+            float4* al = ah + 8 * TC_M;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                float4 hi, lo;
+                hi.x = tf32_hi(g[4 * qd]); hi.y = tf32_hi(g[4 * qd + 1]); hi.z = tf32_hi(g[4 * qd + 2]); hi.w = tf32_hi(g[4 * qd + 3]);
+                lo.x = tf32_hi(g[4 * qd] - hi.x); lo.y = tf32_hi(g[4 * qd + 1] - hi.y);
+                lo.z = tf32_hi(g[4 * qd + 2] - hi.z); lo.w = tf32_hi(g[4 * qd + 3] - hi.w);
+                ah[(4 * half + qd) * TC_M + row] = hi;
+                al[(4 * half + qd) * TC_M + row] = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&a_full[s]);
+        }
+        if (warp < 8) {
+            if (nit > 0) {
+                mbar_wait(acc_full, 0);
+                tc_fence_after();
+            }
+            const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            // destination inside the split's block: units are [bilinear rows i][C1][C2], each [d][K]
+            size_t off = 0;
+            if (type == 0) off = ((size_t)i * p.d + j) * p.K;
+            else if (type > 0) off = ((size_t)((p.hasM ? p.d : 0) + (type - 1)) * p.d + j) * p.K;
+            float* o = p.out + (size_t)split * p.split_stride + off;
+            for (int c0 = 0; c0 < p.NK; c0 += 32) {
+                float t[32];
+                if (nit > 0) {
+                    tc_ld32(lane_base + (uint32_t)c0, t);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) t[x] = 0.f;
+                }
+                if (type >= 0) {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x)
+                        if (c0 + x < p.K) o[c0 + x] = t[x];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+// per-example finishing of the backward (one warp per example): SP terms of dL/dR, dq += entropy term, softmax backward
+__global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
+                                                       const float* __restrict__ logq, const float* __restrict__ dqp, float* __restrict__ dz,
+                                                       float* __restrict__ dzsum_part, int B, int K, int NK, int NS, int d, int dp,
+                                                       int hasSP, float ent_coef) {
+    extern __shared__ float dzs[];     // [8][K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 8 + warp;
+    if (b < B) {
+        float* evb = ev + (size_t)b * E_NV * dp;
+        if (hasSP) {
+            const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
+            for (int j = lane; j < d; j += 32) {
+                evb[E_GA1 * dp + j] = fmaf(gp + g2, evb[E_C1 * dp + j], evb[E_GA1 * dp + j]);
+                evb[E_GA2 * dp + j] = fmaf(gp + g1, evb[E_C2 * dp + j], evb[E_GA2 * dp + j]);
+            }
+        }
+        float dot = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            float v = 0.f;
+            for (int s = 0; s < NS; ++s) v += dqp[((size_t)s * B + b) * NK + k];
+            v = fmaf(ent_coef, logq[(size_t)b * K + k] + 1.f, v);
+            dzs[warp * K + k] = v;
+            dot = fmaf(q[(size_t)b * K + k], v, dot);
+        }
+        dot = warp_sum(dot);
+        for (int k = lane; k < K; k += 32) {
+            const float v = q[(size_t)b * K + k] * (dzs[warp * K + k] - dot);
+            dzs[warp * K + k] = v;
+            dz[(size_t)b * K + k] = v;
+        }
+    } else {
+        for (int k = lane; k < K; k += 32) dzs[warp * K + k] = 0.f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += dzs[w * K + k];
+        dzsum_part[(size_t)blockIdx.x * K + k] = s;
+    }
+}
+
 int tc_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
 
 }  // namespace
@@ -462,13 +911,30 @@ int tc_init(rae_engine* h) {
         return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(k_tc_bilinear): %s", cudaGetErrorString(e));
     RAE_TC_ATTR(32) RAE_TC_ATTR(64) RAE_TC_ATTR(128)
 #undef RAE_TC_ATTR
+    // backward (dq) operand: Cf^T chunks of 32 reduction rows, NK = relations padded to a multiple of 16
+    t.NK = (h->K + 15) & ~15;
+    t.n_chunks32 = t.n_rows_total / TC_NC;
+    t.NS2 = std::max(1, std::min(t.n_chunks32, h->num_sms / t.ntile));
+    t.smem_dq = (size_t)2 * (2 * 8 * TC_M * 16) + (size_t)2 * (2 * 8 * t.NK * 16) + 256;
+    if ((e = cudaMalloc((void**)&t.bop2, (size_t)t.n_chunks32 * 2 * 8 * t.NK * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.dqp, (size_t)t.NS2 * h->B * t.NK * sizeof(float))) != cudaSuccess)
+        return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
+    if ((e = cudaFuncSetAttribute(k_tc_dq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_dq)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tc_dc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_dq)) != cudaSuccess)
+        return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(k_tc_dq/dc): %s", cudaGetErrorString(e));
+    // dC: n-tiles of 128 rows, batch split so that the grid fills the SMs
+    t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
+    t.n_bchunks = (h->B + TC_NC - 1) / TC_NC;
+    t.NSb = std::max(1, std::min(t.n_bchunks, h->num_sms / t.n_ntiles));
+    if ((e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bchunks * 2 * 8 * t.NK * 16)) != cudaSuccess)
+        return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
     t.ready = true;
     return RAE_OK;
 }
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.pop); cudaFree(t.bop); cudaFree(t.vg); cudaFree(t.wp);
+    cudaFree(t.pop); cudaFree(t.bop); cudaFree(t.vg); cudaFree(t.wp); cudaFree(t.bop2); cudaFree(t.dqp); cudaFree(t.pop3);
     t = TcState{};
 }
 
@@ -479,7 +945,13 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_c<<<blocks, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
                                         t.n_rows_total, t.bop);
-    h->launches++;
+    {
+        const size_t total2 = (size_t)(t.n_rows_total / 4) * t.NK;
+        const int blocks2 = (int)std::min<size_t>((total2 + 255) / 256, (size_t)h->num_sms * 8);
+        k_tc_prep_ct<<<blocks2, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.NK, t.DP, t.n_bil_rows,
+                                              t.n_rows_total, t.bop2);
+    }
+    h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
@@ -489,6 +961,12 @@ int tc_prepare_p(rae_engine* h, cudaStream_t st) {
     const size_t total = (size_t)t.ntile * t.KQ * TC_M;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_p<<<blocks, 256, 0, st>>>(h->q, h->B, h->K, t.KQ, t.pop);
+    {
+        const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
+        const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
+        k_tc_prep_qt<<<blocks3, 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3);
+        h->launches++;
+    }
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -511,6 +989,41 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.NS, slotV, slotW);
     h->launches += 4;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+// backward on the tensor path: dL, dR (through the forward kernel with L := a, R := c), dq, softmax backward -> dz
+int tc_backward(rae_engine* h, cudaStream_t st) {
+    TcState& t = h->tc;
+    int rc = tc_contract(h, E_A, E_CV, E_GA1, E_GA2, false, st);
+    if (rc) return rc;
+    TcDqArgs p{};
+    p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.dqp = t.dqp;
+    p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
+    p.n_bil_rows = t.n_bil_rows; p.n_chunks32 = t.n_chunks32; p.NS = t.NS2;
+    k_tc_dq<<<t.ntile * t.NS2, TC_THREADS, t.smem_dq, st>>>(p);
+    const int blocks = (h->B + 7) / 8;
+    if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
+    h->dz_part_used = blocks;
+    k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
+                                                                  t.NK, t.NS2, h->d, h->dp, h->hasSP ? 1 : 0,
+                                                                  (float)(2.0 * h->cfg.alpha / h->Z));
+    h->launches += 2;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+// dC, dC1, dC2 partials on the tensor path (k_dense_finalize sums the NSb batch splits)
+int tc_grad_dense(rae_engine* h, cudaStream_t st) {
+    TcState& t = h->tc;
+    TcDcArgs p{};
+    p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.out = h->gC_part;
+    p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
+    p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
+    p.split_stride = (size_t)h->off_gWb;
+    k_tc_dc<<<t.n_ntiles * t.NSb, TC_THREADS, t.smem_dq, st>>>(p);
+    h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }

@@ -120,9 +120,17 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     RAE_PHASE();   // 4 scoring / loss / d cost / d score
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
     RAE_PHASE();   // 5 decoder backward
-    if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
+    if (h->use_tc) {
+        if ((rc = tc_backward(h, st))) return rc;
+    } else {
+        if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
+    }
     RAE_PHASE();   // 6 dense-parameter gradients
-    if ((rc = launch_grad_dense_simt(h, st))) return rc;
+    if (h->use_tc) {
+        if ((rc = tc_grad_dense(h, st))) return rc;
+    } else {
+        if ((rc = launch_grad_dense_simt(h, st))) return rc;
+    }
     if ((rc = launch_dense_finalize(h, st))) return rc;
     RAE_PHASE();   // 7 cost (uses the pre-update parameters for the regulariser value)
     if ((rc = launch_cost(h, st))) return rc;
@@ -325,6 +333,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
         const int max_by_batch = (h->B + 63) / 64;
         if (ns > max_by_batch) ns = max_by_batch;
         if (ns < 1) ns = 1;
+        if (h->use_tc) ns = h->tc.NSb;      // the tensor path splits the batch its own way
         h->gC_nsplit = ns;
         RAE_CREATE_RC(dev_alloc(h, &h->gC_part, (size_t)ns * (size_t)(dd + 2 * dk)));
     }

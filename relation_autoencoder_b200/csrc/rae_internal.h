@@ -72,6 +72,11 @@ struct TcState {
     float4* bop = nullptr; // B operand chunks [chunk][hi/lo][KQ][64]
     float* vg = nullptr;   // [2][B][dp]
     float* wp = nullptr;   // [NS][2][B][dp]
+    int NK = 0, n_chunks32 = 0, NS2 = 0; size_t smem_dq = 0;
+    float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
+    float* dqp = nullptr;   // [NS2][B][NK]
+    int n_ntiles = 0, n_bchunks = 0, NSb = 0;
+    float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
 };
 
 }  // namespace rae
@@ -162,6 +167,8 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st);
 int tc_prepare_p(rae_engine* h, cudaStream_t st);
 int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
+int tc_backward(rae_engine* h, cudaStream_t st);
+int tc_grad_dense(rae_engine* h, cudaStream_t st);
 
 // ---- sort / segment / updates (rae_update.cu) ----
 size_t segwork_temp_bytes(int64_t n);
