@@ -1,24 +1,30 @@
-// Kernel 2 (tensor-core contraction path, sm_100a): the [B,K] x [K, d*d] bilinear contraction on tcgen05 with TMEM
+// Kernel 2 (tensor-core contraction path, sm_100a): the bilinear contractions of the decoder on tcgen05 with TMEM
 // accumulators, fp32-accurate through an error-compensated 3xTF32 split.
 //
 //   reference: weighted_R = T.tensordot(relation_probs, R, axes=[[1],[2]])   learning/models/decoders/Bilinear.py:33
 //              weightedC  (same)                                             learning/models/decoders/BilinearPlusSP.py:37
 //              weightedC1/C2 = T.dot(relation_probs, C1.T / C2.T)            BilinearPlusSP.py:35-36, SelectionalPreferences.py:31-32
 //              batched_tensordot / batched_dot consumers                     Bilinear.py:58-59,68-69,78-79
+//              and T.grad through them                                       learning/Optimizers.py:27
 //
-// M_b = sum_k q_bk C[:,:,k] is a GEMM  P[B,K] . Cf^T[K, d*d]  whose [B, d*d] result must never reach HBM (64 KiB per
-// example at d = 128).  A CTA owns 128 examples (= the 128 TMEM lanes).  The B operand (rows n = (i,j) of Cf, K-major) is
-// streamed in chunks of 64 rows; each chunk is one 128x64 accumulator (64 TMEM columns, 4 stages) produced by 13 k-steps
-// x 3 MMAs (hi.hi + hi.lo + lo.hi of the TF32 hi/lo split: products carry ~2^-22 relative error, fp32-class).  Epilogue
-// warps read the accumulator rows back with tcgen05.ld and immediately fold them into v = M R and w = M^T L, so only
-// [B,d] vectors leave the SM.  The selectional-preference tensors C1, C2 are extra rows of the same B operand.
+// Three GEMM-shaped contractions per step, none of which may materialise [B, d*d] in HBM (64 KiB per example at d=128):
+//   forward / backward-recompute  M_b = sum_k q_bk C[:,:,k]      D[b, n]  = sum_k P[b,k]  Cf[n,k]     -> v = M R, w = M^T L
+//   backward dq                   dq_bk = <dM_b, C[:,:,k]>        D[b, k]  = sum_n G[b,n]  Cf[n,k]     (G = a R^T + L Y2^T, rank 2)
+//   backward dC                   dC[n,k] = sum_b dM_b[n] q_bk    D[n, k]  = sum_b G[b,n]  q[b,k]
+// fp32 parity: every operand x is split x = hi + lo (both TF32-exact) and each k-step issues hi.hi + hi.lo + lo.hi
+// (3 tcgen05.mma kind::tf32, fp32 accumulation in TMEM; dropped lo.lo ~ 2^-22 relative).
 //
-// Operands are pre-split and pre-arranged in global memory in the exact shared-memory image the MMA descriptors expect
-// (no-swizzle K-major canonical layout: float4 planes T[kq][row]; leading-dim byte offset = rows*16, stride-dim byte
-// offset = 128), so a stage is filled by ONE 1-D bulk copy (cp.async.bulk -> UBLKCP) completing on an mbarrier.
+// Operand placement is dictated by the measured shared-memory -> tensor-core feed (~64 B/cycle/SM): with M = 128 an SS
+// MMA re-reads 4 KB of A per 8-deep k-step and runs at a third of the math rate.  So the M-side (A) operand lives in
+// TMEM (TS mode): the threads that own a TMEM lane (= an example row b, or an output row n) write their row with
+// tcgen05.st - q rows once per CTA for the forward, the generated operand G chunk by chunk for the backward - and only the
+// small N-side (B) operand streams through shared memory.  B operands are pre-split and pre-arranged in HBM as the exact
+// shared-memory image of the no-swizzle K-major canonical layout (float4 planes T[kq][row]; LBO = rows*16 B, SBO = 128 B),
+// so a stage is filled by 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier.
 //
-// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..11 = epilogue
-// (two groups of 4 warps; group g takes the chunks with index parity g, warp w reads TMEM lanes 32*(w%4)..+31).
+// Warp roles (all kernels): warp 0 = bulk-copy producer, 1 = MMA issuer (warp-uniform loop, elect.sync lane issues),
+// 2 = TMEM allocator, 3 = idle, 4.. = row-owning workers (epilogue / operand generators); worker warp w touches TMEM
+// lanes 32*(w%4)..+31 as the hardware requires.
 #include <algorithm>
 
 #include "rae_common.cuh"
@@ -28,11 +34,14 @@ namespace rae {
 
 namespace {
 
-constexpr int TC_M = 128;          // examples per CTA (TMEM lanes)
-constexpr int TC_N = 64;           // B-operand rows per chunk (TMEM columns per accumulator stage)
-constexpr int TC_TSTAGES = 4;      // accumulator stages in TMEM
-constexpr int TC_BSTAGES = 2;      // B-operand smem stages
-constexpr int TC_THREADS = 384;    // 12 warps
+constexpr int TC_M = 128;          // rows per CTA (TMEM lanes)
+constexpr int TC_N = 64;           // forward: B-operand rows per chunk (TMEM columns per accumulator stage)
+constexpr int TC_TSTAGES = 4;      // forward: accumulator stages in TMEM
+constexpr int TC_BSTAGES = 4;      // B-operand smem stages
+constexpr int TC_NC = 32;          // backward: reduction rows per chunk (4 k-steps of 8)
+constexpr int TC_FWD_THREADS = 384;    // 4 control + 8 epilogue warps
+constexpr int TC_BWD_THREADS = 640;    // 4 control + 16 generator warps
+constexpr uint32_t TC_FWD_ACOL = 256;  // forward: first TMEM column of the resident P operand (hi, then lo)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,18 +73,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_pieces(uint8_t* dst_smem, const uint8_t* src_gmem, uint32_t bytes, uint64_t* bar) {
+    constexpr uint32_t PIECE = 8192;
+    for (uint32_t off = 0; off < bytes; off += PIECE) bulk_g2s(dst_smem + off, src_gmem + off, min(PIECE, bytes - off), bar);
+}
+// one lane of a converged warp (the loops around it stay warp-uniform, so descriptor math lives in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by one thread
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32 (TS mode: A rows = TMEM lanes, one 32-bit element per column)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread t = lane base + t)
@@ -95,6 +114,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 registers per thread -> 32 lanes x 8 columns of TMEM (thread t writes lane base + t)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
 // LBO = byte distance between the two 16-byte K-halves of one MMA k-step, SBO = byte distance between 8-row groups
@@ -106,6 +133,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
     return d;                   // layout_type = 0 (SWIZZLE_NONE), base_offset = 0
 }
+// descriptor with the start address advanced by `bytes` (the address field is the low 14 bits, in 16-byte units)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, dense, no negate
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -116,37 +145,38 @@ __device__ __forceinline__ float tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-
-// ------------------------------------------------------------------------------------------------------------
-// operand preparation
-// ------------------------------------------------------------------------------------------------------------
-// P operand: [tile][split hi/lo][kq][row 0..127] float4, rows = examples, 4 consecutive relations per float4
-__global__ void __launch_bounds__(256) k_tc_prep_p(const float* __restrict__ q, int B, int K, int KQ, float4* __restrict__ out) {
-    const int ntile = (B + TC_M - 1) / TC_M;
-    const size_t total = (size_t)ntile * KQ * TC_M;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(idx % TC_M);
-        const int kq = (int)((idx / TC_M) % KQ);
-        const int tile = (int)(idx / ((size_t)TC_M * KQ));
-        const int b = tile * TC_M + r;
-        float x[4];
+__device__ __forceinline__ void split8(const float (&x)[8], float (&hi)[8], float (&lo)[8]) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = 4 * kq + u;
-            x[u] = (b < B && k < K) ? q[(size_t)b * K + k] : 0.f;
-        }
-        float4 hi, lo;
-        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
-        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
-        float4* base = out + (size_t)tile * 2 * KQ * TC_M;
-        base[(size_t)kq * TC_M + r] = hi;
-        base[(size_t)(KQ + kq) * TC_M + r] = lo;
+    for (int u = 0; u < 8; ++u) {
+        hi[u] = tf32_hi(x[u]);
+        lo[u] = tf32_hi(x[u] - hi[u]);
     }
 }
+__device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& lo) {
+    hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
+    lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
+}
 
-// B operand: [chunk][split][kq][row 0..63] float4; row n of the operand = a [K]-vector of C / C1 / C2:
-//   n <  di*DP            : C[i, j, :] with i = n / DP, j = n % DP (zero row when i >= d or j >= d)
-//   then DP rows of C1[j,:] and DP rows of C2[j,:] (when the model has them)
+// row n of the dense operand Cf -> source [K]-vector (nullptr = zero padding row)
+//   n <  n_bil_rows : C[i, j, :] with i = n / DP, j = n % DP
+//   then DP rows of C1[j,:] and DP rows of C2[j,:]
+__device__ __forceinline__ const float* cf_row(const float* C, const float* C1, const float* C2, int d, int K, int DP,
+                                               int n_bil_rows, int n) {
+    if (n < n_bil_rows) {
+        const int i = n / DP, j = n - i * DP;
+        return (i < d && j < d && C != nullptr) ? C + ((size_t)i * d + j) * K : nullptr;
+    }
+    const int m = n - n_bil_rows;
+    const int which = m / DP, j = m - which * DP;
+    if (j >= d) return nullptr;
+    const float* src = which == 0 ? C1 : C2;
+    return src != nullptr ? src + (size_t)j * K : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// operand preparation (per step; the dense parameters change every step)
+// ------------------------------------------------------------------------------------------------------------
+// forward B operand: [chunk of 64 rows n][hi/lo][kq][row] float4, 4 consecutive relations per float4
 __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, const float* __restrict__ C1,
                                                    const float* __restrict__ C2, int d, int K, int KQ, int DP, int n_bil_rows,
                                                    int n_rows_total, float4* __restrict__ out) {
@@ -154,16 +184,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int kq = (int)(idx % KQ);
         const int n = (int)(idx / KQ);
-        const float* src = nullptr;
-        if (n < n_bil_rows) {
-            const int i = n / DP, j = n - i * DP;
-            if (i < d && j < d && C != nullptr) src = C + ((size_t)i * d + j) * K;
-        } else {
-            const int m = n - n_bil_rows;
-            const int which = m / DP, j = m - which * DP;
-            if (j < d) src = (which == 0 ? C1 : C2);
-            if (src != nullptr) src += (size_t)j * K;
-        }
+        const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, n);
         float x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -171,8 +192,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
             x[u] = (src != nullptr && k < K) ? src[k] : 0.f;
         }
         float4 hi, lo;
-        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
-        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
+        split4(x, hi, lo);
         const int chunk = n / TC_N, r = n - chunk * TC_N;
         float4* base = out + (size_t)chunk * 2 * KQ * TC_N;
         base[(size_t)kq * TC_N + r] = hi;
@@ -180,17 +200,63 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
     }
 }
 
+// dq B operand: Cf transposed, [chunk of 32 rows n][hi/lo][nq 0..7][krow 0..NK-1] float4 = (Cf[32c+4nq+0..3][krow])
+__global__ void __launch_bounds__(256) k_tc_prep_ct(const float* __restrict__ C, const float* __restrict__ C1,
+                                                    const float* __restrict__ C2, int d, int K, int NK, int DP, int n_bil_rows,
+                                                    int n_rows_total, float4* __restrict__ out) {
+    const size_t total = (size_t)(n_rows_total / 4) * NK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int krow = (int)(idx % NK);
+        const int nq_g = (int)(idx / NK);
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 4 * nq_g + u);
+            x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
+        }
+        float4 hi, lo;
+        split4(x, hi, lo);
+        const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
+        float4* base = out + (size_t)c32 * 2 * 8 * NK;
+        base[(size_t)nq * NK + krow] = hi;
+        base[(size_t)(8 + nq) * NK + krow] = lo;
+    }
+}
+
+// dC B operand: q transposed, [chunk of 32 examples][hi/lo][bq 0..7][krow 0..NK-1] float4 = (q[32c+4bq+0..3][krow])
+__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out) {
+    const int nbc = (B + TC_NC - 1) / TC_NC;
+    const size_t total = (size_t)nbc * 8 * NK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int krow = (int)(idx % NK);
+        const int bq = (int)((idx / NK) % 8);
+        const int bc = (int)(idx / ((size_t)8 * NK));
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = bc * TC_NC + 4 * bq + u;
+            x[u] = (b < B && krow < K) ? q[(size_t)b * K + krow] : 0.f;
+        }
+        float4 hi, lo;
+        split4(x, hi, lo);
+        float4* base = out + (size_t)bc * 2 * 8 * NK;
+        base[(size_t)bq * NK + krow] = hi;
+        base[(size_t)(8 + bq) * NK + krow] = lo;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// the contraction kernel
+// forward contraction (also used for the backward recompute with L := a, R := c)
+// TMEM map: accumulator stages [0,256) (4 x 64 columns), P operand hi at [256, 256+Kp), lo at [256+Kp, 256+2Kp)
 // ------------------------------------------------------------------------------------------------------------
 struct TcArgs {
-    const float4* pop;      // P operand tiles
+    const float* q;         // [B,K]
     const float4* bop;      // B operand chunks
     const float* ev;        // per-example vectors (L at slotL, R at slotR), row stride E_NV*dp
     float* ev_out;          // SP chunks write c1 / c2 here (E_C1 / E_C2)
     float* vg;              // [2][B][dp]   v partial per epilogue group
     float* wp;              // [NS][2][B][dp] w partial per (split, group)
-    int B, d, dp, KQ;
+    int B, K, d, dp, KQ;
     int slotL, slotR;
     int n_bil_chunks;       // chunks holding bilinear rows
     int n_sp_chunks;        // chunks holding C1/C2 rows (forward only)
@@ -198,16 +264,15 @@ struct TcArgs {
 };
 
 template <int DP>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
+__global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
-    const uint32_t A_BYTES = 2u * p.KQ * TC_M * 16u;
     const uint32_t B_BYTES = 2u * p.KQ * TC_N * 16u;
-    uint8_t* smA = smem_raw;
-    uint8_t* smB = smem_raw + A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + A_BYTES + TC_BSTAGES * B_BYTES);
-    uint64_t* a_full = bars;
+    const uint32_t Kp = 4u * p.KQ;                          // relations padded to a multiple of 8
+    uint8_t* smB = smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * B_BYTES);
+    uint64_t* a_full = bars;                                // 8 epilogue-warp arrivals: P operand is in TMEM
     uint64_t* b_full = bars + 1;
     uint64_t* b_empty = b_full + TC_BSTAGES;
     uint64_t* t_full = b_empty + TC_BSTAGES;
@@ -226,15 +291,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
     const int nit = c_end - c_begin;
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, 8);
         for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)(TC_TSTAGES * TC_N))
-                     : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -246,53 +309,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     }
     if (warp == 0) {
-        // ===== producer: one bulk copy for the resident P tile, one per B chunk =====
-        if (lane == 0 && nit > 0) {
-            mbar_expect_tx(a_full, A_BYTES);
-            bulk_g2s(smA, reinterpret_cast<const uint8_t*>(p.pop) + (size_t)tile * A_BYTES, A_BYTES, a_full);
+        // ===== producer =====
+        if (lane == 0) {
             for (int it = 0; it < nit; ++it) {
                 const int s = it % TC_BSTAGES;
                 const uint32_t ph = (it / TC_BSTAGES) & 1;
                 mbar_wait(&b_empty[s], ph ^ 1);
                 mbar_expect_tx(&b_full[s], B_BYTES);
-                bulk_g2s(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
-                         B_BYTES, &b_full[s]);
+                bulk_g2s_pieces(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
+                                B_BYTES, &b_full[s]);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && nit > 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+        if (nit > 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
-            const uint32_t a_hi = smem_u32(smA), a_lo = a_hi + p.KQ * TC_M * 16u;
+            const uint32_t a_hi = tmem_base + TC_FWD_ACOL, a_lo = a_hi + Kp;
+            uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
+#pragma unroll
+            for (int s = 0; s < TC_BSTAGES; ++s) {
+                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
+                dbh0[s] = make_desc(b_hi, TC_N * 16u, 128u);
+                dbl0[s] = make_desc(b_hi + p.KQ * TC_N * 16u, TC_N * 16u, 128u);
+            }
             const int ksteps = p.KQ / 2;
             mbar_wait(a_full, 0);
+            tc_fence_after();
             for (int it = 0; it < nit; ++it) {
                 const int s = it % TC_BSTAGES, ts = it % TC_TSTAGES;
                 const uint32_t ph = (it / TC_BSTAGES) & 1, tph = (it / TC_TSTAGES) & 1;
                 mbar_wait(&t_empty[ts], tph ^ 1);
                 mbar_wait(&b_full[s], ph);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES), b_lo = b_hi + p.KQ * TC_N * 16u;
                 const uint32_t dcol = tmem_base + (uint32_t)(ts * TC_N);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t ao = (uint32_t)(2 * ks) * TC_M * 16u, bo = (uint32_t)(2 * ks) * TC_N * 16u;
-                    const uint64_t dah = make_desc(a_hi + ao, TC_M * 16u, 128u), dal = make_desc(a_lo + ao, TC_M * 16u, 128u);
-                    const uint64_t dbh = make_desc(b_hi + bo, TC_N * 16u, 128u), dbl = make_desc(b_lo + bo, TC_N * 16u, 128u);
-                    tc_mma_tf32(dcol, dah, dbh, idesc, ks > 0 ? 1u : 0u);   // hi * hi
-                    tc_mma_tf32(dcol, dah, dbl, idesc, 1u);                 // hi * lo
-                    tc_mma_tf32(dcol, dal, dbh, idesc, 1u);                 // lo * hi
+                if (elect_one()) {
+                    uint64_t dbh = dbh0[s], dbl = dbl0[s];
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        tc_mma_tf32_ts(dcol, a_hi + 8u * ks, dbh, idesc, ks > 0 ? 1u : 0u);   // hi * hi
+                        tc_mma_tf32_ts(dcol, a_hi + 8u * ks, dbl, idesc, 1u);                 // hi * lo
+                        tc_mma_tf32_ts(dcol, a_lo + 8u * ks, dbh, idesc, 1u);                 // lo * hi
+                        dbh = desc_advance(dbh, 2u * TC_N * 16u);
+                        dbl = desc_advance(dbl, 2u * TC_N * 16u);
+                    }
+                    tc_commit(&b_empty[s]);     // smem stage reusable once these MMAs have read it
+                    tc_commit(&t_full[ts]);     // accumulator complete
                 }
-                tc_commit(&b_empty[s]);     // smem stage reusable once these MMAs have read it
-                tc_commit(&t_full[ts]);     // accumulator complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue =====
+        // ===== row-owning warps: P operand -> TMEM, then epilogue =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
         const int ew = warp - 4, g = ew >> 2, q4 = ew & 3;
         const int row = q4 * 32 + lane;
         const int b = tile * TC_M + row;
         const bool ok = b < p.B;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        {
+            // group 0 writes the hi part, group 1 the lo part of this row's q (TF32 split), 8 relations per store
+            const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
+            const uint32_t abase = lane_base + TC_FWD_ACOL + (g == 0 ? 0u : Kp);
+            for (uint32_t k0 = 0; k0 < Kp; k0 += 8) {
+                float x[8], hi[8], lo[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (ok && (int)(k0 + u) < p.K) ? qr[k0 + u] : 0.f;
+                split8(x, hi, lo);
+                if (g == 0) tc_st8(abase + k0, hi); else tc_st8(abase + k0, lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
         constexpr int RW = (DP >= 64) ? 64 : 32;      // columns of R / w held per thread
         const int jbase = (DP == 128) ? 64 * g : 0;
@@ -303,7 +391,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
             Rr[c] = (ok && j < p.d) ? evb[p.slotR * p.dp + j] : 0.f;
             Wr[c] = 0.f;
         }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         for (int it = g; it < nit; it += 2) {
             const int ts = it % TC_TSTAGES;
             const uint32_t tph = (it / TC_TSTAGES) & 1;
@@ -334,20 +421,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 }
                 if (bil) {
                     if (DP >= 64) {
+                        float v4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            vsum = fmaf(t[x], Rr[(32 * hf + x) % RW], vsum);
+                            v4[x & 3] = fmaf(t[x], Rr[(32 * hf + x) % RW], v4[x & 3]);
                             Wr[(32 * hf + x) % RW] = fmaf(t[x], L0, Wr[(32 * hf + x) % RW]);
                         }
+                        vsum += (v4[0] + v4[1]) + (v4[2] + v4[3]);
                     } else {
                         const float Lh = hf == 0 ? L0 : L1;
-                        float vh = 0.f;
+                        float v4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            vh = fmaf(t[x], Rr[x % RW], vh);
+                            v4[x & 3] = fmaf(t[x], Rr[x % RW], v4[x & 3]);
                             Wr[x % RW] = fmaf(t[x], Lh, Wr[x % RW]);
                         }
-                        if (ok && i0 + hf < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0 + hf] = vh;
+                        if (ok && i0 + hf < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0 + hf] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
                     }
                 } else if (ok) {
                     // selectional-preference rows: the accumulator row IS c1 / c2
@@ -384,8 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_bilinear(TcArgs p) {
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_TSTAGES * TC_N))
-                     : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -421,190 +509,215 @@ __global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward, dq[b,k] = sum_n G[b,n] Cf[n,k]  with the generated operand
-//   bilinear row n=(i,j): G = a_bi R_bj + L_bi Y2_bj   (dM_b = a R^T + L Y2^T, rank 2)
-//   C1 row j            : G = a_bj + G2_b L_bj         (d cost / d c1)
-//   C2 row j            : G = c_bj + G1_b R_bj         (d cost / d c2)
-// UMMA: M = 128 examples, N = NK (relations padded to 16), reduction over n in chunks of 32 rows.  The A operand is
-// produced by 8 generator warps straight into the canonical smem image (hi/lo split, fence.proxy.async, mbarrier), the B
-// operand (Cf transposed: K-major along n) is pre-arranged in HBM and bulk-copied.  One TMEM accumulator [128 x NK].
+// backward kernels: generated A operand in TMEM.
+// TMEM map: accumulator [0,128) (NK <= 128 columns used); A stage s: hi at [128 + 64 s, +32), lo at [128 + 64 s + 32, +32)
+// generated operand  G[b,n]:  bilinear row n=(i,j): a_bi R_bj + L_bi Y2_bj ;  C1 row j: a_bj + G2_b L_bj ;  C2 row j: c_bj + G1_b R_bj
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TC_NC = 32;          // reduction rows per chunk (8 float4 planes)
+constexpr uint32_t TC_BWD_ACOL = 128;
 
-__global__ void __launch_bounds__(256) k_tc_prep_ct(const float* __restrict__ C, const float* __restrict__ C1,
-                                                    const float* __restrict__ C2, int d, int K, int NK, int DP, int n_bil_rows,
-                                                    int n_rows_total, float4* __restrict__ out) {
-    // out[c32][split][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
-    const size_t total = (size_t)(n_rows_total / 4) * NK;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int krow = (int)(idx % NK);
-        const int nq_g = (int)(idx / NK);            // global quad index along n
-        float x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int n = 4 * nq_g + u;
-            const float* src = nullptr;
-            if (n < n_bil_rows) {
-                const int i = n / DP, j = n - i * DP;
-                if (i < d && j < d && C != nullptr) src = C + ((size_t)i * d + j) * K;
-            } else {
-                const int m = n - n_bil_rows;
-                const int which = m / DP, j = m - which * DP;
-                if (j < d) src = (which == 0 ? C1 : C2);
-                if (src != nullptr) src += (size_t)j * K;
-            }
-            x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
+// transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
+__global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
+                                                         float* __restrict__ LT) {
+    __shared__ float ta[32][33], tl[32][33];
+    const int b0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of 32
+    for (int r = ty; r < 32; r += 8) {
+        const int b = b0 + r, i = i0 + tx;
+        const bool in = b < B && i < d;
+        ta[r][tx] = in ? ev[((size_t)b * E_NV + E_A) * dp + i] : 0.f;
+        tl[r][tx] = in ? ev[((size_t)b * E_NV + E_L) * dp + i] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, b = b0 + tx;
+        if (i < dp && b < B) {
+            aT[(size_t)i * B + b] = ta[tx][r];
+            LT[(size_t)i * B + b] = tl[tx][r];
         }
-        float4 hi, lo;
-        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
-        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
-        const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
-        float4* base = out + (size_t)c32 * 2 * 8 * NK;
-        base[(size_t)nq * NK + krow] = hi;
-        base[(size_t)(8 + nq) * NK + krow] = lo;
     }
 }
 
 struct TcDqArgs {
     const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
-    const float* ev; const float* sc;
+    const float* ev; const float* sc; const float* aT; const float* LT;
     float* dqp;             // [NS][B][NK]
-    int B, d, dp, K, NK, DP;
+    int B, d, dp, K, NK;
     int n_bil_rows, n_chunks32, NS;
 };
 
-// the generated operand for 4 consecutive rows n = base..base+3 of chunk c32 and example row evb (zero beyond dp)
-__device__ __forceinline__ float4 gen_g4(const float* __restrict__ evb, const float* __restrict__ scb, int dp, int DP,
-                                         int n_bil_rows, int n, bool ok) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!ok) return g;
-    float s1, s2;
-    int sx, sy, j;
-    if (n < n_bil_rows) {
-        const int i = n / DP;
-        j = n - i * DP;
-        if (i >= dp) return g;
-        s1 = evb[E_A * dp + i]; s2 = evb[E_L * dp + i]; sx = E_R; sy = E_Y2;
-    } else {
-        const int m = n - n_bil_rows;
-        const int which = m / DP;
-        j = m - which * DP;
-        s1 = 1.f;
-        if (which == 0) { sx = E_A; s2 = scb[SC_G2]; sy = E_L; }
-        else { sx = E_CV; s2 = scb[SC_G1]; sy = E_R; }
-    }
-    if (j >= dp) return g;
-    const float4 x = *reinterpret_cast<const float4*>(evb + sx * dp + j);
-    const float4 y = *reinterpret_cast<const float4*>(evb + sy * dp + j);
-    g.x = fmaf(s1, x.x, s2 * y.x); g.y = fmaf(s1, x.y, s2 * y.y); g.z = fmaf(s1, x.z, s2 * y.z); g.w = fmaf(s1, x.w, s2 * y.w);
-    return g;
-}
+// shared skeleton pieces of the two backward kernels ------------------------------------------------------------
+struct BwdBars {
+    uint64_t* a_full; uint64_t* a_empty; uint64_t* b_full; uint64_t* b_empty; uint64_t* acc_full; uint32_t* tmem_slot;
+};
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dq(TcDqArgs p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
-    const uint32_t A_BYTES = 2u * 8u * TC_M * 16u;          // hi/lo x 8 planes x 128 rows
-    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
-    uint8_t* smA = smem_raw;
-    uint8_t* smB = smem_raw + 2 * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_BYTES + 2 * B_BYTES);
-    uint64_t* a_full = bars;            // [2] 256 generator arrivals
-    uint64_t* a_empty = bars + 2;       // [2] tcgen05.commit
-    uint64_t* b_full = bars + 4;        // [2] bulk-copy tx
-    uint64_t* b_empty = bars + 6;       // [2] tcgen05.commit
-    uint64_t* acc_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    const int per = (p.n_chunks32 + p.NS - 1) / p.NS;
-    const int c_begin = min(per * split, p.n_chunks32), c_end = min(per * (split + 1), p.n_chunks32);
-    const int nit = c_end - c_begin;
-
+__device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t B_BYTES, int warp, uint32_t& tmem_base) {
+    BwdBars br;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * B_BYTES);
+    br.a_full = bars;                         // [2] 16 generator-warp arrivals
+    br.a_empty = bars + 2;                    // [2] tcgen05.commit
+    br.b_full = bars + 4;                     // [TC_BSTAGES] bulk-copy tx
+    br.b_empty = br.b_full + TC_BSTAGES;      // [TC_BSTAGES] tcgen05.commit
+    br.acc_full = br.b_empty + TC_BSTAGES;
+    br.tmem_slot = reinterpret_cast<uint32_t*>(br.acc_full + 1);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&br.a_full[s], 16); mbar_init(&br.a_empty[s], 1); }
+        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&br.b_full[s], 1); mbar_init(&br.b_empty[s], 1); }
+        mbar_init(br.acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(br.tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    tmem_base = *br.tmem_slot;
+    return br;
+}
 
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < nit; ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&b_empty[s], ph ^ 1);
-                mbar_expect_tx(&b_full[s], B_BYTES);
-                bulk_g2s(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop2) + (size_t)(c_begin + it) * B_BYTES,
-                         B_BYTES, &b_full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && nit > 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, p.NK);
-            for (int it = 0; it < nit; ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&a_full[s], ph);
-                mbar_wait(&b_full[s], ph);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smA + (size_t)s * A_BYTES), a_lo = a_hi + 8u * TC_M * 16u;
-                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES), b_lo = b_hi + 8u * (uint32_t)p.NK * 16u;
+__device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, const uint8_t* src, uint32_t B_BYTES, int c_begin, int nit) {
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % TC_BSTAGES;
+        const uint32_t ph = (it / TC_BSTAGES) & 1;
+        mbar_wait(&br.b_empty[s], ph ^ 1);
+        mbar_expect_tx(&br.b_full[s], B_BYTES);
+        bulk_g2s_pieces(smB + (size_t)s * B_BYTES, src + (size_t)(c_begin + it) * B_BYTES, B_BYTES, &br.b_full[s]);
+    }
+}
+
+__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit) {
+    const uint32_t idesc = make_idesc_tf32(TC_M, NK);
+    uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ao = (uint32_t)(2 * ks) * TC_M * 16u, bo = (uint32_t)(2 * ks) * (uint32_t)p.NK * 16u;
-                    const uint64_t dah = make_desc(a_hi + ao, TC_M * 16u, 128u), dal = make_desc(a_lo + ao, TC_M * 16u, 128u);
-                    const uint64_t dbh = make_desc(b_hi + bo, (uint32_t)p.NK * 16u, 128u), dbl = make_desc(b_lo + bo, (uint32_t)p.NK * 16u, 128u);
-                    tc_mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                    tc_mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                }
-                tc_commit(&a_empty[s]);
-                tc_commit(&b_empty[s]);
+    for (int s = 0; s < TC_BSTAGES; ++s) {
+        const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
+        dbh0[s] = make_desc(b_hi, (uint32_t)NK * 16u, 128u);
+        dbl0[s] = make_desc(b_hi + 8u * (uint32_t)NK * 16u, (uint32_t)NK * 16u, 128u);
+    }
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % TC_BSTAGES, as = it & 1;
+        const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it >> 1) & 1;
+        mbar_wait(&br.a_full[as], aph);
+        mbar_wait(&br.b_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
+            uint64_t dbh = dbh0[s], dbl = dbl0[s];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbl, idesc, 1u);
+                tc_mma_tf32_ts(tmem_base, a_lo + 8u * ks, dbh, idesc, 1u);
+                dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
+                dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
             }
-            tc_commit(acc_full);
+            tc_commit(&br.a_empty[as]);
+            tc_commit(&br.b_empty[s]);
+            if (it == nit - 1) tc_commit(br.acc_full);
         }
+        __syncwarp();
+    }
+}
+
+// generator warp publishes its 8 columns of A stage `as`
+__device__ __forceinline__ void bwd_publish(const BwdBars& br, uint32_t lane_base, int as, int cg, const float (&g)[8], int lane) {
+    float hi[8], lo[8];
+    split8(g, hi, lo);
+    const uint32_t col = lane_base + TC_BWD_ACOL + 64u * as + 8u * cg;
+    tc_st8(col, hi);
+    tc_st8(col + 32u, lo);
+    tc_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&br.a_full[as]);
+}
+
+// dq: rows = examples.  Generator thread = (row b, octet cg of the chunk's 32 reduction rows); the R / Y2 values it needs
+// for every bilinear chunk are cached in registers (X, Y), a_bi / L_bi come coalesced from the transposed copies.
+template <int DP>
+__global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
+    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
+    uint8_t* smB = smem_raw;
+    uint32_t tmem_base;
+    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);
+    constexpr int JQ = DP / 32;                 // chunks per bilinear row i
+    // split the chunk range at row-i boundaries
+    const int per = ((p.n_chunks32 + p.NS - 1) / p.NS + JQ - 1) / JQ * JQ;
+    const int c_begin = min(per * split, p.n_chunks32), c_end = min(per * (split + 1), p.n_chunks32);
+    const int nit = c_end - c_begin;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    }
+    if (warp == 0) {
+        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), B_BYTES, c_begin, nit);
+    } else if (warp == 1) {
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit);
     } else if (warp >= 4) {
-        // ===== generators (8 warps): thread = (row, half of the chunk's 8 planes) =====
-        const int gt = threadIdx.x - 128;
-        const int row = gt & 127, half = gt >> 7;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column octet
+        const int row = q4 * 32 + lane;
         const int b = tile * TC_M + row;
         const bool ok = b < p.B;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
         const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
-        for (int it = 0; it < nit; ++it) {
-            const int s = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const int n0 = (c_begin + it) * TC_NC + 16 * half;
-            float4 g[4];
+        // register cache: for chunk jq of a row i this thread needs j = 32 jq + 8 cg + 0..7
+        float X[JQ][8], Y[JQ][8];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) g[qd] = gen_g4(evb, scb, p.dp, p.DP, p.n_bil_rows, n0 + 4 * qd, ok);
-            mbar_wait(&a_empty[s], ph ^ 1);
-            float4* ah = reinterpret_cast<float4*>(smA + (size_t)s * A_BYTES);
-            float4* al = ah + 8 * TC_M;
+        for (int jq = 0; jq < JQ; ++jq)
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                float4 hi, lo;
-                hi.x = tf32_hi(g[qd].x); hi.y = tf32_hi(g[qd].y); hi.z = tf32_hi(g[qd].z); hi.w = tf32_hi(g[qd].w);
-                lo.x = tf32_hi(g[qd].x - hi.x); lo.y = tf32_hi(g[qd].y - hi.y); lo.z = tf32_hi(g[qd].z - hi.z); lo.w = tf32_hi(g[qd].w - hi.w);
-                ah[(4 * half + qd) * TC_M + row] = hi;
-                al[(4 * half + qd) * TC_M + row] = lo;
+            for (int u = 0; u < 8; ++u) {
+                const int j = 32 * jq + 8 * cg + u;
+                const bool in = ok && j < p.dp;
+                X[jq][u] = in ? evb[E_R * p.dp + j] : 0.f;
+                Y[jq][u] = in ? evb[E_Y2 * p.dp + j] : 0.f;
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA (async proxy)
-            mbar_arrive(&a_full[s]);
+        const int n_bil_chunks = p.n_bil_rows / TC_NC;
+        float ai = 0.f, li = 0.f;
+        for (int it = 0; it < nit; ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int c = c_begin + it;
+            float g[8];
+            if (c < n_bil_chunks) {
+                const int i = c / JQ, jq = c - i * JQ;
+                if (jq == 0 || it == 0) {
+                    ai = (ok && i < p.dp) ? p.aT[(size_t)i * p.B + b] : 0.f;
+                    li = (ok && i < p.dp) ? p.LT[(size_t)i * p.B + b] : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < JQ; ++q)
+                    if (q == jq) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) g[u] = fmaf(ai, X[q][u], li * Y[q][u]);
+                    }
+            } else {
+                // selectional-preference rows (a few chunks per tile): direct loads
+                const int m = c * TC_NC - p.n_bil_rows;
+                const int which = m / DP, j0 = m - which * DP + 8 * cg;
+                const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
+                const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    g[u] = (ok && j < p.dp) ? fmaf(s2, evb[sy * p.dp + j], evb[sx * p.dp + j]) : 0.f;
+                }
+            }
+            mbar_wait(&br.a_empty[as], aph ^ 1);
+            tc_fence_after();
+            bwd_publish(br, lane_base, as, cg, g, lane);
         }
-        if (warp < 8) {
+        if (gw < 4) {
             // ===== epilogue: accumulator row -> dq partial =====
             if (nit > 0) {
-                mbar_wait(acc_full, 0);
+                mbar_wait(br.acc_full, 0);
                 tc_fence_after();
             }
-            const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             float* o = p.dqp + ((size_t)split * p.B + (ok ? b : 0)) * p.NK;
             for (int c0 = 0; c0 < p.NK; c0 += 32) {
                 float t[32];
@@ -626,40 +739,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dq(TcDqArgs p) {
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// backward, dense-parameter gradients: dCf[n,k] = sum_b G[b,n] q[b,k]   (dC, dC1, dC2 in one operand)
-// UMMA: M = 128 rows n (one CTA owns an n-tile), N = NK, reduction over the examples in chunks of 32.  The A operand is
-// G^T generated in shared memory (planes over 4 consecutive examples), the B operand q^T is pre-arranged and bulk-copied.
-// The batch range can be split over CTAs (split-K); partial tiles land in gC_part[split] and are summed in fixed order
-// by k_dense_finalize.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out) {
-    // out[bc][split][bq 0..7][krow 0..NK-1] = (q[32bc+4bq+0..3][krow])
-    const int nbc = (B + TC_NC - 1) / TC_NC;
-    const size_t total = (size_t)nbc * 8 * NK;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int krow = (int)(idx % NK);
-        const int bq = (int)((idx / NK) % 8);
-        const int bc = (int)(idx / ((size_t)8 * NK));
-        float x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int b = bc * TC_NC + 4 * bq + u;
-            x[u] = (b < B && krow < K) ? q[(size_t)b * K + krow] : 0.f;
-        }
-        float4 hi, lo;
-        hi.x = tf32_hi(x[0]); hi.y = tf32_hi(x[1]); hi.z = tf32_hi(x[2]); hi.w = tf32_hi(x[3]);
-        lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
-        float4* base = out + (size_t)bc * 2 * 8 * NK;
-        base[(size_t)bq * NK + krow] = hi;
-        base[(size_t)(8 + bq) * NK + krow] = lo;
-    }
-}
-
+// dC: rows = operand rows n (one CTA per 128-row tile, batch range split NSb ways), reduction over examples.
 struct TcDcArgs {
     const float4* pop3;     // q^T chunks [bc][hi/lo][8][NK]
     const float* ev; const float* sc;
@@ -669,80 +753,31 @@ struct TcDcArgs {
     size_t split_stride;    // units*d*K
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dc(TcDcArgs p) {
+__global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile = blockIdx.x / p.NSb, split = blockIdx.x - ntile * p.NSb;
-    const uint32_t A_BYTES = 2u * 8u * TC_M * 16u;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
-    uint8_t* smA = smem_raw;
-    uint8_t* smB = smem_raw + 2 * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_BYTES + 2 * B_BYTES);
-    uint64_t* a_full = bars;
-    uint64_t* a_empty = bars + 2;
-    uint64_t* b_full = bars + 4;
-    uint64_t* b_empty = bars + 6;
-    uint64_t* acc_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint8_t* smB = smem_raw;
+    uint32_t tmem_base;
+    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);
     const int per = (p.n_bchunks + p.NSb - 1) / p.NSb;
     const int c_begin = min(per * split, p.n_bchunks), c_end = min(per * (split + 1), p.n_bchunks);
     const int nit = c_end - c_begin;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(acc_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
     if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < nit; ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&b_empty[s], ph ^ 1);
-                mbar_expect_tx(&b_full[s], B_BYTES);
-                bulk_g2s(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.pop3) + (size_t)(c_begin + it) * B_BYTES,
-                         B_BYTES, &b_full[s]);
-            }
-        }
+        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit);
     } else if (warp == 1) {
-        if (lane == 0 && nit > 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, p.NK);
-            for (int it = 0; it < nit; ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&a_full[s], ph);
-                mbar_wait(&b_full[s], ph);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smA + (size_t)s * A_BYTES), a_lo = a_hi + 8u * TC_M * 16u;
-                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES), b_lo = b_hi + 8u * (uint32_t)p.NK * 16u;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ao = (uint32_t)(2 * ks) * TC_M * 16u, bo = (uint32_t)(2 * ks) * (uint32_t)p.NK * 16u;
-                    const uint64_t dah = make_desc(a_hi + ao, TC_M * 16u, 128u), dal = make_desc(a_lo + ao, TC_M * 16u, 128u);
-                    const uint64_t dbh = make_desc(b_hi + bo, (uint32_t)p.NK * 16u, 128u), dbl = make_desc(b_lo + bo, (uint32_t)p.NK * 16u, 128u);
-                    tc_mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                    tc_mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                }
-                tc_commit(&a_empty[s]);
-                tc_commit(&b_empty[s]);
-            }
-            tc_commit(acc_full);
-        }
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit);
     } else if (warp >= 4) {
-        // ===== generators: thread = (row n of the tile, half of the chunk's examples) =====
-        const int gt = threadIdx.x - 128;
-        const int row = gt & 127, half = gt >> 7;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
+        const int row = q4 * 32 + lane;
         const int n = ntile * TC_M + row;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         // decode the row once: g(b) = P1(b) * X(b) + P2(b) * Y(b)
         int type = -1, i = 0, j = 0;          // -1: padding row (zero)
         if (n < p.n_bil_rows) {
@@ -755,48 +790,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dc(TcDcArgs p) {
             if (j < p.d) type = 1 + which;
         }
         const size_t estride = (size_t)E_NV * p.dp;
-        int oP1, oX, oP2, oY;                 // float offsets inside an example's ev block (type 0) ...
+        int oP1 = 0, oX, oP2, oY;
         if (type == 0) { oP1 = E_A * p.dp + i; oX = E_R * p.dp + j; oP2 = E_L * p.dp + i; oY = E_Y2 * p.dp + j; }
-        else if (type == 1) { oP1 = -1; oX = E_A * p.dp + j; oP2 = SC_G2; oY = E_L * p.dp + j; }
-        else { oP1 = -1; oX = E_CV * p.dp + j; oP2 = SC_G1; oY = E_R * p.dp + j; }
+        else if (type == 1) { oX = E_A * p.dp + j; oP2 = SC_G2; oY = E_L * p.dp + j; }
+        else { oX = E_CV * p.dp + j; oP2 = SC_G1; oY = E_R * p.dp + j; }
+        if (type < 0) { oX = 0; oY = 0; oP2 = 0; }
         for (int it = 0; it < nit; ++it) {
-            const int s = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const int b0 = (c_begin + it) * TC_NC + 16 * half;
-            float g[16];
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int b0 = (c_begin + it) * TC_NC + 8 * cg;
+            // batched loads first (clamped addresses), arithmetic after: 32 independent loads in flight
+            float p1[8], p2[8], xv[8], yv[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int b = b0 + e;
-                float v = 0.f;
-                if (type >= 0 && b < p.B) {
-                    const float* evb = p.ev + (size_t)b * estride;
-                    const float p1 = (type == 0) ? evb[oP1] : 1.f;
-                    const float p2 = (type == 0) ? evb[oP2] : p.sc[(size_t)b * SC_N + oP2];
-                    v = fmaf(p1, evb[oX], p2 * evb[oY]);
-                }
-                g[e] = v;
+            for (int u = 0; u < 8; ++u) {
+                const int b = min(b0 + u, p.B - 1);
+                const float* evb = p.ev + (size_t)b * estride;
+                xv[u] = evb[oX];
+                yv[u] = evb[oY];
+                p1[u] = (type == 0) ? evb[oP1] : 1.f;
+                p2[u] = (type == 0) ? evb[oP2] : p.sc[(size_t)b * SC_N + oP2];
             }
-            mbar_wait(&a_empty[s], ph ^ 1);
-            float4* ah = reinterpret_cast<float4*>(smA + (size_t)s * A_BYTES);
-            float4* al = ah + 8 * TC_M;
+            float g[8];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                float4 hi, lo;
-                hi.x = tf32_hi(g[4 * qd]); hi.y = tf32_hi(g[4 * qd + 1]); hi.z = tf32_hi(g[4 * qd + 2]); hi.w = tf32_hi(g[4 * qd + 3]);
-                lo.x = tf32_hi(g[4 * qd] - hi.x); lo.y = tf32_hi(g[4 * qd + 1] - hi.y);
-                lo.z = tf32_hi(g[4 * qd + 2] - hi.z); lo.w = tf32_hi(g[4 * qd + 3] - hi.w);
-                ah[(4 * half + qd) * TC_M + row] = hi;
-                al[(4 * half + qd) * TC_M + row] = lo;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&a_full[s]);
+            for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], xv[u], p2[u] * yv[u]) : 0.f;
+            mbar_wait(&br.a_empty[as], aph ^ 1);
+            tc_fence_after();
+            bwd_publish(br, lane_base, as, cg, g, lane);
         }
-        if (warp < 8) {
+        if (gw < 4) {
             if (nit > 0) {
-                mbar_wait(acc_full, 0);
+                mbar_wait(br.acc_full, 0);
                 tc_fence_after();
             }
-            const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             // destination inside the split's block: units are [bilinear rows i][C1][C2], each [d][K]
             size_t off = 0;
             if (type == 0) off = ((size_t)i * p.d + j) * p.K;
@@ -822,7 +847,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_dc(TcDcArgs p) {
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
@@ -873,14 +898,13 @@ int tc_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
 
 }  // namespace
 
-// shapes the tensor path handles: 16 < d <= 128 (padded to 32/64/128 columns per row) and K <= 104 (one resident P tile)
+// shapes the tensor path handles: 16 < d <= 128 (padded to 32/64/128 columns per row) and K <= 104 (P operand resident
+// in TMEM next to the accumulators)
 int tc_supported(const rae_engine* h) {
     if (!h->hasM) return 0;
     if (h->d <= 16 || h->d > 128) return 0;
     if (h->K > 104) return 0;
-    const int KQ = 2 * ((h->K + 7) / 8);
-    const size_t smem = (size_t)2 * KQ * TC_M * 16 + (size_t)TC_BSTAGES * 2 * KQ * TC_N * 16 + 256;
-    return smem <= (size_t)h->max_smem_optin;
+    return 1;
 }
 
 int tc_init(rae_engine* h) {
@@ -899,74 +923,65 @@ int tc_init(rae_engine* h) {
     if (ns > pairs) ns = pairs;
     if (ns < 1) ns = 1;
     t.NS = ns;
-    t.smem = (size_t)2 * t.KQ * TC_M * 16 + (size_t)TC_BSTAGES * 2 * t.KQ * TC_N * 16 + 256;
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&t.pop, (size_t)t.ntile * 2 * t.KQ * TC_M * 16)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.bop, (size_t)(t.n_bil_chunks + t.n_sp_chunks) * 2 * t.KQ * TC_N * 16)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.vg, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.wp, (size_t)2 * t.NS * h->B * h->dp * sizeof(float))) != cudaSuccess)
-        return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
-#define RAE_TC_ATTR(DPV)                                                                                                   \
-    if ((e = cudaFuncSetAttribute(k_tc_bilinear<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)) != cudaSuccess) \
-        return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(k_tc_bilinear): %s", cudaGetErrorString(e));
-    RAE_TC_ATTR(32) RAE_TC_ATTR(64) RAE_TC_ATTR(128)
-#undef RAE_TC_ATTR
-    // backward (dq) operand: Cf^T chunks of 32 reduction rows, NK = relations padded to a multiple of 16
+    t.smem = (size_t)TC_BSTAGES * 2 * t.KQ * TC_N * 16 + 256;
+    // backward operands: NK = relations padded to a multiple of 16, reduction chunks of 32 rows
     t.NK = (h->K + 15) & ~15;
     t.n_chunks32 = t.n_rows_total / TC_NC;
-    t.NS2 = std::max(1, std::min(t.n_chunks32, h->num_sms / t.ntile));
-    t.smem_dq = (size_t)2 * (2 * 8 * TC_M * 16) + (size_t)2 * (2 * 8 * t.NK * 16) + 256;
-    if ((e = cudaMalloc((void**)&t.bop2, (size_t)t.n_chunks32 * 2 * 8 * t.NK * 16)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.dqp, (size_t)t.NS2 * h->B * t.NK * sizeof(float))) != cudaSuccess)
-        return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
-    if ((e = cudaFuncSetAttribute(k_tc_dq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_dq)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_tc_dc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_dq)) != cudaSuccess)
-        return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(k_tc_dq/dc): %s", cudaGetErrorString(e));
-    // dC: n-tiles of 128 rows, batch split so that the grid fills the SMs
+    t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), h->num_sms / t.ntile));
+    t.smem_dq = (size_t)TC_BSTAGES * (2 * 8 * t.NK * 16) + 256;
     t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
     t.n_bchunks = (h->B + TC_NC - 1) / TC_NC;
     t.NSb = std::max(1, std::min(t.n_bchunks, h->num_sms / t.n_ntiles));
-    if ((e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bchunks * 2 * 8 * t.NK * 16)) != cudaSuccess)
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&t.bop, (size_t)(t.n_bil_chunks + t.n_sp_chunks) * 2 * t.KQ * TC_N * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.vg, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.wp, (size_t)2 * t.NS * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.bop2, (size_t)t.n_chunks32 * 2 * 8 * t.NK * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.dqp, (size_t)t.NS2 * h->B * t.NK * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bchunks * 2 * 8 * t.NK * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.aT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.LT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess)
         return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
+#define RAE_TC_ATTR(KERN, BYTES)                                                                                     \
+    if ((e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) \
+        return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(" #KERN "): %s", cudaGetErrorString(e));
+    RAE_TC_ATTR(k_tc_bilinear<32>, t.smem) RAE_TC_ATTR(k_tc_bilinear<64>, t.smem) RAE_TC_ATTR(k_tc_bilinear<128>, t.smem)
+    RAE_TC_ATTR(k_tc_dq<32>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<64>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<128>, t.smem_dq)
+    RAE_TC_ATTR(k_tc_dc, t.smem_dq)
+#undef RAE_TC_ATTR
     t.ready = true;
     return RAE_OK;
 }
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.pop); cudaFree(t.bop); cudaFree(t.vg); cudaFree(t.wp); cudaFree(t.bop2); cudaFree(t.dqp); cudaFree(t.pop3);
+    cudaFree(t.bop); cudaFree(t.vg); cudaFree(t.wp); cudaFree(t.bop2); cudaFree(t.dqp); cudaFree(t.pop3);
+    cudaFree(t.aT); cudaFree(t.LT);
     t = TcState{};
 }
 
-// pre-split / pre-arrange the dense operand (call whenever C, C1, C2 changed, i.e. once per step)
+// pre-split / pre-arrange the dense operands (call whenever C, C1, C2 changed, i.e. once per step)
 int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     const size_t total = (size_t)t.n_rows_total * t.KQ;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_c<<<blocks, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
                                         t.n_rows_total, t.bop);
-    {
-        const size_t total2 = (size_t)(t.n_rows_total / 4) * t.NK;
-        const int blocks2 = (int)std::min<size_t>((total2 + 255) / 256, (size_t)h->num_sms * 8);
-        k_tc_prep_ct<<<blocks2, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.NK, t.DP, t.n_bil_rows,
-                                              t.n_rows_total, t.bop2);
-    }
+    const size_t total2 = (size_t)(t.n_rows_total / 4) * t.NK;
+    const int blocks2 = (int)std::min<size_t>((total2 + 255) / 256, (size_t)h->num_sms * 8);
+    k_tc_prep_ct<<<blocks2, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.NK, t.DP, t.n_bil_rows,
+                                          t.n_rows_total, t.bop2);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
+// q-dependent operand of the dC contraction (after the encoder)
 int tc_prepare_p(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    const size_t total = (size_t)t.ntile * t.KQ * TC_M;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_p<<<blocks, 256, 0, st>>>(h->q, h->B, h->K, t.KQ, t.pop);
-    {
-        const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
-        const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-        k_tc_prep_qt<<<blocks3, 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3);
-        h->launches++;
-    }
+    const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
+    const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
+    k_tc_prep_qt<<<blocks3, 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -976,15 +991,15 @@ int tc_prepare_p(rae_engine* h, cudaStream_t st) {
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st) {
     TcState& t = h->tc;
     TcArgs p{};
-    p.pop = t.pop; p.bop = t.bop; p.ev = h->ev; p.ev_out = h->ev; p.vg = t.vg; p.wp = t.wp;
-    p.B = h->B; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
+    p.q = h->q; p.bop = t.bop; p.ev = h->ev; p.ev_out = h->ev; p.vg = t.vg; p.wp = t.wp;
+    p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
     p.n_bil_chunks = t.n_bil_chunks; p.n_sp_chunks = with_sp ? t.n_sp_chunks : 0; p.NS = t.NS;
     RAE_CUDA(h, cudaMemsetAsync(t.vg, 0, (size_t)2 * h->B * h->dp * sizeof(float), st));
     RAE_CUDA(h, cudaMemsetAsync(t.wp, 0, (size_t)2 * t.NS * h->B * h->dp * sizeof(float), st));
     const int grid = t.ntile * t.NS;
-    if (t.DP == 32) k_tc_bilinear<32><<<grid, TC_THREADS, t.smem, st>>>(p);
-    else if (t.DP == 64) k_tc_bilinear<64><<<grid, TC_THREADS, t.smem, st>>>(p);
-    else k_tc_bilinear<128><<<grid, TC_THREADS, t.smem, st>>>(p);
+    if (t.DP == 32) k_tc_bilinear<32><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
+    else if (t.DP == 64) k_tc_bilinear<64><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
+    else k_tc_bilinear<128><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
     const size_t total = (size_t)h->B * h->dp;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.NS, slotV, slotW);
@@ -998,18 +1013,22 @@ int tc_backward(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     int rc = tc_contract(h, E_A, E_CV, E_GA1, E_GA2, false, st);
     if (rc) return rc;
+    k_tc_transpose_al<<<dim3((h->B + 31) / 32, (h->dp + 31) / 32), 256, 0, st>>>(h->ev, h->B, h->d, h->dp, t.aT, t.LT);
     TcDqArgs p{};
-    p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.dqp = t.dqp;
-    p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
+    p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.dqp = t.dqp;
+    p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
     p.n_bil_rows = t.n_bil_rows; p.n_chunks32 = t.n_chunks32; p.NS = t.NS2;
-    k_tc_dq<<<t.ntile * t.NS2, TC_THREADS, t.smem_dq, st>>>(p);
+    const int grid = t.ntile * t.NS2;
+    if (t.DP == 32) k_tc_dq<32><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    else if (t.DP == 64) k_tc_dq<64><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    else k_tc_dq<128><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     const int blocks = (h->B + 7) / 8;
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
     k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
                                                                   t.NK, t.NS2, h->d, h->dp, h->hasSP ? 1 : 0,
                                                                   (float)(2.0 * h->cfg.alpha / h->Z));
-    h->launches += 2;
+    h->launches += 3;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
@@ -1022,7 +1041,7 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
     p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
     p.split_stride = (size_t)h->off_gWb;
-    k_tc_dc<<<t.n_ntiles * t.NSb, TC_THREADS, t.smem_dq, st>>>(p);
+    k_tc_dc<<<t.n_ntiles * t.NSb, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

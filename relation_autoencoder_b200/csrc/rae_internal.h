@@ -77,6 +77,7 @@ struct TcState {
     float* dqp = nullptr;   // [NS2][B][NK]
     int n_ntiles = 0, n_bchunks = 0, NSb = 0;
     float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
+    float* aT = nullptr; float* LT = nullptr;   // transposed a, L: [dp][B]
 };
 
 }  // namespace rae
