@@ -179,7 +179,29 @@ __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, 
 // forward B operand: [chunk of 64 rows n][hi/lo][kq][row] float4, 4 consecutive relations per float4
 __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, const float* __restrict__ C1,
                                                    const float* __restrict__ C2, int d, int K, int KQ, int DP, int n_bil_rows,
-                                                   int n_rows_total, float4* __restrict__ out) {
+                                                   int n_rows_total, float4* __restrict__ out, int NK, float4* __restrict__ out2) {
+    if (blockIdx.y == 1) {
+        // second half of the grid: the transposed operand of the dq contraction
+        // out2[c32][hi/lo][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
+        const size_t total2 = (size_t)(n_rows_total / 4) * NK;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (size_t)gridDim.x * blockDim.x) {
+            const int krow = (int)(idx % NK);
+            const int nq_g = (int)(idx / NK);
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 4 * nq_g + u);
+                x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
+            }
+            float4 hi, lo;
+            split4(x, hi, lo);
+            const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
+            float4* base = out2 + (size_t)c32 * 2 * 8 * NK;
+            base[(size_t)nq * NK + krow] = hi;
+            base[(size_t)(8 + nq) * NK + krow] = lo;
+        }
+        return;
+    }
     const size_t total = (size_t)n_rows_total * KQ;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int kq = (int)(idx % KQ);
@@ -224,7 +246,22 @@ __global__ void __launch_bounds__(256) k_tc_prep_ct(const float* __restrict__ C,
 }
 
 // dC B operand: q transposed, [chunk of 32 examples][hi/lo][bq 0..7][krow 0..NK-1] float4 = (q[32c+4bq+0..3][krow])
-__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out,
+                                                    const float* __restrict__ A, const int32_t* __restrict__ a1,
+                                                    const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev) {
+    if (blockIdx.y == 1) {
+        // second half of the grid: L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev, one warp per example
+        const int lane = threadIdx.x & 31;
+        for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
+            const int r1 = a1[b], r2 = quirk ? r1 : a2[b];
+            float* o = ev + (size_t)b * E_NV * dp;
+            for (int j = lane; j < d; j += 32) {
+                o[E_L * dp + j] = ld_nc(A + (size_t)r1 * d + j);
+                o[E_R * dp + j] = ld_nc(A + (size_t)r2 * d + j);
+            }
+        }
+        return;
+    }
     const int nbc = (B + TC_NC - 1) / TC_NC;
     const size_t total = (size_t)nbc * 8 * NK;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -477,17 +514,26 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     }
 }
 
-// v[b,:] = vg[0] + vg[1] ; w[b,:] = sum over (split, group) of wp  ->  ev slots (fixed order)
+// v[b,i]: DP=128 both epilogue groups hold a half-row partial; DP=64 group i%2 produced it; DP=32 group (i/2)%2.
+// w[b,j]: sum over splits of the group partials (DP=128: only group j/64 holds column j).  Nothing needs pre-zeroing.
 __global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vg, const float* __restrict__ wp, float* __restrict__ ev,
-                                                    int B, int d, int dp, int NS, int slotV, int slotW) {
+                                                    int B, int d, int dp, int DP, int NS, int slotV, int slotW) {
     const size_t total = (size_t)B * dp;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(idx % dp);
         const size_t b = idx / dp;
         if (j >= d) continue;
-        const float v = vg[idx] + vg[total + idx];
+        float v;
+        if (DP == 128) v = vg[idx] + vg[total + idx];
+        else if (DP == 64) v = vg[(size_t)(j & 1) * total + idx];
+        else v = vg[(size_t)((j >> 1) & 1) * total + idx];
         float w = 0.f;
-        for (int s = 0; s < 2 * NS; ++s) w += wp[(size_t)s * total + idx];
+        if (DP == 128) {
+            const int g = j >> 6;
+            for (int s = 0; s < NS; ++s) w += wp[(size_t)(2 * s + g) * total + idx];
+        } else {
+            for (int s = 0; s < 2 * NS; ++s) w += wp[(size_t)s * total + idx];
+        }
         ev[(b * E_NV + slotV) * dp + j] = v;
         ev[(b * E_NV + slotW) * dp + j] = w;
     }
@@ -965,23 +1011,20 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     const size_t total = (size_t)t.n_rows_total * t.KQ;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_c<<<blocks, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
-                                        t.n_rows_total, t.bop);
-    const size_t total2 = (size_t)(t.n_rows_total / 4) * t.NK;
-    const int blocks2 = (int)std::min<size_t>((total2 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_ct<<<blocks2, 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.NK, t.DP, t.n_bil_rows,
-                                          t.n_rows_total, t.bop2);
-    h->launches += 2;
+    k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
+                                                 t.n_rows_total, t.bop, t.NK, t.bop2);
+    h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
 // q-dependent operand of the dC contraction (after the encoder)
-int tc_prepare_p(rae_engine* h, cudaStream_t st) {
+int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st) {
     TcState& t = h->tc;
     const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<blocks3, 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3);
+    k_tc_prep_qt<<<dim3(blocks3, 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
+                                                   h->quirk ? 1 : 0, h->ev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -994,16 +1037,14 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
     p.q = h->q; p.bop = t.bop; p.ev = h->ev; p.ev_out = h->ev; p.vg = t.vg; p.wp = t.wp;
     p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
     p.n_bil_chunks = t.n_bil_chunks; p.n_sp_chunks = with_sp ? t.n_sp_chunks : 0; p.NS = t.NS;
-    RAE_CUDA(h, cudaMemsetAsync(t.vg, 0, (size_t)2 * h->B * h->dp * sizeof(float), st));
-    RAE_CUDA(h, cudaMemsetAsync(t.wp, 0, (size_t)2 * t.NS * h->B * h->dp * sizeof(float), st));
     const int grid = t.ntile * t.NS;
     if (t.DP == 32) k_tc_bilinear<32><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
     else if (t.DP == 64) k_tc_bilinear<64><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
     else k_tc_bilinear<128><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
     const size_t total = (size_t)h->B * h->dp;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.NS, slotV, slotW);
-    h->launches += 4;
+    k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.DP, t.NS, slotV, slotW);
+    h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }

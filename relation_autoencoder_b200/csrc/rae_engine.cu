@@ -95,24 +95,38 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_phase[phase], st));        \
         ++phase;                                                                       \
     } while (0)
+    // Independent branches run on two handle-owned side streams (forked from / joined into the caller's stream):
+    //   s1: entity keys + stable sort (needs only the indices) ... entity-row update
+    //   s2: W-row update
+    // while the caller's stream carries encoder -> decoder -> dense gradients -> cost -> dense update.
+    // Disabled when gradients are emitted densely (debug / regulariser) or per-phase profiling is on.
+    const bool overlap = !h->dense_w && !h->debug_dense && !h->profiling && h->s1 != nullptr;
+    cudaStream_t se = overlap ? h->s1 : st, sw = overlap ? h->s2 : st;
+    const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
+    if (overlap) {
+        RAE_CUDA(h, cudaEventRecord(h->ev_fork0, st));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_fork0, 0));
+        if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
+        if ((rc = sort_pairs(h, h->ent, n_occ, se, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
+    }
     RAE_PHASE();   // 0 encoder forward: q, log q, entropy
     if ((rc = launch_encoder_forward(h, indptr, indices, h->B, h->q, h->logq, h->sc + SC_ENT, nullptr, st))) return rc;
     RAE_PHASE();   // 1 entity occurrence keys -> stable sort -> segments (depends on the indices only)
-    const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
-    if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
-    if ((rc = sort_pairs(h, h->ent, n_occ, st))) return rc;
+    if (!overlap) {
+        if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+        if ((rc = sort_pairs(h, h->ent, n_occ, st, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
+    }
     RAE_PHASE();   // 2 feature sort (skipped when the per-batch transposed index was cached at bind time)
     if (f_keys_s == nullptr) {
         if ((rc = ensure_feat_capacity(h, nnz))) return rc;
         if ((rc = build_feature_keys(h, indptr, indices, st))) return rc;
-        if ((rc = sort_pairs(h, h->feat, nnz, st))) return rc;
+        if ((rc = sort_pairs(h, h->feat, nnz, st, h->cub_tmp, h->cub_bytes))) return rc;
         f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s;
     }
     RAE_PHASE();   // 3 decoder forward
     if (h->use_tc) {
         if ((rc = tc_prepare_c(h, st))) return rc;
-        if ((rc = tc_prepare_p(h, st))) return rc;
-        if ((rc = tc_gather_lr(h, a1, a2, st))) return rc;
+        if ((rc = tc_prepare_p(h, a1, a2, st))) return rc;
         if ((rc = tc_contract(h, E_L, E_R, E_V1, E_V2, true, st))) return rc;
     } else {
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
@@ -124,6 +138,16 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = tc_backward(h, st))) return rc;
     } else {
         if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
+    }
+    if (overlap) {
+        // dz and the per-example vectors are final: the sparse-row updates can start on their own streams
+        RAE_CUDA(h, cudaEventRecord(h->ev_fork1, st));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_fork1, 0));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork1, 0));
+        if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->emit_only, !h->emit_only, se))) return rc;
+        RAE_CUDA(h, cudaEventRecord(h->ev_join1, h->s1));
+        if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->emit_only, sw))) return rc;
+        RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
     }
     RAE_PHASE();   // 6 dense-parameter gradients
     if (h->use_tc) {
@@ -144,11 +168,19 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = launch_zero(h, h->gAb_dense, sizeof(float) * (size_t)h->cfg.N, st))) return rc;
     }
     RAE_PHASE();   // 8 sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
-    if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense || h->emit_only, !h->emit_only, st))) return rc;
+    if (!overlap) {
+        if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense || h->emit_only, !h->emit_only, st))) return rc;
+    }
     RAE_PHASE();   // 9
-    if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w && !h->emit_only, st))) return rc;
+    if (!overlap) {
+        if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w && !h->emit_only, st))) return rc;
+    }
     RAE_PHASE();   // 10
     if (finish_dense && (rc = launch_dense_apply(h, st))) return rc;
+    if (overlap) {
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
+    }
     RAE_PHASE();   // end
 #undef RAE_PHASE
     h->stats.nnz = nnz;
@@ -206,7 +238,7 @@ int build_feature_cache(rae_engine* h, cudaStream_t st) {
         const int64_t n = c.batch_off[b + 1] - c.batch_off[b];
         const int32_t* ipb = sp.indptr + b * h->B;
         if ((rc = build_feature_keys(h, ipb, sp.indices, st))) return rc;
-        if ((rc = sort_pairs(h, h->feat, n, st))) return rc;
+        if ((rc = sort_pairs(h, h->feat, n, st, h->cub_tmp, h->cub_bytes))) return rc;
         RAE_CUDA(h, cudaMemcpyAsync(c.keys_s + c.batch_off[b], h->feat.keys_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
         RAE_CUDA(h, cudaMemcpyAsync(c.vals_s + c.batch_off[b], h->feat.vals_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
     }
@@ -346,6 +378,14 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
     RAE_CREATE_RC(alloc_segwork(h, h->ent, n_occ, bits_for(cfg->N)));
     RAE_CREATE_RC(ensure_cub(h, n_occ));
+    h->ent_cub_bytes = segwork_temp_bytes(n_occ);
+    RAE_CREATE_CUDA(cudaMalloc(&h->ent_cub_tmp, h->ent_cub_bytes));
+    RAE_CREATE_CUDA(cudaStreamCreateWithFlags(&h->s1, cudaStreamNonBlocking));
+    RAE_CREATE_CUDA(cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork1, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join1, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
@@ -367,6 +407,13 @@ void rae_destroy(rae_engine* h) {
     cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev);
     cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
     if (h->ev_created) for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
+    if (h->s1) cudaStreamDestroy(h->s1);
+    if (h->s2) cudaStreamDestroy(h->s2);
+    if (h->ev_fork0) cudaEventDestroy(h->ev_fork0);
+    if (h->ev_fork1) cudaEventDestroy(h->ev_fork1);
+    if (h->ev_join1) cudaEventDestroy(h->ev_join1);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+    cudaFree(h->ent_cub_tmp);
     if (h->cost_pinned) cudaFreeHost(h->cost_pinned);
     if (h->pinned_neg) cudaFreeHost(h->pinned_neg);
     free_segwork(h->ent);
@@ -571,7 +618,7 @@ int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width
     if ((rc = build_row_keys(h, rows, n, st))) return rc;
     const int saved_bits = h->feat.key_bits;
     h->feat.key_bits = bits_for(n_table_rows);
-    rc = sort_pairs(h, h->feat, n, st);
+    rc = sort_pairs(h, h->feat, n, st, h->cub_tmp, h->cub_bytes);
     h->feat.key_bits = saved_bits;
     if (rc) return rc;
     return launch_rows_apply(h, table, acc, (int)width, h->feat.keys_s, h->feat.vals_s, grads, n, st);

@@ -121,6 +121,9 @@ struct rae_engine {
     rae::FeatureCache fcache;
     rae::TcState tc; bool use_tc;
     void* cub_tmp; size_t cub_bytes;
+    void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
+    cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
+    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2;
     // explicit-step staging
     int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
     int32_t* pinned_neg;                         // host pinned [2,S,B]
@@ -165,8 +168,7 @@ int tc_supported(const rae_engine* h);
 int tc_init(rae_engine* h);
 void tc_free(rae_engine* h);
 int tc_prepare_c(rae_engine* h, cudaStream_t st);
-int tc_prepare_p(rae_engine* h, cudaStream_t st);
-int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);
+int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // q^T operand + gather L, R
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
 int tc_backward(rae_engine* h, cudaStream_t st);
 int tc_grad_dense(rae_engine* h, cudaStream_t st);
@@ -176,7 +178,7 @@ size_t segwork_temp_bytes(int64_t n);
 int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
                       int64_t neg_ld, cudaStream_t st);
 int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indices, cudaStream_t st);
-int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st);                 // stable radix sort by row
+int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st, void* tmp, size_t tmp_bytes);   // stable radix sort by row
 int segment_heads(rae_engine* h, const uint32_t* keys_s, int64_t n, SegWork& w, cudaStream_t st);   // introspection
 int count_unique(rae_engine* h, const uint32_t* keys_s, int64_t n, int32_t* out_dev, cudaStream_t st);
 int build_feature_cache(rae_engine* h, cudaStream_t st);

@@ -918,12 +918,12 @@ int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indi
     return RAE_OK;
 }
 
-int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st) {
+int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st, void* tmp, size_t tmp_bytes) {
     if (n > w.capacity) return fail(h, RAE_EINVAL, "internal: sort workspace too small (%lld > %lld)", (long long)n, (long long)w.capacity);
     if (n <= 0) return RAE_OK;
-    size_t bytes = h->cub_bytes;
+    size_t bytes = tmp_bytes;
     // LSD radix sort is stable: equal rows keep ascending occurrence order == np.argsort(kind='stable')
-    RAE_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp, bytes, w.keys, w.keys_s, w.vals, w.vals_s, (int)n, 0,
+    RAE_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, bytes, w.keys, w.keys_s, w.vals, w.vals_s, (int)n, 0,
                                                 w.key_bits, st));
     h->launches += (w.key_bits + 7) / 8 + 2;
     return RAE_OK;
