@@ -46,53 +46,80 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md:70-72)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md:70-72): NVML polled from a thread
+    every ~2 ms (nvidia-smi -lms as a fallback, which is too slow for short regions)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, device_index=0, period_ms=20):
-        self.rows = []
-        self.proc = None
+    def __init__(self, device_index=0, period_s=0.002):
         self.dev = device_index
-        self.period = period_ms
+        self.period = period_s
+        self.sm, self.mask = [], 0
+        self.max_sm = None
+        self._stop = threading.Event()
+        self._t = None
+        self._nvml = None
+        self._h = None
+        self._smi = None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self._nvml = pynvml
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.dev)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self._h = self._handle()
+            self.max_sm = float(self._nvml.nvmlDeviceGetMaxClockInfo(self._h, self._nvml.NVML_CLOCK_SM))
+            self._t = threading.Thread(target=self._poll, daemon=True)
+            self._t.start()
         except Exception:
-            self.proc = None
+            self._h = None
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                              "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self._t = threading.Thread(target=self._read_smi, daemon=True)
+                self._t.start()
+            except Exception:
+                self._smi = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _read_smi(self):
+        for line in self._smi.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.sm.append(float(f[0]))
+                self.max_sm = float(f[1])
+                self.mask |= int(f[2], 16)
+            except Exception:
+                continue
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._smi is not None:
+            time.sleep(0.05)
+            self._smi.terminate()
+        if self._t is not None:
+            self._t.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "samples": 0, "reasons": ["no clock samples"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.max_sm,
+                "samples": len(self.sm), "reasons": sorted(name for name, bit in self.REASONS if self.mask & bit)}
 
 
 def _needed_examples(wl, steps, warmup, extra):
@@ -266,9 +293,11 @@ def run_ours(args, wl, rank, world, local_rank):
         phase_ms = acc
         st = eng.stats()
 
+    p_cpu = eng.get_params_numpy() if (world == 1 and not args.no_cpu_baseline) else None
+    eng.close()                      # collective for N > 1 (nobody unmaps peer memory while a peer may still read it)
+    if dist is not None:
+        dist.destroy_process_group()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
     pk = _peaks()
     ms_step = ms_dev / steps
@@ -300,7 +329,6 @@ def run_ours(args, wl, rank, world, local_rank):
         n_cpu = min(data.n // B, 3) * B
         sub = SY.SyntheticData(data.indptr[: n_cpu + 1], data.indices[: data.indptr[n_cpu]], data.args1[:n_cpu],
                                data.args2[:n_cpu], data.neg_cum, n_cpu)
-        p_cpu = eng.get_params_numpy()
         eps, sec, done = cpu_reference_steps(wl, sub, p_cpu, neg1[:, :n_cpu], neg2[:, :n_cpu], steps=6, warmup=1,
                                              budget_s=args.cpu_budget)
         eps_sp, sec_sp, done_sp = cpu_reference_steps(wl, sub, p_cpu, neg1[:, :n_cpu], neg2[:, :n_cpu], steps=6, warmup=1,
@@ -312,9 +340,6 @@ def run_ours(args, wl, rank, world, local_rank):
             "sparse_row_variant": {"value": eps_sp, "sec_per_step": sec_sp,
                                    "note": "same math, touched rows only (what a tuned CPU port would do)"}}
     print(json.dumps(line))
-    eng.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 def _dominant_roofline(wl, st, phase_ms, pk):

@@ -162,6 +162,43 @@ int rae_gather_rows(rae_engine* h, const float* table, int64_t width, const int3
 int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows, const float* grads,
                           int64_t n, int64_t n_table_rows, void* stream);
 
+/* ---- peer-memory data path over NVLink / NVSwitch (one process per GPU, one node) ----------------------------------
+ * The sharded tables and the per-rank compact gradient buffers live in cudaMalloc'ed memory exported with CUDA IPC, so a
+ * rank's kernels read its peers' rows DIRECTLY (no collective in the sparse data path): rae_fetch_rows gathers the rows a
+ * batch touches from their owner shards into the rank's compact tables; after the step (RAE_FLAG_EMIT_ONLY) and the
+ * dense all-reduce, rae_pull_apply lets every OWNER read the reduced gradient rows of its rows from all ranks' compact
+ * gradient buffers, sum them in rank order (deterministic) and apply the optimiser once per row.  The routing (which
+ * rows, which slots) depends only on the ids and is planned once per split / epoch by the host side. */
+#define RAE_MAX_PEERS 16
+#define RAE_IPC_HANDLE_BYTES 64
+/* zero-initialised device allocation + its IPC handle (handle_out: RAE_IPC_HANDLE_BYTES bytes, may be NULL) */
+int rae_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out);
+int rae_peer_free(void* ptr);
+/* map a peer process's allocation into this process (enables peer access lazily) / unmap it */
+int rae_peer_open(const void* handle, void** ptr_out);
+int rae_peer_close(void* ptr);
+/* out[i, :] = tables[ids[i] % world][(ids[i] / world) * width ...]   (tables: HOST array of `world` device pointers, the
+ * row-sharded table of every rank, own shard included; ids: device int32 global row ids) */
+int rae_fetch_rows(rae_engine* h, const void* const* tables, int32_t world, int64_t width, const int32_t* ids, int64_t n,
+                   float* out, void* stream);
+/* owner-side update of n_rows rows of `table` (local row indices rows_local[i]): g = sum over e in
+ * [ent_off[i], ent_off[i+1]) - in that order - of grads[ent_src[e]][ent_slot[e] * width ...], then the handle's optimiser
+ * rule (Optimizers.py:29-32 / :51) on table / acc.  grads: HOST array of `world` device pointers (every rank's compact
+ * gradient buffer of this table). */
+int rae_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows_local, const int32_t* ent_off,
+                   const int32_t* ent_src, const int32_t* ent_slot, int64_t n_rows, const void* const* grads, int32_t world,
+                   void* stream);
+/* first part of a step on batch `batch_index` of the BOUND train split (cached transposed feature index) with explicit
+ * device entity ids: args1/args2 [B], neg1/neg2 [S, neg_ld].  Like rae_train_step_begin_explicit, the dense optimiser
+ * update is left to rae_train_step_end. */
+int rae_train_step_begin(rae_engine* h, int64_t batch_index, const int32_t* args1, const int32_t* args2, const int32_t* neg1,
+                         const int32_t* neg2, int64_t neg_ld, void* stream);
+/* copy the last step's (local) cost into a DEVICE double (no synchronisation) */
+int rae_copy_cost(rae_engine* h, double* dst_device, void* stream);
+/* encoder on explicit device inputs (indptr has n_rows+1 entries; n_rows <= B): labels int64[n_rows], probs [n_rows, K] */
+int rae_label_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t n_rows, int64_t* labels,
+                       float* probs, void* stream);
+
 /* ---- func['label_<split>'] ------------------------------------------------------------------------------ */
 /* labels = argmax of the scores, first max wins (RelationClassifier.py:45-47); probs = softmax.  Device outputs. */
 int rae_label(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels, float* probs, void* stream);

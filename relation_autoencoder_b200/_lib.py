@@ -71,6 +71,15 @@ _SIGNATURES = {
     "rae_read_cost": (C.c_int, [_P, C.POINTER(C.c_double), _P]),
     "rae_gather_rows": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
     "rae_sparse_rows_apply": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P]),
+    "rae_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(_P), _P]),
+    "rae_peer_free": (C.c_int, [_P]),
+    "rae_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "rae_peer_close": (C.c_int, [_P]),
+    "rae_fetch_rows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int64, _P, _P]),
+    "rae_pull_apply": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P]),
+    "rae_train_step_begin": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
+    "rae_copy_cost": (C.c_int, [_P, _P, _P]),
+    "rae_label_explicit": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "rae_set_profiling": (C.c_int, [_P, C.c_int32]),
     "rae_get_phase_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rae_phase_name": (C.c_char_p, [C.c_int32]),

@@ -589,6 +589,38 @@ int rae_train_step_begin_explicit(rae_engine* h, const int32_t* indptr, const in
     return run_step(h, indptr, indices, nnz, args1, args2, neg1, neg2, neg_ld, nullptr, nullptr, (cudaStream_t)stream, false);
 }
 
+int rae_train_step_begin(rae_engine* h, int64_t batch_index, const int32_t* args1, const int32_t* args2, const int32_t* neg1,
+                         const int32_t* neg2, int64_t neg_ld, void* stream) {
+    int rc = check_ready(h, true, false);
+    if (rc) return rc;
+    if (!args1 || !args2 || ((!neg1 || !neg2) && h->S > 0)) return fail(h, RAE_EINVAL, "rae_train_step_begin: null pointer");
+    SplitBinding& sp = h->split[RAE_SPLIT_TRAIN];
+    const int64_t nb = sp.n_rows / h->B;
+    if (batch_index < 0 || batch_index >= nb) return fail(h, RAE_EINVAL, "batch_index %lld out of range [0,%lld)", (long long)batch_index, (long long)nb);
+    if (!h->fcache.valid) return fail(h, RAE_EINVAL, "rae_train_step_begin needs the cached feature index (do not set RAE_FLAG_NO_FEATURE_CACHE)");
+    const int64_t r0 = batch_index * h->B;
+    const FeatureCache& c = h->fcache;
+    const int64_t nnz = c.batch_off[batch_index + 1] - c.batch_off[batch_index];
+    return run_step(h, sp.indptr + r0, sp.indices, nnz, args1, args2, neg1, neg2, neg_ld, c.keys_s + c.batch_off[batch_index],
+                    c.vals_s + c.batch_off[batch_index], (cudaStream_t)stream, false);
+}
+
+int rae_copy_cost(rae_engine* h, double* dst_device, void* stream) {
+    if (!h || !dst_device) return RAE_EINVAL;
+    RAE_CUDA(h, cudaMemcpyAsync(dst_device, h->cost_dev, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return RAE_OK;
+}
+
+int rae_label_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t n_rows, int64_t* labels,
+                       float* probs, void* stream) {
+    if (!h) return RAE_EINVAL;
+    if (!h->params_bound) return fail(h, RAE_ENOTBOUND, "parameters are not bound (rae_bind_params)");
+    if (!indptr || !indices || !labels || !probs || n_rows < 0 || n_rows > h->B) return fail(h, RAE_EINVAL, "rae_label_explicit: bad argument");
+    h->launches = 0;
+    if (n_rows == 0) return RAE_OK;
+    return launch_encoder_forward(h, indptr, indices, (int)n_rows, probs, nullptr, nullptr, labels, (cudaStream_t)stream);
+}
+
 int rae_train_step_end(rae_engine* h, void* stream) {
     int rc = check_ready(h, false, false);
     if (rc) return rc;

@@ -191,6 +191,12 @@ int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const 
                       const float* grads, int64_t n, cudaStream_t st);
 int launch_gather_rows(rae_engine* h, const float* table, int64_t width, const int32_t* rows, int64_t n, float* out,
                        cudaStream_t st);
+// ---- peer-memory path (rae_peer.cu) ----
+int launch_fetch_rows(rae_engine* h, const void* const* tables, int world, int64_t width, const int32_t* ids, int64_t n,
+                      float* out, cudaStream_t st);
+int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows_local, const int32_t* ent_off,
+                      const int32_t* ent_src, const int32_t* ent_slot, int64_t n_rows, const void* const* grads, int world,
+                      cudaStream_t st);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser

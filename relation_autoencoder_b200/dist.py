@@ -3,16 +3,23 @@ counterpart; the partitioning follows from its objective: examples are independe
 a sum over examples divided by the global Z (learning/OieModel.py:90).
 
 * batch: every rank owns B examples of each global batch of world*B; Z and adj are global.
-* dense parameters C/R, C1, C2, Wb: replicated; local gradients are summed with ONE all-reduce per step (flat buffer),
-  then every rank applies the identical optimiser step (Optimizers.py:29-32).
+* dense parameters C/R, C1, C2, Wb: replicated; the local gradients are summed with ONE NCCL all-reduce per step (flat
+  buffer), then every rank applies the identical optimiser step (Optimizers.py:29-32).
 * sparse tables W[F,K], A[N,d], Ab[N] (+ AdaGrad accumulators): row-sharded, owner(row) = row mod world, local index =
-  row // world.  Per step a rank (1) receives the rows its batch touches from their owners (all-to-all) into compact
-  tables, (2) runs the fused step on the compact tables with RAE_FLAG_EMIT_ONLY (one reduced gradient row per touched
-  row, duplicates inside the rank already summed), (3) returns the gradient rows to the owners (all-to-all), and (4) each
-  owner stable-sorts the received (row, gradient) pairs - input order is source-rank major - segment-reduces them and
-  applies ONE optimiser RMW per row.  Fixed orders everywhere: bitwise reproducible for a given world size.
-* routing (which rows, to whom) depends only on the ids: plans are built once per batch at bind time (features) / once
-  per epoch (entities), so the step itself needs no host synchronisation.
+  row // world, in CUDA-IPC memory every rank of the node maps.  There is NO collective in the sparse data path:
+    (1) fetch   - a rank's kernel reads the distinct rows its batch touches straight from their owners' HBM over
+                  NVLink into compact tables (``rae_fetch_rows``); ids are remapped to compact slots (ascending id);
+    (2) step    - the fused step runs on the compact tables with RAE_FLAG_EMIT_ONLY: one reduced gradient row per compact
+                  row (duplicates inside the rank already summed, in sorted order);
+    (3) pull    - after the dense all-reduce (which also orders "every rank has emitted"), each OWNER reads the gradient
+                  rows of its rows from all ranks' compact gradient buffers, sums them in rank order and applies ONE
+                  optimiser read-modify-write per row (``rae_pull_apply``);
+    (4) barrier - a one-element all-reduce (it carries the global cost) orders "every owner has applied" before the next
+                  step's fetch.
+  Fixed orders everywhere: bitwise reproducible for a given world size.
+* routing (which rows, which slots, who owns what) depends only on the ids: the plans of ALL batches are built at bind
+  time (features) / once per epoch (entities) with a handful of vectorised tensor ops and two all-gathers, so the step
+  itself needs no host synchronisation and no id exchange.
 
 torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests); the numerical work is done by a backend:
 :class:`CudaBackend` (librae.so) in production.  The CPU tests inject a NumPy backend to check the routing logic.
@@ -30,109 +37,274 @@ import torch.distributed as dist
 SPARSE = ("W", "A", "Ab")
 
 
-@dataclass
-class RowPlan:
-    """Routing of one batch's distinct rows of one table."""
-    ids_sorted: torch.Tensor     # int64 [U] distinct global row ids, ascending
-    inv: torch.Tensor            # int64 [U] position in ids_sorted -> compact row (owner-major order)
-    send_counts: List[int]       # rows requested from each owner
-    recv_counts: List[int]       # rows each rank requests from me
-    recv_rows: torch.Tensor      # int32 [sum recv] local row index (id // world) of the requested rows, source-rank major
-    U: int
-
-    def remap(self, x: torch.Tensor) -> torch.Tensor:
-        return self.inv[torch.searchsorted(self.ids_sorted, x.to(torch.int64))].to(torch.int32)
-
-
-def build_plan(ids: torch.Tensor, world: int, group=None) -> RowPlan:
-    """Collective: every rank calls it with the distinct ids it needs (any order)."""
-    ids = torch.unique(ids.to(torch.int64), sorted=True)
-    owner = ids % world
-    order = torch.argsort(owner, stable=True)
-    send_ids = ids[order].contiguous()
-    counts = torch.bincount(owner, minlength=world)
-    recv_counts = torch.empty_like(counts)
-    dist.all_to_all_single(recv_counts, counts, group=group)
-    sc, rc = counts.tolist(), recv_counts.tolist()
-    recv_ids = torch.empty(int(sum(rc)), dtype=torch.int64, device=ids.device)
-    dist.all_to_all_single(recv_ids, send_ids, rc, sc, group=group)
-    inv = torch.empty_like(order)
-    inv[order] = torch.arange(order.numel(), device=ids.device)
-    return RowPlan(ids, inv, sc, rc, (recv_ids // world).to(torch.int32).contiguous(), int(ids.numel()))
-
-
 def shard_rows(full: np.ndarray, rank: int, world: int) -> np.ndarray:
     return np.ascontiguousarray(full[rank::world])
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# routing plans
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class EpochPlan:
+    """Routing of one table family (features -> W, entities -> A/Ab) for every batch of a split / epoch."""
+    nb: int
+    u_ids: torch.Tensor        # int32 [sum U_b]  distinct global row ids of each batch, ascending within the batch
+    u_off: List[int]           # [nb+1] offsets into u_ids
+    compact: torch.Tensor      # int32 [n_occ]    compact slot (position in the batch's u_ids) of every occurrence
+    rows_local: torch.Tensor   # int32 [sum R_b]  owner side: local row index of every row this rank owns and any rank touches
+    r_off: List[int]           # [nb+1] offsets into rows_local (and into ent_off)
+    ent_off: torch.Tensor      # int32 [sum R_b + 1] absolute offsets into ent_src / ent_slot
+    ent_src: torch.Tensor      # int32 [E] source rank of each contribution (ascending within a row)
+    ent_slot: torch.Tensor     # int32 [E] compact slot of the row in the source rank's gradient buffer
+    max_u: int
+
+    def ids_of(self, b):
+        return self.u_ids[self.u_off[b]:self.u_off[b + 1]]
+
+
+def _excl_cumsum(cnt: torch.Tensor) -> torch.Tensor:
+    off = torch.zeros(cnt.numel() + 1, dtype=torch.int64, device=cnt.device)
+    off[1:] = torch.cumsum(cnt, 0)
+    return off
+
+
+def build_epoch_plan(ids: torch.Tensor, batch_of: torch.Tensor, nb: int, n_rows_total: int, rank: int, world: int,
+                     group=None) -> EpochPlan:
+    """Collective.  ``ids`` int64 [n]: global row id of every occurrence this rank has in the epoch; ``batch_of`` int64 [n]:
+    the batch each occurrence belongs to."""
+    dev = ids.device
+    stride = int(n_rows_total)
+    n_local = (stride + world - 1) // world
+    key = batch_of * stride + ids
+    ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
+    ub = torch.div(ukey, stride, rounding_mode="floor")
+    u_off_t = _excl_cumsum(torch.bincount(ub, minlength=nb))
+    compact = (inverse - u_off_t[batch_of]).to(torch.int32)
+    u_ids = (ukey - ub * stride).to(torch.int32)
+    # every rank learns every rank's distinct (batch, row) keys
+    if world > 1:
+        n_mine = torch.tensor([ukey.numel()], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n_mine) for _ in range(world)]
+        dist.all_gather(sizes, n_mine, group=group)
+        sizes = [int(s.item()) for s in sizes]
+        mx = max(max(sizes), 1)
+        padded = torch.zeros(mx, dtype=torch.int64, device=dev)
+        padded[: ukey.numel()] = ukey
+        gathered = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(gathered, padded, group=group)
+        keys = [gathered[s][: sizes[s]] for s in range(world)]
+    else:
+        keys = [ukey]
+    eb, erow, esrc, eslot = [], [], [], []
+    for s in range(world):
+        k = keys[s]
+        b = torch.div(k, stride, rounding_mode="floor")
+        idd = k - b * stride
+        off = _excl_cumsum(torch.bincount(b, minlength=nb))
+        slot = torch.arange(k.numel(), device=dev, dtype=torch.int64) - off[b]
+        own = (idd % world) == rank
+        eb.append(b[own])
+        erow.append(torch.div(idd[own], world, rounding_mode="floor"))
+        eslot.append(slot[own])
+        esrc.append(torch.full((int(own.sum().item()),), s, dtype=torch.int64, device=dev))
+    eb, erow, esrc, eslot = torch.cat(eb), torch.cat(erow), torch.cat(esrc), torch.cat(eslot)
+    key2 = (eb * n_local + erow) * world + esrc            # distinct by construction: any sort gives the same order
+    order = torch.argsort(key2)
+    rowkey = torch.div(key2[order], world, rounding_mode="floor")
+    uniq, counts = torch.unique_consecutive(rowkey, return_counts=True)
+    rb = torch.div(uniq, n_local, rounding_mode="floor")
+    rows_local = (uniq - rb * n_local).to(torch.int32)
+    r_off_t = _excl_cumsum(torch.bincount(rb, minlength=nb))
+    ent_off = _excl_cumsum(counts).to(torch.int32)
+    return EpochPlan(nb=nb, u_ids=u_ids.contiguous(), u_off=u_off_t.tolist(), compact=compact.contiguous(),
+                     rows_local=rows_local.contiguous(), r_off=r_off_t.tolist(), ent_off=ent_off.contiguous(),
+                     ent_src=esrc[order].to(torch.int32).contiguous(), ent_slot=eslot[order].to(torch.int32).contiguous(),
+                     max_u=int((u_off_t[1:] - u_off_t[:-1]).max().item()) if nb > 0 else 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CUDA backend: librae.so + CUDA-IPC peer memory
+# ----------------------------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Raw device allocation exposed to torch through ``__cuda_array_interface__`` (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerBuffer:
+    """fp32 device buffer allocated by librae (cudaMalloc, zeroed) whose IPC handle the other ranks can open."""
+
+    def __init__(self, lib, shape, device):
+        self.lib = lib
+        self.shape = tuple(int(x) for x in shape)
+        n = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.nbytes = max(4 * n, 4)
+        ptr = C.c_void_p(0)
+        self.handle = (C.c_ubyte * 64)()
+        rc = lib.rae_peer_alloc(self.nbytes, C.byref(ptr), self.handle)
+        if rc != 0:
+            raise RuntimeError("rae_peer_alloc failed (%d): %s" % (rc, lib.rae_last_error(None).decode()))
+        self.ptr = int(ptr.value)
+        self.tensor = torch.as_tensor(_DevArray(self.ptr, self.shape if n > 0 else (0,)), device=device)
+        self.peers: List[int] = [self.ptr]       # device pointers of this buffer on every rank (own rank included)
+        self._opened: List[int] = []
+
+    def handle_bytes(self) -> bytes:
+        return bytes(self.handle)
+
+    def open_peers(self, handles: List[bytes], rank: int):
+        self.peers = []
+        for r, hb in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.ptr)
+                continue
+            buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+            p = C.c_void_p(0)
+            rc = self.lib.rae_peer_open(buf, C.byref(p))
+            if rc != 0:
+                raise RuntimeError("rae_peer_open failed (%d): %s" % (rc, self.lib.rae_last_error(None).decode()))
+            self.peers.append(int(p.value))
+            self._opened.append(int(p.value))
+
+    def peer_array(self):
+        return (C.c_void_p * len(self.peers))(*self.peers)
+
+    def close(self):
+        for p in self._opened:
+            self.lib.rae_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self.ptr:
+            self.tensor = None
+            self.lib.rae_peer_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
 class CudaBackend:
-    """Local numerical work on one GPU through librae.so (emit-only engine on compact tables)."""
+    """Local numerical work on one GPU through librae.so (emit-only engine on compact tables) and the peer-memory
+    fetch / pull kernels."""
 
-    def __init__(self, model, K, d, S, B, F_cap, N_cap, n_train, lr, alpha, optimizer, device, z_total, adj):
+    def __init__(self, de: "DistributedEngine"):
         from . import _lib as L
-        from .engine import Engine
         self.L = L
-        self.eng = Engine(model, K, d, S, B, F_cap, N_cap, n_train, lr=lr, alpha=alpha, optimizer=optimizer, device=device,
-                          flags=L.RAE_FLAG_EMIT_ONLY | L.RAE_FLAG_NO_FEATURE_CACHE, z_total=z_total, adj=adj)
-        self.lib, self.h = self.eng.lib, self.eng._h
-        self.device = self.eng.device
-        self.K, self.d = K, d
-        f32 = dict(dtype=torch.float32, device=self.device)
-        self.compact = {"W": torch.zeros(F_cap, K, **f32), "A": torch.zeros(N_cap, d, **f32), "Ab": torch.zeros(N_cap, **f32)}
-        self.grads = {"W": torch.zeros(F_cap, K, **f32), "A": torch.zeros(N_cap, d, **f32), "Ab": torch.zeros(N_cap, **f32)}
-        self.dense_grad = torch.zeros(int(self.lib.rae_dense_grad_size(self.h)), **f32)
-        self.dense: Dict[str, torch.Tensor] = {}
-        self.dense_acc: Dict[str, torch.Tensor] = {}
-        self._cost = C.c_double(0.0)
+        self.lib = L.load()
+        self.de = de
+        self.device = de.dev
+        torch.cuda.set_device(self.device)
+        self.eng = None
+        self.shard_buf: Dict[str, PeerBuffer] = {}
+        self.grad_buf: Dict[str, PeerBuffer] = {}
+        self.compact: Dict[str, torch.Tensor] = {}
+        self.dense_grad = None
+        self.cost_t = torch.zeros(1, dtype=torch.float64, device=self.device)
 
-    def _p(self, t):
+    @staticmethod
+    def _p(t):
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _exchange(self, bufs: Dict[str, PeerBuffer]):
+        de = self.de
+        if de.world == 1:
+            return
+        mine = {n: b.handle_bytes() for n, b in bufs.items()}
+        allh = [None] * de.world
+        dist.all_gather_object(allh, mine, group=de.group)
+        for n, b in bufs.items():
+            b.open_peers([allh[r][n] for r in range(de.world)], de.rank)
+
+    # -- tables
+    def alloc_tables(self, shapes: Dict[str, tuple]) -> Dict[str, torch.Tensor]:
+        """Collective: the row shards of W / A / Ab in peer-visible memory."""
+        for b in self.shard_buf.values():
+            b.close()
+        self.shard_buf = {n: PeerBuffer(self.lib, shp, self.device) for n, shp in shapes.items()}
+        self._exchange(self.shard_buf)
+        return {n: b.tensor for n, b in self.shard_buf.items()}
+
+    def setup(self, f_cap: int, n_cap: int):
+        """Collective: emit-only engine on compact tables of capacity f_cap / n_cap, peer-visible gradient buffers."""
+        from .engine import Engine
+        de = self.de
+        L = self.L
+        self.eng = Engine(de.model, de.K, de.d, de.S, de.B, f_cap, n_cap, de.n_train, lr=de.lr, alpha=de.alpha,
+                          optimizer=de.optimizer, device=self.device.index, flags=L.RAE_FLAG_EMIT_ONLY, z_total=de.z_total,
+                          adj=de.adj)
+        self.h = self.eng._h
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.compact = {"W": torch.zeros(f_cap, de.K, **f32), "A": torch.zeros(n_cap, de.d, **f32), "Ab": torch.zeros(n_cap, **f32)}
+        self.grad_buf = {"W": PeerBuffer(self.lib, (f_cap, de.K), self.device), "A": PeerBuffer(self.lib, (n_cap, de.d), self.device),
+                         "Ab": PeerBuffer(self.lib, (n_cap,), self.device)}
+        self._exchange(self.grad_buf)
+        self.dense_grad = torch.zeros(int(self.lib.rae_dense_grad_size(self.h)), **f32)
+
     def bind_dense(self, dense: Dict[str, torch.Tensor], dense_acc: Dict[str, torch.Tensor]):
-        self.dense, self.dense_acc = dense, dense_acc
         g = lambda m, n: self._p(m.get(n))
         e = self.eng
         e._check(self.lib.rae_bind_params(self.h, self._p(self.compact["W"]), g(dense, "Wb"), self._p(self.compact["A"]),
                                           self._p(self.compact["Ab"]), g(dense, "C"), g(dense, "C1"), g(dense, "C2")), "rae_bind_params")
         e._check(self.lib.rae_bind_accumulators(self.h, None, g(dense_acc, "Wb"), None, None, g(dense_acc, "C"),
                                                 g(dense_acc, "C1"), g(dense_acc, "C2")), "rae_bind_accumulators")
-        e._check(self.lib.rae_bind_grad_buffers(self.h, self._p(self.grads["W"]), self._p(self.grads["A"]),
-                                                self._p(self.grads["Ab"]), self._p(self.dense_grad)), "rae_bind_grad_buffers")
+        gb = self.grad_buf
+        e._check(self.lib.rae_bind_grad_buffers(self.h, self._p(gb["W"].tensor), self._p(gb["A"].tensor), self._p(gb["Ab"].tensor),
+                                                self._p(self.dense_grad)), "rae_bind_grad_buffers")
 
-    def gather_rows(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
-        width = 1 if table.dim() == 1 else table.shape[1]
-        out = torch.empty((rows.numel(), width), dtype=torch.float32, device=self.device)
-        self.eng._check(self.lib.rae_gather_rows(self.h, self._p(table), width, self._p(rows), rows.numel(), self._p(out),
-                                                 self.eng._stream), "rae_gather_rows")
-        return out
+    def bind_train_csr(self, indptr: torch.Tensor, indices_compact: torch.Tensor, a1: torch.Tensor, a2: torch.Tensor):
+        """The local train rows with COMPACT feature slots as column ids: the engine caches the per-batch transposed index."""
+        self.eng.bind_split("train", indptr, indices_compact, a1, a2)
 
-    def rows_apply(self, table, acc, rows, grads):
-        width = 1 if table.dim() == 1 else table.shape[1]
-        self.eng._check(self.lib.rae_sparse_rows_apply(self.h, self._p(table), self._p(acc), width, self._p(rows),
-                                                       self._p(grads), rows.numel(), table.shape[0], self.eng._stream),
-                        "rae_sparse_rows_apply")
+    # -- the step
+    def fetch(self, name: str, ids: torch.Tensor):
+        t = self.compact[name]
+        width = 1 if t.dim() == 1 else t.shape[1]
+        self.eng._check(self.lib.rae_fetch_rows(self.h, self.shard_buf[name].peer_array(), self.de.world, width, self._p(ids),
+                                                ids.numel(), self._p(t), self._stream), "rae_fetch_rows")
 
-    def local_step(self, indptr, indices, nnz, a1, a2, n1, n2, neg_ld):
-        self.eng._check(self.lib.rae_train_step_begin_explicit(self.h, self._p(indptr), self._p(indices), int(nnz), self._p(a1),
-                                                               self._p(a2), self._p(n1), self._p(n2), int(neg_ld),
-                                                               self.eng._stream), "rae_train_step_begin_explicit")
+    def local_step(self, batch_index, a1c, a2c, n1c, n2c, neg_ld):
+        self.eng._check(self.lib.rae_train_step_begin(self.h, int(batch_index), self._p(a1c), self._p(a2c), self._p(n1c),
+                                                      self._p(n2c), int(neg_ld), self._stream), "rae_train_step_begin")
 
     def dense_apply(self):
-        self.eng._check(self.lib.rae_train_step_end(self.h, self.eng._stream), "rae_train_step_end")
+        self.eng._check(self.lib.rae_train_step_end(self.h, self._stream), "rae_train_step_end")
 
-    def local_cost(self) -> float:
-        self.eng._check(self.lib.rae_read_cost(self.h, C.byref(self._cost), self.eng._stream), "rae_read_cost")
-        return float(self._cost.value)
+    def pull_apply(self, name: str, table, acc, rows_local, ent_off, ent_src, ent_slot):
+        width = 1 if table.dim() == 1 else table.shape[1]
+        n_rows = rows_local.numel()
+        if n_rows == 0:
+            return
+        self.eng._check(self.lib.rae_pull_apply(self.h, self._p(table), self._p(acc), width, self._p(rows_local), self._p(ent_off),
+                                                self._p(ent_src), self._p(ent_slot), n_rows, self.grad_buf[name].peer_array(),
+                                                self.de.world, self._stream), "rae_pull_apply")
 
-    def label(self, indptr, indices):
-        # emit-only engines label through the explicit encoder on the compact W (bound as the 'test' split)
-        self.eng.bind_split("test", indptr, indices)
-        return self.eng.label("test", 0)
+    def local_cost_tensor(self) -> torch.Tensor:
+        self.eng._check(self.lib.rae_copy_cost(self.h, self._p(self.cost_t), self._stream), "rae_copy_cost")
+        return self.cost_t
 
-    def synchronize(self):
-        torch.cuda.synchronize(self.device)
+    def label(self, indptr: torch.Tensor, indices_compact: torch.Tensor):
+        n = indptr.numel() - 1
+        labels = torch.empty(n, dtype=torch.int64, device=self.device)
+        probs = torch.empty((n, self.de.K), dtype=torch.float32, device=self.device)
+        self.eng._check(self.lib.rae_label_explicit(self.h, self._p(indptr), self._p(indices_compact), n, self._p(labels),
+                                                    self._p(probs), self._stream), "rae_label_explicit")
+        return labels.cpu().numpy(), probs.cpu().numpy()
+
+    def close(self):
+        if self.eng is not None:
+            torch.cuda.synchronize(self.device)
+            if self.de.world > 1:
+                dist.barrier(group=self.de.group)      # nobody unmaps while a peer may still read
+            self.eng.close()
+            self.eng = None
+        for b in list(self.grad_buf.values()) + list(self.shard_buf.values()):
+            b.close()
+        self.grad_buf, self.shard_buf = {}, {}
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 class DistributedEngine:
     """Same calls as :class:`relation_autoencoder_b200.engine.Engine`, one instance per rank."""
 
@@ -144,6 +316,8 @@ class DistributedEngine:
         from .engine import MODEL_IDS, MODEL_PARAMS
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
+        if self.world > 16:
+            raise ValueError("at most 16 ranks (RAE_MAX_PEERS)")
         self.group = group
         self.model, self.K, self.d, self.S, self.B, self.F, self.N = model, K, d, S, B, F, N
         self.n_train = n_train
@@ -152,50 +326,64 @@ class DistributedEngine:
         self.dense_names = [n for n in self.names if n not in SPARSE]
         self.z_total = self.world * (4 * B + 2 * B * S)                       # global Z (OieModel.py:90)
         self.adj = float(self.world * B) / float(max(1, n_train))              # OieInduction.py:131 with the global batch
-        self.backend_factory = backend_factory
-        self.device_index = device
-        self.backend = None
         self.dev = torch.device("cpu") if backend_factory is not None else torch.device("cuda", device)
+        self.backend = backend_factory(self) if backend_factory is not None else CudaBackend(self)
         self.shard: Dict[str, torch.Tensor] = {}
         self.shard_acc: Dict[str, torch.Tensor] = {}
         self.dense: Dict[str, torch.Tensor] = {}
         self.dense_acc: Dict[str, torch.Tensor] = {}
-        self.fplans: List[RowPlan] = []
-        self.fcsr = []
-        self.eplans: List[RowPlan] = []
-        self.eidx = []
-        self._pending = None
-        self._last_cost = None
+        self.fplan: Optional[EpochPlan] = None
+        self.eplan: Optional[EpochPlan] = None
+        self.nb = 0
+        self._ready = False
+        self._label_split = {}
+
+    def _rows_total(self, name):
+        return self.F if name == "W" else self.N
+
+    def _width(self, name):
+        return {"W": (self.K,), "A": (self.d,), "Ab": ()}[name]
 
     # ------------------------------------------------------------------ parameters
     def set_params_numpy(self, params: Dict[str, np.ndarray], acc: Optional[Dict[str, np.ndarray]] = None):
-        """``params`` are the FULL tables (every rank passes the same arrays); each rank keeps its own rows."""
-        dt = torch.float64 if self.backend_factory is not None else torch.float32
+        """``params`` are the FULL tables (every rank passes the same arrays); each rank keeps its own rows.  Collective."""
+        dt = self.backend.dtype if hasattr(self.backend, "dtype") else torch.float32
+        shapes = {n: (len(range(self.rank, self._rows_total(n), self.world)),) + self._width(n) for n in SPARSE}
+        self.shard = self.backend.alloc_tables(shapes)
         for n in self.names:
-            a = params[n] if acc is None else acc[n]
             if n in SPARSE:
-                self.shard[n] = torch.as_tensor(shard_rows(np.asarray(params[n]), self.rank, self.world)).to(self.dev, dt).contiguous()
+                self.shard[n].copy_(torch.as_tensor(shard_rows(np.asarray(params[n]), self.rank, self.world)).to(self.dev, dt))
                 self.shard_acc[n] = (torch.zeros_like(self.shard[n]) if acc is None else
-                                     torch.as_tensor(shard_rows(np.asarray(a), self.rank, self.world)).to(self.dev, dt).contiguous())
+                                     torch.as_tensor(shard_rows(np.asarray(acc[n]), self.rank, self.world)).to(self.dev, dt).contiguous())
             else:
                 self.dense[n] = torch.as_tensor(np.ascontiguousarray(params[n])).to(self.dev, dt).contiguous()
                 self.dense_acc[n] = (torch.zeros_like(self.dense[n]) if acc is None else
-                                     torch.as_tensor(np.ascontiguousarray(a)).to(self.dev, dt).contiguous())
-        if self.backend is not None:
+                                     torch.as_tensor(np.ascontiguousarray(acc[n])).to(self.dev, dt).contiguous())
+        if self._ready:
             self.backend.bind_dense(self.dense, self.dense_acc)
+        self._sync_all()
+
+    def _sync_all(self):
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier(group=self.group)
 
     def _gather_full(self, shards: Dict[str, torch.Tensor], dense: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         out = {}
         for n in self.names:
             if n in SPARSE:
-                total = self.F if n == "W" else self.N
-                width = shards[n].shape[1:] if shards[n].dim() > 1 else ()
-                full = torch.zeros((total,) + tuple(width), dtype=shards[n].dtype, device=self.dev)
+                total = self._rows_total(n)
+                width = tuple(shards[n].shape[1:])
+                full = torch.zeros((total,) + width, dtype=shards[n].dtype, device=self.dev)
                 rows = (total + self.world - 1) // self.world
-                pad = torch.zeros((rows,) + tuple(width), dtype=shards[n].dtype, device=self.dev)
+                pad = torch.zeros((rows,) + width, dtype=shards[n].dtype, device=self.dev)
                 pad[: shards[n].shape[0]] = shards[n]
-                parts = [torch.empty_like(pad) for _ in range(self.world)]
-                dist.all_gather(parts, pad, group=self.group)
+                if self.world > 1:
+                    parts = [torch.empty_like(pad) for _ in range(self.world)]
+                    dist.all_gather(parts, pad, group=self.group)
+                else:
+                    parts = [pad]
                 for r in range(self.world):
                     cnt = len(range(r, total, self.world))
                     full[r::self.world] = parts[r][:cnt]
@@ -217,116 +405,136 @@ class DistributedEngine:
         return torch.as_tensor(np.ascontiguousarray(x)).to(self.dev, torch.int64)
 
     def bind_split(self, split: str, indptr, indices, args1=None, args2=None):
-        """Local rows of the split.  For 'train': builds the per-batch feature routing plans (collective)."""
+        """Local rows of the split.  For 'train' (collective): routing plan of the feature rows of every batch."""
         ip, ix = self._i64(indptr), self._i64(indices)
         if split != "train":
-            self._label_split = getattr(self, "_label_split", {})
             self._label_split[split] = (ip, ix)
             return
+        B = self.B
+        nb = (ip.numel() - 1) // B
+        if self.world > 1:
+            nbt = torch.tensor([nb], device=self.dev)
+            dist.all_reduce(nbt, op=dist.ReduceOp.MIN, group=self.group)
+            nb = int(nbt.item())                                               # every rank steps the same number of batches
+        self.nb = nb
+        n_used = nb * B
+        ip = ip[: n_used + 1].contiguous()
+        base = int(ip[0].item())
+        ix = ix[base:int(ip[-1].item())].contiguous()
+        ip = ip - base
         self.ip, self.ix = ip, ix
-        self.a1, self.a2 = self._i64(args1), self._i64(args2)
-        nb = (ip.numel() - 1) // self.B
-        nbt = torch.tensor([nb], device=self.dev)
-        dist.all_reduce(nbt, op=dist.ReduceOp.MIN, group=self.group)
-        self.nb = int(nbt.item())                                              # every rank steps the same number of batches
-        self.fplans, self.fcsr = [], []
-        for b in range(self.nb):
-            lo, hi = int(ip[b * self.B]), int(ip[(b + 1) * self.B])
-            feats = ix[lo:hi]
-            plan = build_plan(feats, self.world, self.group)
-            self.fplans.append(plan)
-            self.fcsr.append(((ip[b * self.B:(b + 1) * self.B + 1] - lo).to(torch.int32).contiguous(),
-                              plan.remap(feats).contiguous(), hi - lo))
-        if self.backend is None:
-            f_cap = max([p.U for p in self.fplans] + [1])
-            n_cap = (2 + 2 * self.S) * self.B
-            if self.backend_factory is not None:
-                self.backend = self.backend_factory(self, f_cap, n_cap)
-            else:
-                self.backend = CudaBackend(self.model, self.K, self.d, self.S, self.B, f_cap, n_cap, self.n_train, self.lr,
-                                           self.alpha, self.optimizer, self.device_index, self.z_total, self.adj)
-            self.backend.bind_dense(self.dense, self.dense_acc)
+        self.a1, self.a2 = self._i64(args1)[:n_used].contiguous(), self._i64(args2)[:n_used].contiguous()
+        counts = ip[1:] - ip[:-1]
+        row_of = torch.repeat_interleave(torch.arange(n_used, device=self.dev, dtype=torch.int64), counts)
+        self.fplan = build_epoch_plan(ix, torch.div(row_of, B, rounding_mode="floor"), nb, self.F, self.rank, self.world, self.group)
+        f_cap = max(self.fplan.max_u, 1)
+        if self.world > 1:
+            cap = torch.tensor([f_cap], device=self.dev)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            f_cap = int(cap.item())
+        n_cap = (2 + 2 * self.S) * B
+        self.backend.setup(f_cap, n_cap)
+        self.backend.bind_dense(self.dense, self.dense_acc)
+        self._ready = True
+        # placeholders for the entity ids: the compact slots are per epoch (bind_epoch_negatives)
+        zeros = torch.zeros(n_used, dtype=torch.int32, device=self.dev)
+        self.backend.bind_train_csr(ip.to(torch.int32).contiguous(), self.fplan.compact, zeros, zeros)
+        self._sync_all()
 
     def n_batches(self, split: str = "train") -> int:
         return self.nb
 
-    def _entity_plan(self, b, n1, n2):
-        """n1, n2: int64 [S, B] negatives of batch b (this rank's columns)."""
-        a1 = self.a1[b * self.B:(b + 1) * self.B]
-        a2 = self.a2[b * self.B:(b + 1) * self.B]
-        plan = build_plan(torch.cat([a1, a2, n1.reshape(-1), n2.reshape(-1)]), self.world, self.group)
-        idx = (plan.remap(a1).contiguous(), plan.remap(a2).contiguous(),
-               plan.remap(n1.reshape(-1)).reshape(n1.shape).contiguous(), plan.remap(n2.reshape(-1)).reshape(n2.shape).contiguous())
-        return plan, idx
-
     def bind_epoch_negatives(self, neg1, neg2):
-        """The epoch's negatives [S, n_local] (OieInduction.py:183-184): builds the entity routing plans (collective)."""
-        n1, n2 = self._i64(neg1), self._i64(neg2)
-        self.eplans, self.eidx = [], []
-        for b in range(self.nb):
-            plan, idx = self._entity_plan(b, n1[:, b * self.B:(b + 1) * self.B], n2[:, b * self.B:(b + 1) * self.B])
-            self.eplans.append(plan)
-            self.eidx.append(idx)
+        """The epoch's negatives [S, n_local] (OieInduction.py:183-184).  Collective: routing plan of the entity rows of
+        every batch (args1, args2 and the 2S negatives of each example)."""
+        B, S, nb = self.B, self.S, self.nb
+        n_used = nb * B
+        n1 = self._i64(neg1)[:, :n_used]
+        n2 = self._i64(neg2)[:, :n_used]
+        col_batch = torch.div(torch.arange(n_used, device=self.dev, dtype=torch.int64), B, rounding_mode="floor")
+        ids = torch.cat([self.a1, self.a2, n1.reshape(-1), n2.reshape(-1)])
+        batch_of = torch.cat([col_batch, col_batch, col_batch.repeat(S), col_batch.repeat(S)])
+        self.eplan = build_epoch_plan(ids, batch_of, nb, self.N, self.rank, self.world, self.group)
+        c = self.eplan.compact
+        self.a1c = c[:n_used].contiguous()
+        self.a2c = c[n_used:2 * n_used].contiguous()
+        self.n1c = c[2 * n_used:(2 + S) * n_used].reshape(S, n_used).contiguous()
+        self.n2c = c[(2 + S) * n_used:].reshape(S, n_used).contiguous()
+        self._sync_all()
 
     # ------------------------------------------------------------------ the step
-    def _fetch(self, plan: RowPlan, name: str, out: torch.Tensor):
-        rows = self.backend.gather_rows(self.shard[name], plan.recv_rows)
-        view = out[: plan.U].reshape(plan.U, -1)
-        dist.all_to_all_single(view, rows, plan.send_counts, plan.recv_counts, group=self.group)
-
-    def _return_and_apply(self, plan: RowPlan, name: str, grads: torch.Tensor):
-        view = grads[: plan.U].reshape(plan.U, -1)
-        recv = torch.empty((int(sum(plan.recv_counts)), view.shape[1]), dtype=view.dtype, device=self.dev)
-        dist.all_to_all_single(recv, view.contiguous(), plan.recv_counts, plan.send_counts, group=self.group)
-        self.backend.rows_apply(self.shard[name], self.shard_acc[name], plan.recv_rows, recv)
-
-    def _step(self, b, eplan, eidx, want_cost):
-        fplan = self.fplans[b]
-        ipc, ixc, nnz = self.fcsr[b]
-        bk = self.backend
-        self._fetch(fplan, "W", bk.compact["W"])
-        self._fetch(eplan, "A", bk.compact["A"])
-        self._fetch(eplan, "Ab", bk.compact["Ab"])
-        a1c, a2c, n1c, n2c = eidx
-        bk.local_step(ipc, ixc, nnz, a1c, a2c, n1c, n2c, self.B)
-        dist.all_reduce(bk.dense_grad, group=self.group)          # sum of the ranks' dense gradients (C | C1 | C2 | Wb)
-        bk.dense_apply()
-        self._return_and_apply(fplan, "W", bk.grads["W"])
-        self._return_and_apply(eplan, "A", bk.grads["A"])
-        self._return_and_apply(eplan, "Ab", bk.grads["Ab"])
-        if want_cost:
-            c = torch.tensor([bk.local_cost()], dtype=torch.float64, device=self.dev)
-            dist.all_reduce(c, group=self.group)
-            return float(c.item())
-        return None
+    def _step(self, b, a1c, a2c, n1c, n2c, neg_ld, want_cost):
+        fp, ep, bk = self.fplan, self.eplan, self.backend
+        e_ids = ep.ids_of(b)
+        bk.fetch("W", fp.ids_of(b))
+        bk.fetch("A", e_ids)
+        bk.fetch("Ab", e_ids)
+        bk.local_step(b, a1c, a2c, n1c, n2c, neg_ld)
+        if self.world > 1:
+            dist.all_reduce(bk.dense_grad, group=self.group)      # sum of the ranks' dense gradients (C | C1 | C2 | Wb);
+        bk.dense_apply()                                          # also orders "every rank has emitted" before the pulls
+        for name, plan in (("W", fp), ("A", ep), ("Ab", ep)):
+            lo, hi = plan.r_off[b], plan.r_off[b + 1]
+            bk.pull_apply(name, self.shard[name], self.shard_acc[name], plan.rows_local[lo:hi], plan.ent_off[lo:hi + 1],
+                          plan.ent_src, plan.ent_slot)
+        cost = bk.local_cost_tensor()
+        if self.world > 1:
+            dist.all_reduce(cost, group=self.group)               # global cost; orders "every owner has applied"
+        return float(cost.item()) if want_cost else None
 
     def train_device(self, batch_index: int, want_cost: bool = True):
-        return self._step(batch_index, self.eplans[batch_index], self.eidx[batch_index], want_cost)
+        b, B = int(batch_index), self.B
+        if not (0 <= b < self.nb):
+            raise RuntimeError("batch_index %d out of range [0,%d)" % (b, self.nb))
+        if self.eplan is None:
+            raise RuntimeError("epoch negatives are not bound (bind_epoch_negatives)")
+        n_used = self.nb * B
+        return self._step(b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], self.n1c[:, b * B:], self.n2c[:, b * B:],
+                          n_used, want_cost)
 
     def train(self, batch_index: int, neg1, neg2) -> float:
-        """func['train'](batch_index, neg1, neg2) with this rank's host negatives [S,B]; returns the GLOBAL batch cost."""
-        plan, idx = self._entity_plan(batch_index, self._i64(neg1), self._i64(neg2))
-        return self._step(batch_index, plan, idx, True)
+        """func['train'](batch_index, neg1, neg2) with this rank's HOST negatives [S,B] (the columns of the bound epoch
+        negatives, as the reference's driver passes them, OieInduction.py:187-189); returns the GLOBAL batch cost."""
+        b, B = int(batch_index), self.B
+        if self.eplan is None:
+            raise RuntimeError("epoch negatives are not bound (bind_epoch_negatives)")
+        u = self.eplan.ids_of(b).to(torch.int64)
+        out = []
+        ok = torch.ones((), dtype=torch.bool, device=self.dev)
+        for x in (neg1, neg2):
+            t = self._i64(x).contiguous()
+            c = torch.searchsorted(u, t.reshape(-1)).clamp_(max=max(u.numel() - 1, 0))
+            ok = ok & (u[c] == t.reshape(-1)).all()
+            out.append(c.to(torch.int32).reshape(t.shape).contiguous())
+        cost = self._step(b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], out[0], out[1], B, True)
+        if not bool(ok.item()):
+            raise RuntimeError("train(): the negatives passed for batch %d are not the columns of the bound epoch negatives" % b)
+        return cost
 
     def label(self, split: str, batch_index: int):
+        """func['label_<split>'](batch_index) for this rank's rows: the needed W rows are read from their owners (no
+        collective with the CUDA backend)."""
+        B = self.B
         if split == "train":
             ip, ix = self.ip, self.ix
         else:
             ip, ix = self._label_split[split]
-        lo, hi = int(ip[batch_index * self.B]), int(ip[(batch_index + 1) * self.B])
+        lo, hi = int(ip[batch_index * B].item()), int(ip[(batch_index + 1) * B].item())
         feats = ix[lo:hi]
-        plan = build_plan(feats, self.world, self.group)
-        self._fetch(plan, "W", self.backend.compact["W"])
-        return self.backend.label((ip[batch_index * self.B:(batch_index + 1) * self.B + 1] - lo).to(torch.int32), plan.remap(feats))
+        u, inv = torch.unique(feats, sorted=True, return_inverse=True)
+        if u.numel() > self.backend.compact["W"].shape[0]:
+            raise RuntimeError("label(): batch touches more feature rows than the compact table holds")
+        self.backend.fetch("W", u.to(torch.int32).contiguous())
+        return self.backend.label((ip[batch_index * B:(batch_index + 1) * B + 1] - lo).to(torch.int32).contiguous(),
+                                  inv.to(torch.int32).contiguous())
 
     # ------------------------------------------------------------------ misc
     def stats(self) -> dict:
-        st = self.backend.eng.stats() if hasattr(self.backend, "eng") else {}
-        return st
+        eng = getattr(self.backend, "eng", None)
+        return eng.stats() if eng is not None else {}
 
     def set_profiling(self, on: bool):
         pass
 
     def close(self):
-        if self.backend is not None and hasattr(self.backend, "eng"):
-            self.backend.eng.close()
+        self.backend.close()

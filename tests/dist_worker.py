@@ -41,7 +41,7 @@ def main():
         loc_ip.append(len(loc_ix))
     de = DistributedEngine(model, K, d, S, B, F, N, n_train=Bg * nb, lr=0.1, alpha=0.7, rank=rank, world=world,
                            device=int(os.environ.get("LOCAL_RANK", "0")),
-                           backend_factory=None if cuda else (lambda eng, fc, nc: NumpyBackend(eng, fc, nc)))
+                           backend_factory=None if cuda else NumpyBackend)
     tol = 2e-5 if cuda else 1e-12
     de.set_params_numpy(p0)
     de.bind_split("train", np.asarray(loc_ip), np.asarray(loc_ix), pr["a1"][rows], pr["a2"][rows])
