@@ -481,15 +481,18 @@ struct ScoreArgs {
     float invZ;
 };
 
+// Two warps per example, one per side (side 0: neg1 / e1 slot, side 1: neg2 / e2 slot); 4 examples per CTA.  Both warps
+// recompute the cheap positive score; each gathers only its own S negative rows, UN rows in flight per lane.
 template <int DT>
 __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
     __shared__ double wl[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * 8 + warp;
+    const int side = warp & 1;
+    const int b = blockIdx.x * 4 + (warp >> 1);
     double loss = 0.0;
     if (b < p.B) {
         float* evb = p.ev + (size_t)b * E_NV * p.dp;
-        float L[DT], R[DT], V1[DT], V2[DT];
+        float L[DT], R[DT], V[DT];      // V: direction the negatives of this side are scored against (v + c1 | w + c2)
         float sp1 = 0.f, sp2 = 0.f, pos = 0.f;
 #pragma unroll
         for (int t = 0; t < DT; ++t) {
@@ -497,85 +500,112 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
             const bool in = j < p.d;
             L[t] = in ? evb[E_L * p.dp + j] : 0.f;
             R[t] = in ? evb[E_R * p.dp + j] : 0.f;
-            float v = (in && p.hasM) ? evb[E_V1 * p.dp + j] : 0.f;
-            float w = (in && p.hasM) ? evb[E_V2 * p.dp + j] : 0.f;
-            float c1 = (in && p.hasSP) ? evb[E_C1 * p.dp + j] : 0.f;
-            float c2 = (in && p.hasSP) ? evb[E_C2 * p.dp + j] : 0.f;
-            V1[t] = v + c1;
-            V2[t] = w + c2;
+            const float v = (in && p.hasM) ? evb[E_V1 * p.dp + j] : 0.f;
+            const float w = (in && p.hasM) ? evb[E_V2 * p.dp + j] : 0.f;
+            const float c1 = (in && p.hasSP) ? evb[E_C1 * p.dp + j] : 0.f;
+            const float c2 = (in && p.hasSP) ? evb[E_C2 * p.dp + j] : 0.f;
+            const float V1 = v + c1, V2 = w + c2;
+            V[t] = side == 0 ? V1 : V2;
             sp1 = fmaf(c1, L[t], sp1);
             sp2 = fmaf(c2, R[t], sp2);
-            pos = fmaf(L[t], V1[t], pos);
-            if (in) { evb[E_V1 * p.dp + j] = V1[t]; evb[E_V2 * p.dp + j] = V2[t]; }
+            pos = fmaf(L[t], V1, pos);
         }
         sp1 = warp_sum(sp1);
         sp2 = warp_sum(sp2);
         pos = warp_sum(pos) + sp2;       // L.v + c1.L + c2.R   (Bilinear.py:58-59 / BilinearPlusSP.py:68-72)
-        const int r1 = p.a1[b], r2 = p.a2[b];
-        const float u1 = pos + ld_nc(p.Ab + r1), u2 = pos + ld_nc(p.Ab + r2);          // Bilinear.py:36
-        float lsum = log_sigmoid(u1) + log_sigmoid(u2) + 2.f * p.sc[(size_t)b * SC_N + SC_ENT];   // :38-39
-        const float gu1 = -sigmoidf(-u1) * p.invZ, gu2 = -sigmoidf(-u2) * p.invZ;
-        const float gp = gu1 + gu2;
-        float X1[DT], Y2[DT];
+        // both warps have read v, w before either overwrites its slot with the gradient direction
+        __syncthreads();
 #pragma unroll
-        for (int t = 0; t < DT; ++t) { X1[t] = 0.f; Y2[t] = 0.f; }
-        float G1 = 0.f, G2 = 0.f;
-        constexpr int UN = (DT <= 4) ? 4 : 2;
-        for (int side = 0; side < 2; ++side) {
-            const int32_t* neg = side == 0 ? p.neg1 : p.neg2;
-            float* gn = side == 0 ? p.gn1 : p.gn2;
-            const float add = side == 0 ? sp2 : sp1;     // BilinearPlusSP.py:86-87 / :100,102
-            for (int s0 = 0; s0 < p.S; s0 += UN) {
-                float x[UN][DT];
-                float ab[UN];
-                int row[UN];
+        for (int t = 0; t < DT; ++t) {
+            const int j = lane + 32 * t;
+            if (j < p.d) evb[(side == 0 ? E_V1 : E_V2) * p.dp + j] = V[t];
+        }
+        const int r = side == 0 ? p.a1[b] : p.a2[b];
+        const float u = pos + ld_nc(p.Ab + r);                                           // Bilinear.py:36
+        // lane 0 carries the positive term and the entropy; lanes 0..UN-1 carry one negative each (summed at the end)
+        float lsum = lane == 0 ? log_sigmoid(u) + p.sc[(size_t)b * SC_N + SC_ENT] : 0.f;  // :38-39 (entropy counted twice)
+        const float gu = -sigmoidf(-u) * p.invZ;
+        float X[DT];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const bool ok = s0 + u < p.S;
-                    row[u] = ok ? neg[(size_t)(s0 + u) * p.neg_ld + b] : 0;
-                    ab[u] = ok ? ld_nc(p.Ab + row[u]) : 0.f;
+        for (int t = 0; t < DT; ++t) X[t] = 0.f;
+        float G = 0.f;
+        constexpr int UN = (DT <= 2) ? 10 : (DT <= 4 ? 8 : 4);
+        const int32_t* neg = side == 0 ? p.neg1 : p.neg2;
+        float* gn = side == 0 ? p.gn1 : p.gn2;
+        const float add = side == 0 ? sp2 : sp1;         // BilinearPlusSP.py:86-87 / :100,102
+        for (int s0 = 0; s0 < p.S; s0 += UN) {
+            float x[UN][DT];
+            float dots[UN];
+            // lane uu owns negative s0 + uu: its id, its bias, later its sigmoid / log-sigmoid
+            const bool mine = lane < UN && s0 + lane < p.S;
+            const int myrow = mine ? neg[(size_t)(s0 + lane) * p.neg_ld + b] : 0;
+            const float myab = mine ? ld_nc(p.Ab + myrow) : 0.f;
 #pragma unroll
-                    for (int t = 0; t < DT; ++t) {
-                        const int j = lane + 32 * t;
-                        x[u][t] = (ok && j < p.d) ? ld_nc(p.A + (size_t)row[u] * p.d + j) : 0.f;
-                    }
-                }
+            for (int uu = 0; uu < UN; ++uu) {
+                const int row = __shfl_sync(kFull, myrow, uu);
+                const bool ok = s0 + uu < p.S;
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    if (s0 + u >= p.S) break;
-                    float dot = 0.f;
-#pragma unroll
-                    for (int t = 0; t < DT; ++t) dot = fmaf(x[u][t], side == 0 ? V1[t] : V2[t], dot);
-                    dot = warp_sum(dot) + add + ab[u];
-                    lsum += log_sigmoid(-dot);                      // Bilinear.py:47
-                    const float g = sigmoidf(dot) * p.invZ;
-                    if (lane == 0) gn[(size_t)(s0 + u) * p.B + b] = g;
-                    if (side == 0) {
-                        G1 += g;
-#pragma unroll
-                        for (int t = 0; t < DT; ++t) X1[t] = fmaf(g, x[u][t], X1[t]);
-                    } else {
-                        G2 += g;
-#pragma unroll
-                        for (int t = 0; t < DT; ++t) Y2[t] = fmaf(g, x[u][t], Y2[t]);
-                    }
+                for (int t = 0; t < DT; ++t) {
+                    const int j = lane + 32 * t;
+                    x[uu][t] = (ok && j < p.d) ? ld_nc(p.A + (size_t)row * p.d + j) : 0.f;
                 }
             }
+#pragma unroll
+            for (int uu = 0; uu < UN; ++uu) {
+                float dot = 0.f;
+#pragma unroll
+                for (int t = 0; t < DT; ++t) dot = fmaf(x[uu][t], V[t], dot);
+                dots[uu] = dot;
+            }
+            // UN independent butterfly reductions (no control flow in between: the shuffles pipeline)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) dots[uu] += __shfl_xor_sync(kFull, dots[uu], o);
+            float mydot = 0.f;
+#pragma unroll
+            for (int uu = 0; uu < UN; ++uu)
+                if (lane == uu) mydot = dots[uu];
+            float myg = 0.f;
+            if (mine) {
+                mydot += add + myab;
+                lsum += log_sigmoid(-mydot);                        // Bilinear.py:47
+                myg = sigmoidf(mydot) * p.invZ;
+                gn[(size_t)(s0 + lane) * p.B + b] = myg;
+            }
+#pragma unroll
+            for (int uu = 0; uu < UN; ++uu) {
+                const float g = __shfl_sync(kFull, myg, uu);        // 0 for the padding rows
+                G += g;
+#pragma unroll
+                for (int t = 0; t < DT; ++t) X[t] = fmaf(g, x[uu][t], X[t]);
+            }
         }
+        lsum = warp_sum(lsum);
+        // the other warp's gu is needed for gp = gu1 + gu2: recomputed here (one bias load + one sigmoid)
+        const int ro = side == 0 ? p.a2[b] : p.a1[b];
+        const float guo = -sigmoidf(-(pos + ld_nc(p.Ab + ro))) * p.invZ;
+        const float gp = side == 0 ? gu + guo : guo + gu;
 #pragma unroll
         for (int t = 0; t < DT; ++t) {
             const int j = lane + 32 * t;
             if (j < p.d) {
-                evb[E_A * p.dp + j] = fmaf(gp, L[t], X1[t]);
-                evb[E_CV * p.dp + j] = fmaf(gp, R[t], Y2[t]);
-                evb[E_Y2 * p.dp + j] = Y2[t];
+                if (side == 0) {
+                    evb[E_A * p.dp + j] = fmaf(gp, L[t], X[t]);          // a = gp L + X1
+                } else {
+                    evb[E_CV * p.dp + j] = fmaf(gp, R[t], X[t]);         // c = gp R + Y2
+                    evb[E_Y2 * p.dp + j] = X[t];
+                }
             }
         }
         if (lane == 0) {
-            float* s = p.sc + (size_t)b * SC_N;
-            s[SC_GU1] = gu1; s[SC_GU2] = gu2; s[SC_GP] = gp; s[SC_G1] = G1; s[SC_G2] = G2;
+            float* sc = p.sc + (size_t)b * SC_N;
+            if (side == 0) { sc[SC_GU1] = gu; sc[SC_GP] = gp; sc[SC_G1] = G; }
+            else { sc[SC_GU2] = gu; sc[SC_G2] = G; }
         }
         loss = (double)lsum;
+    } else {
+        __syncthreads();
     }
     if (lane == 0) wl[warp] = loss;
     __syncthreads();
@@ -755,7 +785,7 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
     p.loss_part = h->loss_part;
     p.B = h->B; p.S = h->S; p.d = h->d; p.dp = h->dp; p.hasM = h->hasM; p.hasSP = h->hasSP;
     p.invZ = (float)(1.0 / h->Z);
-    const int blocks = (h->B + 7) / 8;
+    const int blocks = (h->B + 3) / 4;
     if (blocks > h->n_loss_part) return fail(h, RAE_EINVAL, "internal: loss_part too small");
     const int dt = (h->d + 31) / 32;
     if (dt <= 1) k_score<1><<<blocks, 256, 0, st>>>(p);

@@ -123,6 +123,19 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 32 consecutive floats of one accumulator row -> global memory; 16-byte stores when the row is 16-byte aligned
+__device__ __forceinline__ void store_row32(float* o, const float (&t)[32], int nvalid, bool vec) {
+    if (vec) {
+#pragma unroll
+        for (int x = 0; x < 32; x += 4)
+            if (x < nvalid) *reinterpret_cast<float4*>(o + x) = make_float4(t[x], t[x + 1], t[x + 2], t[x + 3]);
+    } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x)
+            if (x < nvalid) o[x] = t[x];
+    }
+}
+
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
 // LBO = byte distance between the two 16-byte K-halves of one MMA k-step, SBO = byte distance between 8-row groups
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -403,15 +416,32 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
         const bool ok = b < p.B;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         {
-            // group 0 writes the hi part, group 1 the lo part of this row's q (TF32 split), 8 relations per store
+            // group 0 writes the hi part, group 1 the lo part of this row's q (TF32 split), 8 relations per store.
+            // The whole row (K <= 104) is loaded first so that every load is in flight at once (one memory latency).
             const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
             const uint32_t abase = lane_base + TC_FWD_ACOL + (g == 0 ? 0u : Kp);
-            for (uint32_t k0 = 0; k0 < Kp; k0 += 8) {
-                float x[8], hi[8], lo[8];
+            float qv[104];
+            if ((p.K & 3) == 0) {
+                const float4* q4 = reinterpret_cast<const float4*>(qr);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = (ok && (int)(k0 + u) < p.K) ? qr[k0 + u] : 0.f;
-                split8(x, hi, lo);
-                if (g == 0) tc_st8(abase + k0, hi); else tc_st8(abase + k0, lo);
+                for (int i = 0; i < 26; ++i) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && 4 * i < p.K) v = q4[i];
+                    qv[4 * i] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 104; ++i) qv[i] = (ok && i < p.K) ? qr[i] : 0.f;
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 13; ++c8) {
+                if ((uint32_t)(8 * c8) < Kp) {
+                    float x[8], hi[8], lo[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = qv[8 * c8 + u];
+                    split8(x, hi, lo);
+                    if (g == 0) tc_st8(abase + 8u * c8, hi); else tc_st8(abase + 8u * c8, lo);
+                }
             }
             tc_wait_st();
             tc_fence_before();
@@ -724,7 +754,16 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
                 Y[jq][u] = in ? evb[E_Y2 * p.dp + j] : 0.f;
             }
         const int n_bil_chunks = p.n_bil_rows / TC_NC;
-        float ai = 0.f, li = 0.f;
+        // a_bi / L_bi of bilinear row i: loaded one row AHEAD of their use so the load latency hides behind the chunks
+        // of the current row (the split ranges start at row boundaries)
+        float ai = 0.f, li = 0.f, ai_n = 0.f, li_n = 0.f;
+        {
+            const int i0 = c_begin / JQ;
+            if (nit > 0 && c_begin < n_bil_chunks && ok && i0 < p.dp) {
+                ai_n = p.aT[(size_t)i0 * p.B + b];
+                li_n = p.LT[(size_t)i0 * p.B + b];
+            }
+        }
         for (int it = 0; it < nit; ++it) {
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -733,8 +772,11 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
             if (c < n_bil_chunks) {
                 const int i = c / JQ, jq = c - i * JQ;
                 if (jq == 0 || it == 0) {
-                    ai = (ok && i < p.dp) ? p.aT[(size_t)i * p.B + b] : 0.f;
-                    li = (ok && i < p.dp) ? p.LT[(size_t)i * p.B + b] : 0.f;
+                    ai = ai_n; li = li_n;
+                    const int in = i + 1;
+                    const bool more = ok && in < p.dp && in * JQ < min(c_end, n_bil_chunks);
+                    ai_n = more ? p.aT[(size_t)in * p.B + b] : 0.f;
+                    li_n = more ? p.LT[(size_t)in * p.B + b] : 0.f;
                 }
 #pragma unroll
                 for (int q = 0; q < JQ; ++q)
@@ -773,11 +815,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) t[x] = 0.f;
                 }
-                if (ok) {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x)
-                        if (c0 + x < p.NK) o[c0 + x] = t[x];
-                }
+                if (ok) store_row32(o + c0, t, p.NK - c0, true);       // NK is a multiple of 16
             }
         }
     }
@@ -792,7 +830,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
 // dC: rows = operand rows n (one CTA per 128-row tile, batch range split NSb ways), reduction over examples.
 struct TcDcArgs {
     const float4* pop3;     // q^T chunks [bc][hi/lo][8][NK]
-    const float* ev; const float* sc;
+    const float* ev; const float* sc; const float* aT; const float* LT;
     float* out;             // gC_part [NSb][units*d*K]
     int B, d, dp, K, NK, DP;
     int n_bil_rows, n_rows_total, n_bchunks, NSb, hasM;
@@ -805,11 +843,35 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     const int ntile = blockIdx.x / p.NSb, split = blockIdx.x - ntile * p.NSb;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
-    uint32_t tmem_base;
-    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);
     const int per = (p.n_bchunks + p.NSb - 1) / p.NSb;
     const int c_begin = min(per * split, p.n_bchunks), c_end = min(per * (split + 1), p.n_bchunks);
     const int nit = c_end - c_begin;
+    // Per-example scalars of the generated operand, staged once in shared memory.  A 32-row quarter of the tile is one
+    // bilinear row i (P1 = a_bi, P2 = L_bi) or one selectional-preference table (P1 = 1, P2 = G2_b | G1_b); the tile
+    // holds TC_M / DP such sources.  Coalesced reads of the transposed copies aT / LT.
+    const int nsrc = TC_M / p.DP;
+    const int nbc = per * TC_NC;
+    float* sP1 = reinterpret_cast<float*>(smem_raw + TC_BSTAGES * B_BYTES + 256);
+    float* sP2 = sP1 + (size_t)nsrc * nbc;
+    for (int idx = threadIdx.x; idx < nsrc * nbc; idx += blockDim.x) {
+        const int src = idx / nbc, bl = idx - src * nbc;
+        const int b = c_begin * TC_NC + bl;
+        const int n0 = ntile * TC_M + src * p.DP;
+        float v1 = 0.f, v2 = 0.f;
+        if (b < p.B && bl < nit * TC_NC) {
+            if (n0 < p.n_bil_rows) {
+                const int i = n0 / p.DP;
+                if (i < p.d) { v1 = p.aT[(size_t)i * p.B + b]; v2 = p.LT[(size_t)i * p.B + b]; }
+            } else if (n0 < p.n_rows_total) {
+                v1 = 1.f;
+                v2 = p.sc[(size_t)b * SC_N + ((n0 - p.n_bil_rows) / p.DP == 0 ? SC_G2 : SC_G1)];
+            }
+        }
+        sP1[idx] = v1;
+        sP2[idx] = v2;
+    }
+    uint32_t tmem_base;
+    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);      // __syncthreads inside: staging visible
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
@@ -836,32 +898,48 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
             if (j < p.d) type = 1 + which;
         }
         const size_t estride = (size_t)E_NV * p.dp;
-        int oP1 = 0, oX, oP2, oY;
-        if (type == 0) { oP1 = E_A * p.dp + i; oX = E_R * p.dp + j; oP2 = E_L * p.dp + i; oY = E_Y2 * p.dp + j; }
-        else if (type == 1) { oX = E_A * p.dp + j; oP2 = SC_G2; oY = E_L * p.dp + j; }
-        else { oX = E_CV * p.dp + j; oP2 = SC_G1; oY = E_R * p.dp + j; }
-        if (type < 0) { oX = 0; oY = 0; oP2 = 0; }
-        for (int it = 0; it < nit; ++it) {
+        int oX = 0, oY = 0;
+        if (type == 0) { oX = E_R * p.dp + j; oY = E_Y2 * p.dp + j; }
+        else if (type == 1) { oX = E_A * p.dp + j; oY = E_L * p.dp + j; }
+        else if (type == 2) { oX = E_CV * p.dp + j; oY = E_R * p.dp + j; }
+        const int src = q4 / (p.DP >> 5);
+        const float* s1 = sP1 + (size_t)src * nbc + 8 * cg;
+        const float* s2 = sP2 + (size_t)src * nbc + 8 * cg;
+        // the 16 per-lane loads of chunk it+1 are issued before chunk it is generated and published (register double
+        // buffer): the generator loop no longer pays a global-memory latency per chunk
+        auto load = [&](int it, float (&x)[8], float (&y)[8]) {
+            const int b0 = (c_begin + it) * TC_NC + 8 * cg;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float* evb = p.ev + (size_t)min(b0 + u, p.B - 1) * estride;
+                x[u] = evb[oX];
+                y[u] = evb[oY];
+            }
+        };
+        auto process = [&](int it, const float (&x)[8], const float (&y)[8]) {
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int b0 = (c_begin + it) * TC_NC + 8 * cg;
-            // batched loads first (clamped addresses), arithmetic after: 32 independent loads in flight
-            float p1[8], p2[8], xv[8], yv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int b = min(b0 + u, p.B - 1);
-                const float* evb = p.ev + (size_t)b * estride;
-                xv[u] = evb[oX];
-                yv[u] = evb[oY];
-                p1[u] = (type == 0) ? evb[oP1] : 1.f;
-                p2[u] = (type == 0) ? evb[oP2] : p.sc[(size_t)b * SC_N + oP2];
-            }
+            const float4 pa = *reinterpret_cast<const float4*>(s1 + it * TC_NC), pb = *reinterpret_cast<const float4*>(s1 + it * TC_NC + 4);
+            const float4 qa = *reinterpret_cast<const float4*>(s2 + it * TC_NC), qb = *reinterpret_cast<const float4*>(s2 + it * TC_NC + 4);
+            const float p1[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            const float p2[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
             float g[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], xv[u], p2[u] * yv[u]) : 0.f;
+            for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], x[u], p2[u] * y[u]) : 0.f;
             mbar_wait(&br.a_empty[as], aph ^ 1);
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
+        };
+        float xa[8], ya[8], xb[8], yb[8];
+        if (nit > 0) load(0, xa, ya);
+        for (int it = 0; it < nit; it += 2) {
+            if (it + 1 < nit) load(it + 1, xb, yb);
+            process(it, xa, ya);
+            if (it + 1 < nit) {
+                if (it + 2 < nit) load(it + 2, xa, ya);
+                process(it + 1, xb, yb);
+            }
         }
         if (gw < 4) {
             if (nit > 0) {
@@ -881,11 +959,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) t[x] = 0.f;
                 }
-                if (type >= 0) {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x)
-                        if (c0 + x < p.K) o[c0 + x] = t[x];
-                }
+                if (type >= 0) store_row32(o + c0, t, p.K - c0, (p.K & 3) == 0);
             }
         }
     }
@@ -978,6 +1052,12 @@ int tc_init(rae_engine* h) {
     t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
     t.n_bchunks = (h->B + TC_NC - 1) / TC_NC;
     t.NSb = std::max(1, std::min(t.n_bchunks, h->num_sms / t.n_ntiles));
+    for (;;) {
+        const int per = (t.n_bchunks + t.NSb - 1) / t.NSb;       // batch chunks per CTA of the dC kernel
+        t.smem_dc = t.smem_dq + (size_t)(TC_M / DP) * 2 * per * TC_NC * sizeof(float);
+        if (t.smem_dc <= (size_t)h->max_smem_optin || t.NSb >= t.n_bchunks) break;
+        t.NSb = std::min(t.n_bchunks, t.NSb * 2);               // large batches: more batch splits, smaller staging area
+    }
     cudaError_t e;
     if ((e = cudaMalloc((void**)&t.bop, (size_t)(t.n_bil_chunks + t.n_sp_chunks) * 2 * t.KQ * TC_N * 16)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.vg, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
@@ -993,7 +1073,7 @@ int tc_init(rae_engine* h) {
         return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(" #KERN "): %s", cudaGetErrorString(e));
     RAE_TC_ATTR(k_tc_bilinear<32>, t.smem) RAE_TC_ATTR(k_tc_bilinear<64>, t.smem) RAE_TC_ATTR(k_tc_bilinear<128>, t.smem)
     RAE_TC_ATTR(k_tc_dq<32>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<64>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<128>, t.smem_dq)
-    RAE_TC_ATTR(k_tc_dc, t.smem_dq)
+    RAE_TC_ATTR(k_tc_dc, t.smem_dc)
 #undef RAE_TC_ATTR
     t.ready = true;
     return RAE_OK;
@@ -1078,11 +1158,11 @@ int tc_backward(rae_engine* h, cudaStream_t st) {
 int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     TcDcArgs p{};
-    p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.out = h->gC_part;
+    p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
     p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
     p.split_stride = (size_t)h->off_gWb;
-    k_tc_dc<<<t.n_ntiles * t.NSb, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    k_tc_dc<<<t.n_ntiles * t.NSb, TC_BWD_THREADS, t.smem_dc, st>>>(p);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

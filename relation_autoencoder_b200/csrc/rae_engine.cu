@@ -106,6 +106,12 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     if (overlap) {
         RAE_CUDA(h, cudaEventRecord(h->ev_fork0, st));
         RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_fork0, 0));
+        if (h->use_tc) {
+            // the pre-split dense operands depend only on the parameters: prepared beside the encoder
+            RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork0, 0));
+            if ((rc = tc_prepare_c(h, h->s2))) return rc;
+            RAE_CUDA(h, cudaEventRecord(h->ev_prepc, h->s2));
+        }
         if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
         if ((rc = sort_pairs(h, h->ent, n_occ, se, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
     }
@@ -125,7 +131,8 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 3 decoder forward
     if (h->use_tc) {
-        if ((rc = tc_prepare_c(h, st))) return rc;
+        if (overlap) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
+        else if ((rc = tc_prepare_c(h, st))) return rc;
         if ((rc = tc_prepare_p(h, a1, a2, st))) return rc;
         if ((rc = tc_contract(h, E_L, E_R, E_V1, E_V2, true, st))) return rc;
     } else {
@@ -348,7 +355,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_RC(dev_alloc(h, &h->gn2, (size_t)h->S * h->B));
     RAE_CREATE_CUDA(cudaMemset(h->ev, 0, sizeof(float) * (size_t)h->B * E_NV * h->dp));
     RAE_CREATE_CUDA(cudaMemset(h->sc, 0, sizeof(float) * (size_t)h->B * SC_N));
-    h->n_loss_part = (h->B + 7) / 8;
+    h->n_loss_part = (h->B + 3) / 4;   // one partial per CTA of k_score (4 examples each)
     RAE_CREATE_RC(dev_alloc(h, &h->loss_part, (size_t)h->n_loss_part));
     h->n_reg_part = 64 * 4;
     RAE_CREATE_RC(dev_alloc(h, &h->reg_part, (size_t)2 * h->n_reg_part));
@@ -386,6 +393,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork1, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join1, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_prepc, cudaEventDisableTiming));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
@@ -413,6 +421,7 @@ void rae_destroy(rae_engine* h) {
     if (h->ev_fork1) cudaEventDestroy(h->ev_fork1);
     if (h->ev_join1) cudaEventDestroy(h->ev_join1);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+    if (h->ev_prepc) cudaEventDestroy(h->ev_prepc);
     cudaFree(h->ent_cub_tmp);
     if (h->cost_pinned) cudaFreeHost(h->cost_pinned);
     if (h->pinned_neg) cudaFreeHost(h->pinned_neg);

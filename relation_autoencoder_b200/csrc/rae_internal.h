@@ -72,7 +72,7 @@ struct TcState {
     float4* bop = nullptr; // B operand chunks [chunk][hi/lo][KQ][64]
     float* vg = nullptr;   // [2][B][dp]
     float* wp = nullptr;   // [NS][2][B][dp]
-    int NK = 0, n_chunks32 = 0, NS2 = 0; size_t smem_dq = 0;
+    int NK = 0, n_chunks32 = 0, NS2 = 0; size_t smem_dq = 0, smem_dc = 0;
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
     float* dqp = nullptr;   // [NS2][B][NK]
     int n_ntiles = 0, n_bchunks = 0, NSb = 0;
@@ -123,7 +123,7 @@ struct rae_engine {
     void* cub_tmp; size_t cub_bytes;
     void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
     cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
-    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2;
+    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc;
     // explicit-step staging
     int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
     int32_t* pinned_neg;                         // host pinned [2,S,B]

@@ -794,21 +794,43 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
 }
 
 // ---- dense parameters ----
-// sum the batch-split partials of dC/dC1/dC2 and the per-CTA partials of dWb into the flat dense gradient buffer
-__global__ void k_dense_finalize(const float* __restrict__ part, int nsplit, size_t n_units_elems,
-                                 const float* __restrict__ dzsum_part, int n_dz_part, int K, float* __restrict__ out,
-                                 size_t off_wb) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_units_elems) {
-        float s = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * n_units_elems + i];
-        out[i] = s;
-    } else if (i < n_units_elems + (size_t)K) {
-        const int k = (int)(i - n_units_elems);
-        float s = 0.f;
-        for (int c = 0; c < n_dz_part; ++c) s += dzsum_part[(size_t)c * K + k];
-        out[off_wb + k] = s;
+// sum the batch-split partials of dC/dC1/dC2 and the per-CTA partials of dWb into the flat dense gradient buffer.
+// blocks [0, n_elem_blocks): 4 consecutive elements per thread (float4 when aligned), the splits summed in split order;
+// blocks [n_elem_blocks, +K): one CTA per column k of dWb - thread t sums partial rows t, t+256, ... and a fixed-shape
+// shared-memory tree combines the 256 values (deterministic).
+__global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, int nsplit, size_t n_units_elems,
+                                                        const float* __restrict__ dzsum_part, int n_dz_part, int K,
+                                                        float* __restrict__ out, size_t off_wb, int n_elem_blocks) {
+    if ((int)blockIdx.x < n_elem_blocks) {
+        const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (i0 >= n_units_elems) return;
+        if ((n_units_elems & 3) == 0) {
+            float4 s = *reinterpret_cast<const float4*>(part + i0);
+            for (int sp = 1; sp < nsplit; ++sp) {
+                const float4 x = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
+                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            }
+            *reinterpret_cast<float4*>(out + i0) = s;
+        } else {
+            for (size_t i = i0; i < min(i0 + 4, n_units_elems); ++i) {
+                float s = 0.f;
+                for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * n_units_elems + i];
+                out[i] = s;
+            }
+        }
+        return;
     }
+    __shared__ float red[256];
+    const int k = (int)blockIdx.x - n_elem_blocks;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < n_dz_part; c += 256) s += dzsum_part[(size_t)c * K + k];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[off_wb + k] = red[0];
 }
 
 // elementwise optimiser over up to 5 dense tensors in one launch (blockIdx.y = tensor):
@@ -1074,10 +1096,9 @@ int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const 
 
 int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
     const size_t n_units = (size_t)h->off_gWb;   // elements of [C | C1 | C2]
-    const size_t total = n_units + (size_t)h->K;
-    const int blocks = (int)((total + 255) / 256);
-    k_dense_finalize<<<blocks, 256, 0, st>>>(h->gC_part, h->gC_nsplit, n_units, h->dzsum_part, h->dz_part_used, h->K,
-                                             h->dense_grad, (size_t)h->off_gWb);
+    const int n_elem_blocks = (int)((n_units + 1023) / 1024);
+    k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, h->gC_nsplit, n_units, h->dzsum_part, h->dz_part_used, h->K,
+                                                          h->dense_grad, (size_t)h->off_gWb, n_elem_blocks);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1140,7 +1161,7 @@ int launch_cost(rae_engine* h, cudaStream_t st) {
             }
         }
     }
-    const int n_loss = (h->B + 7) / 8;
+    const int n_loss = h->n_loss_part;
     k_cost<<<1, 256, 0, st>>>(h->loss_part, n_loss, h->reg_part, n_reg, 1.0 / h->Z, h->cfg.adj * h->cfg.l1,
                               h->cfg.adj * h->cfg.l2, h->cost_dev);
     h->launches++;
