@@ -38,9 +38,14 @@ __device__ __forceinline__ float sigmoidf(float x) {
 __device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }
 
 // AdaGrad row rule, Optimizers.py:29-32: acc' = acc + g^2 ; p' = p - lr*g/(sqrt(acc') + 1e-6)
+// sqrt.approx / rcp.approx (1 ulp each, MUFU) instead of the IEEE sequences: the update kernels are instruction-bound and
+// the rule is checked against its float64 evaluation at 2e-6 relative (tests/test_gpu_parity.py), 3 ulp is 4e-7.
 __device__ __forceinline__ void adagrad_apply(float& p, float& acc, float g, float lr) {
     acc = fmaf(g, g, acc);
-    p = p - lr * g / (sqrtf(acc) + 1e-6f);
+    float r, inv;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(acc));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + 1e-6f));
+    p = fmaf(-lr * g, inv, p);
 }
 
 }  // namespace rae

@@ -34,6 +34,17 @@ namespace rae {
 
 namespace {
 
+// optional in-kernel timeline (build with -DRAE_TRACE): SM cycle counter of CTA-local milestones, [CTA][64] slots
+#ifdef RAE_TRACE
+__device__ unsigned long long* g_tc_trace = nullptr;
+#define TC_TRACE(slot)                                                                                         \
+    do {                                                                                                       \
+        if (g_tc_trace != nullptr && (slot) < 64) g_tc_trace[(size_t)blockIdx.x * 64 + (slot)] = clock64();    \
+    } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
+
 constexpr int TC_M = 128;          // rows per CTA (TMEM lanes)
 constexpr int TC_N = 64;           // forward: B-operand rows per chunk (TMEM columns per accumulator stage)
 constexpr int TC_TSTAGES = 4;      // forward: accumulator stages in TMEM
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
         if (split == p.NS - 1) c_end = p.n_bil_chunks + p.n_sp_chunks;
     }
     const int nit = c_end - c_begin;
+    if (threadIdx.x == 0) TC_TRACE(0);
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 8);
@@ -354,6 +366,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(1);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
@@ -368,7 +381,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 mbar_expect_tx(&b_full[s], B_BYTES);
                 bulk_g2s_pieces(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
                                 B_BYTES, &b_full[s]);
+                if (it == 0) TC_TRACE(2);
             }
+            TC_TRACE(3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
@@ -385,24 +400,44 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
             const int ksteps = p.KQ / 2;
             mbar_wait(a_full, 0);
             tc_fence_after();
-            for (int it = 0; it < nit; ++it) {
-                const int s = it % TC_BSTAGES, ts = it % TC_TSTAGES;
-                const uint32_t ph = (it / TC_BSTAGES) & 1, tph = (it / TC_TSTAGES) & 1;
-                mbar_wait(&t_empty[ts], tph ^ 1);
-                mbar_wait(&b_full[s], ph);
+            if (lane == 0) TC_TRACE(4);
+            // Two chunks are issued INTERLEAVED (different accumulator stages): consecutive MMAs into one accumulator are
+            // a dependent chain whose latency (~60 cycles, measured) exceeds the 32-cycle issue slot of a 128x64x8 MMA.
+            for (int it = 0; it < nit; it += 2) {
+                const bool two = it + 1 < nit;
+                const int s0 = it % TC_BSTAGES, ts0 = it % TC_TSTAGES;
+                const int s1 = (it + 1) % TC_BSTAGES, ts1 = (it + 1) % TC_TSTAGES;
+                mbar_wait(&t_empty[ts0], ((it / TC_TSTAGES) & 1) ^ 1);
+                if (lane == 0 && it < 6) TC_TRACE(8 + 2 * it);
+                mbar_wait(&b_full[s0], (it / TC_BSTAGES) & 1);
+                if (two) {
+                    mbar_wait(&t_empty[ts1], (((it + 1) / TC_TSTAGES) & 1) ^ 1);
+                    mbar_wait(&b_full[s1], ((it + 1) / TC_BSTAGES) & 1);
+                }
+                if (lane == 0 && it < 6) TC_TRACE(9 + 2 * it);
                 tc_fence_after();
-                const uint32_t dcol = tmem_base + (uint32_t)(ts * TC_N);
+                const uint32_t d0 = tmem_base + (uint32_t)(ts0 * TC_N), d1 = tmem_base + (uint32_t)(ts1 * TC_N);
                 if (elect_one()) {
-                    uint64_t dbh = dbh0[s], dbl = dbl0[s];
+                    uint64_t h0 = dbh0[s0], l0 = dbl0[s0], h1 = dbh0[s1], l1 = dbl0[s1];
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        tc_mma_tf32_ts(dcol, a_hi + 8u * ks, dbh, idesc, ks > 0 ? 1u : 0u);   // hi * hi
-                        tc_mma_tf32_ts(dcol, a_hi + 8u * ks, dbl, idesc, 1u);                 // hi * lo
-                        tc_mma_tf32_ts(dcol, a_lo + 8u * ks, dbh, idesc, 1u);                 // lo * hi
-                        dbh = desc_advance(dbh, 2u * TC_N * 16u);
-                        dbl = desc_advance(dbl, 2u * TC_N * 16u);
+                        const uint32_t acc = ks > 0 ? 1u : 0u;
+                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, h0, idesc, acc);                   // hi * hi
+                        if (two) tc_mma_tf32_ts(d1, a_hi + 8u * ks, h1, idesc, acc);
+                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, l0, idesc, 1u);                    // hi * lo
+                        if (two) tc_mma_tf32_ts(d1, a_hi + 8u * ks, l1, idesc, 1u);
+                        tc_mma_tf32_ts(d0, a_lo + 8u * ks, h0, idesc, 1u);                    // lo * hi
+                        if (two) tc_mma_tf32_ts(d1, a_lo + 8u * ks, h1, idesc, 1u);
+                        h0 = desc_advance(h0, 2u * TC_N * 16u);
+                        l0 = desc_advance(l0, 2u * TC_N * 16u);
+                        h1 = desc_advance(h1, 2u * TC_N * 16u);
+                        l1 = desc_advance(l1, 2u * TC_N * 16u);
                     }
-                    tc_commit(&b_empty[s]);     // smem stage reusable once these MMAs have read it
-                    tc_commit(&t_full[ts]);     // accumulator complete
+                    tc_commit(&b_empty[s0]);     // smem stages reusable once these MMAs have read them
+                    tc_commit(&t_full[ts0]);     // accumulators complete
+                    if (two) {
+                        tc_commit(&b_empty[s1]);
+                        tc_commit(&t_full[ts1]);
+                    }
                 }
                 __syncwarp();
             }
@@ -416,37 +451,41 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
         const bool ok = b < p.B;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         {
-            // group 0 writes the hi part, group 1 the lo part of this row's q (TF32 split), 8 relations per store.
-            // The whole row (K <= 104) is loaded first so that every load is in flight at once (one memory latency).
+            // q row -> TF32 hi / lo planes of the A operand in TMEM.  Group g converts relations [56 g, 56 g + 56): all of a
+            // thread's loads are issued before the first conversion (one memory latency) and the code stays small
+            // (straight-line code that runs once is paid in instruction-cache misses).
             const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
-            const uint32_t abase = lane_base + TC_FWD_ACOL + (g == 0 ? 0u : Kp);
-            float qv[104];
+            const int kb = 56 * g;
+            float qh[56];
             if ((p.K & 3) == 0) {
-                const float4* q4 = reinterpret_cast<const float4*>(qr);
+                const float4* q4 = reinterpret_cast<const float4*>(qr + kb);
 #pragma unroll
-                for (int i = 0; i < 26; ++i) {
+                for (int i = 0; i < 14; ++i) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && 4 * i < p.K) v = q4[i];
-                    qv[4 * i] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
+                    if (ok && kb + 4 * i < p.K) v = q4[i];
+                    qh[4 * i] = v.x; qh[4 * i + 1] = v.y; qh[4 * i + 2] = v.z; qh[4 * i + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 104; ++i) qv[i] = (ok && i < p.K) ? qr[i] : 0.f;
+                for (int i = 0; i < 56; ++i) qh[i] = (ok && kb + i < p.K) ? qr[kb + i] : 0.f;
             }
+            const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)kb, a_lo_col = a_hi_col + Kp;
 #pragma unroll
-            for (int c8 = 0; c8 < 13; ++c8) {
-                if ((uint32_t)(8 * c8) < Kp) {
+            for (int c8 = 0; c8 < 7; ++c8) {
+                if ((uint32_t)(kb + 8 * c8) < Kp) {
                     float x[8], hi[8], lo[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) x[u] = qv[8 * c8 + u];
+                    for (int u = 0; u < 8; ++u) x[u] = qh[8 * c8 + u];
                     split8(x, hi, lo);
-                    if (g == 0) tc_st8(abase + 8u * c8, hi); else tc_st8(abase + 8u * c8, lo);
+                    tc_st8(a_hi_col + 8u * c8, hi);
+                    tc_st8(a_lo_col + 8u * c8, lo);
                 }
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
+            if (warp == 4 && lane == 0) TC_TRACE(5);
         }
         const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
         constexpr int RW = (DP >= 64) ? 64 : 32;      // columns of R / w held per thread
@@ -470,7 +509,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 if (ok && i0 < p.d) L0 = evb[p.slotL * p.dp + i0];
                 if (DP == 32 && ok && i0 + 1 < p.d) L1 = evb[p.slotL * p.dp + i0 + 1];
             }
+            if (ew == 0 && lane == 0 && it < 4) TC_TRACE(24 + 2 * it);
             mbar_wait(&t_full[ts], tph);
+            if (ew == 0 && lane == 0 && it < 4) TC_TRACE(25 + 2 * it);
             tc_fence_after();
             const bool bil = c < p.n_bil_chunks;
             const int sc = c - p.n_bil_chunks;
@@ -527,20 +568,24 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
             }
             if (DP >= 64 && bil && ok && i0 < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0] = vsum;
         }
+        if (ew == 0 && lane == 0) TC_TRACE(6);
         if (ok) {
-            float* o = p.wp + (((size_t)split * 2 + g) * p.B + b) * p.dp;
+            float* o = p.wp + (((size_t)split * 2 + g) * p.B + b) * p.dp;      // dp % 4 == 0: 16-byte stores
 #pragma unroll
-            for (int c = 0; c < RW; ++c) {
+            for (int c = 0; c < RW; c += 4) {
                 const int j = jbase + c;
-                if (j < p.dp) o[j] = Wr[c];
+                if (j < p.dp) *reinterpret_cast<float4*>(o + j) = make_float4(Wr[c], Wr[c + 1], Wr[c + 2], Wr[c + 3]);
             }
         }
+        if (ew == 0 && lane == 0) TC_TRACE(7);
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(62);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (lane == 0) TC_TRACE(63);
     }
 }
 
@@ -662,7 +707,7 @@ __device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, co
     }
 }
 
-__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit) {
+__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base) {
     const uint32_t idesc = make_idesc_tf32(TC_M, NK);
     uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
 #pragma unroll
@@ -675,7 +720,9 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
         const int s = it % TC_BSTAGES, as = it & 1;
         const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it >> 1) & 1;
         mbar_wait(&br.a_full[as], aph);
+        if ((threadIdx.x & 31) == 0 && it < 3) TC_TRACE(trace_base + 2 * it);
         mbar_wait(&br.b_full[s], ph);
+        if ((threadIdx.x & 31) == 0 && it < 3) TC_TRACE(trace_base + 2 * it + 1);
         tc_fence_after();
         if (elect_one()) {
             const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
@@ -719,7 +766,9 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     uint32_t tmem_base;
+    if (threadIdx.x == 0) TC_TRACE(32);
     const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);
+    if (threadIdx.x == 0) TC_TRACE(33);
     constexpr int JQ = DP / 32;                 // chunks per bilinear row i
     // split the chunk range at row-i boundaries
     const int per = ((p.n_chunks32 + p.NS - 1) / p.NS + JQ - 1) / JQ * JQ;
@@ -732,7 +781,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     if (warp == 0) {
         if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), B_BYTES, c_begin, nit);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 8);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column octet
@@ -796,10 +845,13 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
                     g[u] = (ok && j < p.dp) ? fmaf(s2, evb[sy * p.dp + j], evb[sx * p.dp + j]) : 0.f;
                 }
             }
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(36 + 2 * it);
             mbar_wait(&br.a_empty[as], aph ^ 1);
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(37 + 2 * it);
         }
+        if (gw == 0 && lane == 0) TC_TRACE(34);
         if (gw < 4) {
             // ===== epilogue: accumulator row -> dq partial =====
             if (nit > 0) {
@@ -821,6 +873,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(35);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
@@ -870,8 +923,10 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
         sP1[idx] = v1;
         sP2[idx] = v2;
     }
+    if (threadIdx.x == 0) TC_TRACE(52);
     uint32_t tmem_base;
     const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);      // __syncthreads inside: staging visible
+    if (threadIdx.x == 0) TC_TRACE(53);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
@@ -879,7 +934,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     if (warp == 0) {
         if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 56);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
@@ -927,9 +982,11 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
             float g[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], x[u], p2[u] * y[u]) : 0.f;
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(44 + 2 * it);
             mbar_wait(&br.a_empty[as], aph ^ 1);
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(45 + 2 * it);
         };
         float xa[8], ya[8], xb[8], yb[8];
         if (nit > 0) load(0, xa, ya);
@@ -941,6 +998,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                 process(it + 1, xb, yb);
             }
         }
+        if (gw == 0 && lane == 0) TC_TRACE(55);
         if (gw < 4) {
             if (nit > 0) {
                 mbar_wait(br.acc_full, 0);
@@ -965,6 +1023,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(54);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
@@ -1015,6 +1074,14 @@ __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, c
 }
 
 int tc_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
+
+#ifdef RAE_TRACE
+}  // namespace
+extern "C" int rae_debug_set_trace(unsigned long long* dev_buf) {
+    return (int)cudaMemcpyToSymbol(g_tc_trace, &dev_buf, sizeof(dev_buf));
+}
+namespace {
+#endif
 
 }  // namespace
 

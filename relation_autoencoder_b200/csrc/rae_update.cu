@@ -104,12 +104,17 @@ __global__ void k_count_heads(const uint32_t* __restrict__ keys_s, int n, int32_
 }
 
 // ---- segmented reduction of sorted occurrences, balanced over warps -------------------------------------------------
-// Level 1: one warp per chunk of 32 sorted positions.  Runs (equal keys) that begin and end inside the chunk are
-// complete segments: reduced in position order and applied at once (fused optimiser RMW).  Runs that continue from the
-// previous chunk or into the next one write a partial row to scratch slot 2c (run starts at the chunk's first position)
-// or 2c+1.  Level 2: the warp of the chunk in which a multi-chunk segment STARTS walks the following chunks while their
-// first key continues the row, adds the partials in chunk order and applies the update.  Hot rows (Zipf) are thereby
-// spread over many warps; the summation order is a fixed function of the sorted layout -> bitwise reproducible.
+// Level 1 (k_rows_chunk): one warp per chunk of 32 sorted positions.
+//   phase 1  lanes = COLUMNS (one float4 each, tiles of 128 columns): the chunk's payload rows are streamed 8 at a time
+//            (coalesced row reads, all 8 in flight) and accumulated in position order; at every run boundary - warp-uniform,
+//            taken from the ballot of the keys - the finished run's sum is parked in the warp's shared-memory slab;
+//   phase 2  the runs are visited 4 at a time: table + accumulator rows of 4 runs are in flight together, the optimiser
+//            rule is applied once per row and the row is written back coalesced (or the reduced gradient row is emitted).
+//   Runs that continue from the previous chunk / into the next one park their partial row in scratch slot 2c / 2c+1.
+// Level 2 (k_*_long2): the CTA of the chunk in which a multi-chunk segment STARTS finds its extent, sums the partial rows
+// in chunk order and applies the update.  Hot rows (Zipf) are thereby spread over many warps; the summation order is a
+// fixed function of the sorted layout -> bitwise reproducible.  No atomics.
+
 struct EntArgs {
     const uint32_t* keys_s; const uint32_t* vals_s;
     const float* ev; const float* sc; const float* gn1; const float* gn2;
@@ -121,125 +126,6 @@ struct EntArgs {
     int adagrad, emit, apply;
 };
 
-template <int DT>
-__device__ __forceinline__ void entity_finish(const EntArgs& p, uint32_t row, const float (&g)[DT], float gb, int lane) {
-    if (p.emit) {
-#pragma unroll
-        for (int t = 0; t < DT; ++t) {
-            const int j = lane + 32 * t;
-            if (j < p.d) p.gA_dense[(size_t)row * p.d + j] = g[t];
-        }
-        if (lane == 0) p.gAb_dense[row] = gb;
-    }
-    if (p.apply) {
-#pragma unroll
-        for (int t = 0; t < DT; ++t) {
-            const int j = lane + 32 * t;
-            if (j < p.d) {
-                const size_t idx = (size_t)row * p.d + j;
-                float w = p.A[idx];
-                if (p.adagrad) {
-                    float a = p.accA[idx];
-                    adagrad_apply(w, a, g[t], p.lr);
-                    p.accA[idx] = a;
-                } else {
-                    w -= p.lr * g[t];
-                }
-                p.A[idx] = w;
-            }
-        }
-        if (lane == 0) {
-            float w = p.Ab[row];
-            if (p.adagrad) {
-                float a = p.accAb[row];
-                adagrad_apply(w, a, gb, p.lr);
-                p.accAb[row] = a;
-            } else {
-                w -= p.lr * gb;
-            }
-            p.Ab[row] = w;
-        }
-    }
-}
-
-template <int DT>
-__global__ void __launch_bounds__(256) k_entity_chunks(EntArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int n = p.n;
-    const int nchunks = (n + 31) >> 5;
-    const int PE = p.dp + 4;
-    for (int c = gw; c < nchunks; c += nw) {
-        const int p0 = c << 5;
-        const int cnt = min(32, n - p0);
-        const bool live = lane < cnt;
-        const uint32_t key = live ? p.keys_s[p0 + lane] : 0u;
-        const uint32_t mine = live ? p.vals_s[p0 + lane] : 0u;
-        // decode this lane's occurrence: o = slot*B + b
-        const int slot_m = (int)(mine / (uint32_t)p.B);
-        const int b_m = (int)(mine - (uint32_t)slot_m * (uint32_t)p.B);
-        int vs_m; float coef_m, bias_m;
-        if (slot_m == 0) { vs_m = E_GA1; coef_m = 1.f; bias_m = p.sc[(size_t)b_m * SC_N + SC_GU1]; }
-        else if (slot_m == 1) { vs_m = E_GA2; coef_m = 1.f; bias_m = p.sc[(size_t)b_m * SC_N + SC_GU2]; }
-        else if (slot_m < 2 + p.S) { vs_m = E_V1; coef_m = p.gn1[(size_t)(slot_m - 2) * p.B + b_m]; bias_m = coef_m; }
-        else { vs_m = E_V2; coef_m = p.gn2[(size_t)(slot_m - 2 - p.S) * p.B + b_m]; bias_m = coef_m; }
-        if (!live) { coef_m = 0.f; bias_m = 0.f; }
-        const int off_m = (b_m * E_NV + vs_m) * p.dp;
-        const uint32_t up = __shfl_up_sync(kFull, key, 1);
-        const unsigned heads = __ballot_sync(kFull, live && (lane == 0 || key != up));
-        const uint32_t key0 = __shfl_sync(kFull, key, 0), keyl = __shfl_sync(kFull, key, cnt - 1);
-        const bool cont_prev = p0 > 0 && p.keys_s[p0 - 1] == key0;
-        const bool cont_next = p0 + cnt < n && p.keys_s[p0 + cnt] == keyl;
-        unsigned m = heads;
-        while (m) {
-            const int r0 = __ffs(m) - 1;
-            m &= m - 1;
-            const int r1 = m ? (__ffs(m) - 1) : cnt;
-            const uint32_t row = __shfl_sync(kFull, key, r0);
-            float g[DT];
-#pragma unroll
-            for (int t = 0; t < DT; ++t) g[t] = 0.f;
-            float gb = 0.f;
-            constexpr int UN = 4;
-            for (int t0 = r0; t0 < r1; t0 += UN) {
-                float x[UN][DT], cf[UN], bs[UN];
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int src = (t0 + u) & 31;
-                    const int off = __shfl_sync(kFull, off_m, src);
-                    cf[u] = __shfl_sync(kFull, coef_m, src);
-                    bs[u] = __shfl_sync(kFull, bias_m, src);
-                    const bool ok = (t0 + u) < r1;
-                    if (!ok) { cf[u] = 0.f; bs[u] = 0.f; }
-#pragma unroll
-                    for (int t = 0; t < DT; ++t) {
-                        const int j = lane + 32 * t;
-                        x[u][t] = (ok && j < p.d) ? p.ev[(size_t)off + j] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    gb += bs[u];
-#pragma unroll
-                    for (int t = 0; t < DT; ++t) g[t] = fmaf(cf[u], x[u][t], g[t]);
-                }
-            }
-            const bool partial = (r0 == 0 && cont_prev) || (r1 == cnt && cont_next);
-            if (!partial) {
-                entity_finish<DT>(p, row, g, gb, lane);
-            } else {
-                float* o = p.part + (size_t)(2 * c + (r0 == 0 ? 0 : 1)) * PE;
-#pragma unroll
-                for (int t = 0; t < DT; ++t) {
-                    const int j = lane + 32 * t;
-                    if (j < p.d) o[j] = g[t];
-                }
-                if (lane == 0) o[p.dp] = gb;
-            }
-        }
-    }
-}
 
 // does a multi-chunk segment start in chunk c?  returns its first partial slot (or -1) and its row
 __device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ keys_s, int n, int c, uint32_t* row) {
@@ -256,55 +142,6 @@ __device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ k
     return 2 * c + 1;
 }
 
-template <int DT>
-__global__ void __launch_bounds__(256) k_entity_long(EntArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int n = p.n;
-    const int nchunks = (n + 31) >> 5;
-    const int PE = p.dp + 4;
-    for (int c0 = gw; c0 < nchunks; c0 += nw) {
-        uint32_t row = 0;
-        const int slot0 = long_segment_start(p.keys_s, n, c0, &row);
-        if (slot0 < 0) continue;
-        float g[DT];
-        const float* s0 = p.part + (size_t)slot0 * PE;
-#pragma unroll
-        for (int t = 0; t < DT; ++t) {
-            const int j = lane + 32 * t;
-            g[t] = (j < p.d) ? s0[j] : 0.f;
-        }
-        float gb = s0[p.dp];
-        constexpr int UN = 4;
-        bool more = true;
-        for (int c = c0 + 1; more; c += UN) {
-            float x[UN][DT], bs[UN];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                // chunk c+u belongs to the segment iff every chunk up to it starts with the row
-                const bool ok = more && (c + u) < nchunks && p.keys_s[(size_t)(c + u) << 5] == row;
-                more = ok;
-                const float* s = p.part + (size_t)(2 * (ok ? c + u : c0)) * PE;
-                bs[u] = ok ? s[p.dp] : 0.f;
-#pragma unroll
-                for (int t = 0; t < DT; ++t) {
-                    const int j = lane + 32 * t;
-                    x[u][t] = (ok && j < p.d) ? s[j] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                gb += bs[u];
-#pragma unroll
-                for (int t = 0; t < DT; ++t) g[t] += x[u][t];
-            }
-        }
-        entity_finish<DT>(p, row, g, gb, lane);
-    }
-}
-
-// ---- feature rows: grad W[f,:] = sum over the examples containing f (sorted order) of dz[b,:] ----
 struct WArgs {
     const uint32_t* keys_s; const uint32_t* vals_s;
     const float* dz;
@@ -315,136 +152,7 @@ struct WArgs {
     int adagrad, emit, apply;
 };
 
-template <int KT>
-__device__ __forceinline__ void w_finish(const WArgs& p, uint32_t row, const float (&g)[KT], int lane) {
-#pragma unroll
-    for (int t = 0; t < KT; ++t) {
-        const int k = lane + 32 * t;
-        if (k < p.K) {
-            const size_t idx = (size_t)row * p.K + k;
-            if (p.emit) p.gW_dense[idx] = g[t];
-            if (p.apply) {
-                float w = p.W[idx];
-                if (p.adagrad) {
-                    float a = p.accW[idx];
-                    adagrad_apply(w, a, g[t], p.lr);
-                    p.accW[idx] = a;
-                } else {
-                    w -= p.lr * g[t];
-                }
-                p.W[idx] = w;
-            }
-        }
-    }
-}
 
-template <int KT>
-__global__ void __launch_bounds__(256) k_w_chunks(WArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int n = p.n;
-    const int nchunks = (n + 31) >> 5;
-    for (int c = gw; c < nchunks; c += nw) {
-        const int p0 = c << 5;
-        const int cnt = min(32, n - p0);
-        const bool live = lane < cnt;
-        const uint32_t key = live ? p.keys_s[p0 + lane] : 0u;
-        const uint32_t mine = live ? p.vals_s[p0 + lane] : 0u;
-        const uint32_t up = __shfl_up_sync(kFull, key, 1);
-        const unsigned heads = __ballot_sync(kFull, live && (lane == 0 || key != up));
-        const uint32_t key0 = __shfl_sync(kFull, key, 0), keyl = __shfl_sync(kFull, key, cnt - 1);
-        const bool cont_prev = p0 > 0 && p.keys_s[p0 - 1] == key0;
-        const bool cont_next = p0 + cnt < n && p.keys_s[p0 + cnt] == keyl;
-        unsigned m = heads;
-        while (m) {
-            const int r0 = __ffs(m) - 1;
-            m &= m - 1;
-            const int r1 = m ? (__ffs(m) - 1) : cnt;
-            const uint32_t row = __shfl_sync(kFull, key, r0);
-            float g[KT];
-#pragma unroll
-            for (int t = 0; t < KT; ++t) g[t] = 0.f;
-            constexpr int UN = (KT <= 4) ? 8 : 2;
-            for (int t0 = r0; t0 < r1; t0 += UN) {
-                float x[UN][KT];
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const uint32_t b = __shfl_sync(kFull, mine, (t0 + u) & 31);
-                    const bool ok = (t0 + u) < r1;
-#pragma unroll
-                    for (int t = 0; t < KT; ++t) {
-                        const int k = lane + 32 * t;
-                        x[u][t] = (ok && k < p.K) ? p.dz[(size_t)b * p.K + k] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UN; ++u)
-#pragma unroll
-                    for (int t = 0; t < KT; ++t) g[t] += x[u][t];
-            }
-            const bool partial = (r0 == 0 && cont_prev) || (r1 == cnt && cont_next);
-            if (!partial) {
-                w_finish<KT>(p, row, g, lane);
-            } else {
-                float* o = p.part + (size_t)(2 * c + (r0 == 0 ? 0 : 1)) * p.K;
-#pragma unroll
-                for (int t = 0; t < KT; ++t) {
-                    const int k = lane + 32 * t;
-                    if (k < p.K) o[k] = g[t];
-                }
-            }
-        }
-    }
-}
-
-template <int KT>
-__global__ void __launch_bounds__(256) k_w_long(WArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int n = p.n;
-    const int nchunks = (n + 31) >> 5;
-    for (int c0 = gw; c0 < nchunks; c0 += nw) {
-        uint32_t row = 0;
-        const int slot0 = long_segment_start(p.keys_s, n, c0, &row);
-        if (slot0 < 0) continue;
-        float g[KT];
-        const float* s0 = p.part + (size_t)slot0 * p.K;
-#pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            const int k = lane + 32 * t;
-            g[t] = (k < p.K) ? s0[k] : 0.f;
-        }
-        constexpr int UN = (KT <= 4) ? 8 : 2;
-        bool more = true;
-        for (int c = c0 + 1; more; c += UN) {
-            float x[UN][KT];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const bool ok = more && (c + u) < nchunks && p.keys_s[(size_t)(c + u) << 5] == row;
-                more = ok;
-                const float* s = p.part + (size_t)(2 * (ok ? c + u : c0)) * p.K;
-#pragma unroll
-                for (int t = 0; t < KT; ++t) {
-                    const int k = lane + 32 * t;
-                    x[u][t] = (ok && k < p.K) ? s[k] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u)
-#pragma unroll
-                for (int t = 0; t < KT; ++t) g[t] += x[u][t];
-        }
-        w_finish<KT>(p, row, g, lane);
-    }
-}
-
-// ---- lane-per-position formulation (fast path) ------------------------------------------------------------------------
-// One warp per chunk of 32 sorted positions, lane = position.  The row payload is streamed 8 floats at a time; a warp
-// segmented inclusive scan (5 shuffle steps, predicates precomputed from the keys) gives every run's sum on its last
-// lane, which applies the optimiser (complete run) or stores the partial (run crosses a chunk boundary).  All runs of a
-// chunk are in flight together, loads are sector-aligned, and the reduction tree is a fixed function of the layout.
 struct ScanCtx {
     unsigned same;      // bit i: lane - 2^i belongs to the same run
     bool live, is_last, partial;
@@ -494,59 +202,216 @@ __device__ __forceinline__ void opt_apply4(float4& w, float4& a, const float4& g
     }
 }
 
-// requires K % 4 == 0
-__global__ void __launch_bounds__(256) k_w_scan(WArgs p) {
-    const int lane = threadIdx.x & 31;
+
+struct RowsArgs {
+    const uint32_t* keys_s; const uint32_t* vals_s; int n;
+    const float* payload;      // W: dz [B,K] ; entity: ev
+    int width;                 // floats per table row (K or d)
+    int pitch;                 // floats per partial slot in `part` (W: K ; entity: dp + 4, bias partial at [dp])
+    float* table; float* acc; float* g_out; float* part;
+    float lr; int adagrad, emit, apply;
+    // entity rows only
+    int B, S, dp; const float* sc; const float* gn1; const float* gn2;
+    float* tableb; float* accb; float* gb_out;
+};
+
+constexpr int ROWS_TILE = 128;     // columns per pass (one float4 per lane)
+
+// MODE 0: feature rows (payload row = dz[val,:], coefficient 1).  MODE 1: entity rows (occurrence decode, coefficient,
+// bias scalar).  VEC: the table rows are 16-byte aligned (width % 4 == 0).
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
+    extern __shared__ float4 slab4[];                      // [8 warps][32 runs][slab_cols / 4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     const int nchunks = (p.n + 31) >> 5;
-    const int nq = p.K >> 2;
+    const int sq = slab_cols >> 2;
+    float4* S = slab4 + (size_t)warp * 32 * sq;
     for (int c = gw; c < nchunks; c += nw) {
         const ScanCtx s = scan_ctx(p.keys_s, p.n, c, lane);
-        const uint32_t b = s.live ? p.vals_s[(c << 5) + lane] : 0u;
-        const float4* src = reinterpret_cast<const float4*>(p.dz + (size_t)b * p.K);
-        const size_t rowoff = (size_t)s.key * p.K;
-#pragma unroll 2
-        for (int q0 = 0; q0 < nq; q0 += 2) {
-            const bool two = q0 + 1 < nq;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (s.live) {
-                v0 = src[q0];
-                if (two) v1 = src[q0 + 1];
-            }
-            v0.x = seg_scan(v0.x, s.same); v0.y = seg_scan(v0.y, s.same); v0.z = seg_scan(v0.z, s.same); v0.w = seg_scan(v0.w, s.same);
-            v1.x = seg_scan(v1.x, s.same); v1.y = seg_scan(v1.y, s.same); v1.z = seg_scan(v1.z, s.same); v1.w = seg_scan(v1.w, s.same);
+        const int p0 = c << 5;
+        const int cnt = min(32, p.n - p0);
+        const uint32_t mine = s.live ? p.vals_s[p0 + lane] : 0u;
+        const unsigned heads = __ballot_sync(kFull, s.live && !(s.same & 1u));
+        const int nr = __popc(heads);
+        // chunk-level continuation flags (recomputed from lane-local data of scan_ctx: partial is set on the last lane of a
+        // partial run; the run-level predicate is rebuilt below from the first / last run)
+        const uint32_t key0 = __shfl_sync(kFull, s.key, 0), keyl = __shfl_sync(kFull, s.key, cnt - 1);
+        const bool cont_prev = p0 > 0 && p.keys_s[p0 - 1] == key0;
+        const bool cont_next = p0 + cnt < p.n && p.keys_s[p0 + cnt] == keyl;
+        int off_m;
+        float coef_m = 1.f;
+        if (MODE == 0) {
+            off_m = (int)mine * p.width;
+        } else {
+            const int slot_m = (int)(mine / (uint32_t)p.B);
+            const int b_m = (int)(mine - (uint32_t)slot_m * (uint32_t)p.B);
+            int vs; float bias;
+            if (slot_m == 0) { vs = E_GA1; coef_m = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU1]; }
+            else if (slot_m == 1) { vs = E_GA2; coef_m = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU2]; }
+            else if (slot_m < 2 + p.S) { vs = E_V1; coef_m = p.gn1[(size_t)(slot_m - 2) * p.B + b_m]; bias = coef_m; }
+            else { vs = E_V2; coef_m = p.gn2[(size_t)(slot_m - 2 - p.S) * p.B + b_m]; bias = coef_m; }
+            if (!s.live) { coef_m = 0.f; bias = 0.f; }
+            off_m = (b_m * E_NV + vs) * p.dp;
+            // bias column: lane = position, segmented scan, the last lane of a run applies / parks it
+            const float gb = seg_scan(bias, s.same);
             if (s.is_last) {
                 if (s.partial) {
-                    float4* o = reinterpret_cast<float4*>(p.part + (size_t)s.slot * p.K);
-                    o[q0] = v0;
-                    if (two) o[q0 + 1] = v1;
+                    p.part[(size_t)s.slot * p.pitch + p.dp] = gb;
                 } else {
-                    if (p.emit) {
-                        float4* o = reinterpret_cast<float4*>(p.gW_dense + rowoff);
-                        o[q0] = v0;
-                        if (two) o[q0 + 1] = v1;
-                    }
+                    if (p.emit) p.gb_out[s.key] = gb;
                     if (p.apply) {
-                        float4* wp = reinterpret_cast<float4*>(p.W + rowoff);
-                        float4* ap = reinterpret_cast<float4*>(p.accW + rowoff);
-                        float4 w0 = wp[q0], a0 = p.adagrad ? ap[q0] : v0;
-                        float4 w1 = v1, a1 = v1;
-                        if (two) { w1 = wp[q0 + 1]; if (p.adagrad) a1 = ap[q0 + 1]; }
-                        opt_apply4(w0, a0, v0, p.lr, p.adagrad);
-                        wp[q0] = w0;
-                        if (p.adagrad) ap[q0] = a0;
-                        if (two) {
-                            opt_apply4(w1, a1, v1, p.lr, p.adagrad);
-                            wp[q0 + 1] = w1;
-                            if (p.adagrad) ap[q0 + 1] = a1;
+                        float w = p.tableb[s.key];
+                        if (p.adagrad) {
+                            float a = p.accb[s.key];
+                            adagrad_apply(w, a, gb, p.lr);
+                            p.accb[s.key] = a;
+                        } else {
+                            w -= p.lr * gb;
                         }
+                        p.tableb[s.key] = w;
                     }
                 }
             }
         }
+        constexpr bool pay_vec = MODE == 1 || VEC;         // ev rows are always 16-byte aligned; dz rows iff K % 4 == 0
+        for (int col0 = 0; col0 < p.width; col0 += ROWS_TILE) {
+            const int q = col0 + 4 * lane;                 // first column of this lane
+            const bool inq = q < p.width;
+            // ---- phase 1: accumulate runs in position order ----
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            int r = -1;
+            constexpr int UN = 8;
+            for (int b0 = 0; b0 < cnt; b0 += UN) {
+                float4 v[UN];
+                float cf[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int pp = (b0 + u) & 31;
+                    const int off = __shfl_sync(kFull, off_m, pp);
+                    cf[u] = __shfl_sync(kFull, coef_m, pp);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + u < cnt && inq) {
+                        const float* src = p.payload + (size_t)off + q;
+                        if (pay_vec) {
+                            v[u] = *reinterpret_cast<const float4*>(src);
+                        } else {
+                            v[u].x = src[0];
+                            if (q + 1 < p.width) v[u].y = src[1];
+                            if (q + 2 < p.width) v[u].z = src[2];
+                            if (q + 3 < p.width) v[u].w = src[3];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int pp = b0 + u;
+                    if (pp < cnt) {
+                        if ((heads >> pp) & 1u) {
+                            if (r >= 0 && lane < sq) S[r * sq + lane] = a;
+                            ++r;
+                            a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (MODE == 0) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                        else { a.x = fmaf(cf[u], v[u].x, a.x); a.y = fmaf(cf[u], v[u].y, a.y); a.z = fmaf(cf[u], v[u].z, a.z); a.w = fmaf(cf[u], v[u].w, a.w); }
+                    }
+                }
+            }
+            if (r >= 0 && lane < sq) S[r * sq + lane] = a;
+            __syncwarp();
+            // ---- phase 2: one optimiser read-modify-write (or one emitted gradient row) per run ----
+            constexpr int RN = 4;
+            unsigned hm = heads;                          // run heads still to visit (lowest set bit = next run)
+            for (int r0 = 0; r0 < nr; r0 += RN) {
+                float4 w[RN], ac[RN];
+                uint32_t row[RN];
+                int kind[RN];            // 0 nothing, 1 complete run, 2 partial -> slot 2c, 3 partial -> slot 2c+1
+#pragma unroll
+                for (int u = 0; u < RN; ++u) {
+                    const int rr = r0 + u;
+                    kind[u] = 0;
+                    row[u] = 0;
+                    w[u] = ac[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < nr) {
+                        const int hp = __ffs(hm) - 1;                   // position of the rr-th run head
+                        hm &= hm - 1;
+                        row[u] = __shfl_sync(kFull, s.key, hp);
+                        const bool partial = (rr == 0 && cont_prev) || (rr == nr - 1 && cont_next);
+                        kind[u] = partial ? (hp == 0 ? 2 : 3) : 1;
+                        if (kind[u] == 1 && p.apply && inq) {
+                            const size_t idx = (size_t)row[u] * p.width + q;
+                            if (VEC) {
+                                w[u] = *reinterpret_cast<const float4*>(p.table + idx);
+                                if (p.adagrad) ac[u] = *reinterpret_cast<const float4*>(p.acc + idx);
+                            } else {
+                                w[u].x = p.table[idx];
+                                if (q + 1 < p.width) w[u].y = p.table[idx + 1];
+                                if (q + 2 < p.width) w[u].z = p.table[idx + 2];
+                                if (q + 3 < p.width) w[u].w = p.table[idx + 3];
+                                if (p.adagrad) {
+                                    ac[u].x = p.acc[idx];
+                                    if (q + 1 < p.width) ac[u].y = p.acc[idx + 1];
+                                    if (q + 2 < p.width) ac[u].z = p.acc[idx + 2];
+                                    if (q + 3 < p.width) ac[u].w = p.acc[idx + 3];
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RN; ++u) {
+                    if (kind[u] == 0 || !inq || lane >= sq) continue;
+                    const float4 g = S[(r0 + u) * sq + lane];
+                    if (kind[u] >= 2) {
+                        float* o = p.part + (size_t)(2 * c + (kind[u] - 2)) * p.pitch + q;
+                        if ((p.pitch & 3) == 0) {
+                            *reinterpret_cast<float4*>(o) = g;
+                        } else {
+                            o[0] = g.x;
+                            if (q + 1 < p.width) o[1] = g.y;
+                            if (q + 2 < p.width) o[2] = g.z;
+                            if (q + 3 < p.width) o[3] = g.w;
+                        }
+                        continue;
+                    }
+                    const size_t idx = (size_t)row[u] * p.width + q;
+                    if (p.emit) {
+                        if (VEC) {
+                            *reinterpret_cast<float4*>(p.g_out + idx) = g;
+                        } else {
+                            p.g_out[idx] = g.x;
+                            if (q + 1 < p.width) p.g_out[idx + 1] = g.y;
+                            if (q + 2 < p.width) p.g_out[idx + 2] = g.z;
+                            if (q + 3 < p.width) p.g_out[idx + 3] = g.w;
+                        }
+                    }
+                    if (p.apply) {
+                        float4 wv = w[u], av = ac[u];
+                        opt_apply4(wv, av, g, p.lr, p.adagrad);
+                        if (VEC) {
+                            *reinterpret_cast<float4*>(p.table + idx) = wv;
+                            if (p.adagrad) *reinterpret_cast<float4*>(p.acc + idx) = av;
+                        } else {
+                            p.table[idx] = wv.x;
+                            if (q + 1 < p.width) p.table[idx + 1] = wv.y;
+                            if (q + 2 < p.width) p.table[idx + 2] = wv.z;
+                            if (q + 3 < p.width) p.table[idx + 3] = wv.w;
+                            if (p.adagrad) {
+                                p.acc[idx] = av.x;
+                                if (q + 1 < p.width) p.acc[idx + 1] = av.y;
+                                if (q + 2 < p.width) p.acc[idx + 2] = av.z;
+                                if (q + 3 < p.width) p.acc[idx + 3] = av.w;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
 }
+
 
 // level 2, one CTA per chunk: if a multi-chunk segment starts here, lanes of warp 0 probe the first key of the next
 // chunks 32 at a time to find its extent, the 8 warps sum disjoint strided subsets of its partial rows, and the CTA
@@ -621,112 +486,6 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
             }
         }
         __syncthreads();
-    }
-}
-
-// entity rows, lane = occurrence: payload = coef * direction row (ev, stride dp, float4-aligned) and the bias scalar
-__global__ void __launch_bounds__(256) k_entity_scan(EntArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int nchunks = (p.n + 31) >> 5;
-    const int PE = p.dp + 4;
-    const int nq = p.dp >> 2;
-    const bool vec = (p.d & 3) == 0;
-    for (int c = gw; c < nchunks; c += nw) {
-        const ScanCtx s = scan_ctx(p.keys_s, p.n, c, lane);
-        const uint32_t mine = s.live ? p.vals_s[(c << 5) + lane] : 0u;
-        const int slot_m = (int)(mine / (uint32_t)p.B);
-        const int b_m = (int)(mine - (uint32_t)slot_m * (uint32_t)p.B);
-        int vs; float coef, bias;
-        if (slot_m == 0) { vs = E_GA1; coef = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU1]; }
-        else if (slot_m == 1) { vs = E_GA2; coef = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU2]; }
-        else if (slot_m < 2 + p.S) { vs = E_V1; coef = p.gn1[(size_t)(slot_m - 2) * p.B + b_m]; bias = coef; }
-        else { vs = E_V2; coef = p.gn2[(size_t)(slot_m - 2 - p.S) * p.B + b_m]; bias = coef; }
-        if (!s.live) { coef = 0.f; bias = 0.f; }
-        const float4* src = reinterpret_cast<const float4*>(p.ev + (size_t)(b_m * E_NV + vs) * p.dp);
-        const float gb = seg_scan(bias, s.same);
-        const size_t rowoff = (size_t)s.key * p.d;
-        if (s.is_last) {
-            if (s.partial) {
-                p.part[(size_t)s.slot * PE + p.dp] = gb;
-            } else {
-                if (p.emit) p.gAb_dense[s.key] = gb;
-                if (p.apply) {
-                    float w = p.Ab[s.key];
-                    if (p.adagrad) {
-                        float a = p.accAb[s.key];
-                        adagrad_apply(w, a, gb, p.lr);
-                        p.accAb[s.key] = a;
-                    } else {
-                        w -= p.lr * gb;
-                    }
-                    p.Ab[s.key] = w;
-                }
-            }
-        }
-#pragma unroll 2
-        for (int q0 = 0; q0 < nq; q0 += 2) {
-            const bool two = q0 + 1 < nq;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (s.live) {
-                v0 = src[q0];
-                if (two) v1 = src[q0 + 1];
-            }
-            v0.x *= coef; v0.y *= coef; v0.z *= coef; v0.w *= coef;
-            v1.x *= coef; v1.y *= coef; v1.z *= coef; v1.w *= coef;
-            v0.x = seg_scan(v0.x, s.same); v0.y = seg_scan(v0.y, s.same); v0.z = seg_scan(v0.z, s.same); v0.w = seg_scan(v0.w, s.same);
-            v1.x = seg_scan(v1.x, s.same); v1.y = seg_scan(v1.y, s.same); v1.z = seg_scan(v1.z, s.same); v1.w = seg_scan(v1.w, s.same);
-            if (s.is_last) {
-                if (s.partial) {
-                    float4* o = reinterpret_cast<float4*>(p.part + (size_t)s.slot * PE);
-                    o[q0] = v0;
-                    if (two) o[q0 + 1] = v1;
-                } else if (vec) {
-                    if (p.emit) {
-                        float4* o = reinterpret_cast<float4*>(p.gA_dense + rowoff);
-                        o[q0] = v0;
-                        if (two) o[q0 + 1] = v1;
-                    }
-                    if (p.apply) {
-                        float4* wp = reinterpret_cast<float4*>(p.A + rowoff);
-                        float4* ap = reinterpret_cast<float4*>(p.accA + rowoff);
-                        float4 w0 = wp[q0], a0 = p.adagrad ? ap[q0] : v0;
-                        float4 w1 = v1, a1 = v1;
-                        if (two) { w1 = wp[q0 + 1]; if (p.adagrad) a1 = ap[q0 + 1]; }
-                        opt_apply4(w0, a0, v0, p.lr, p.adagrad);
-                        wp[q0] = w0;
-                        if (p.adagrad) ap[q0] = a0;
-                        if (two) {
-                            opt_apply4(w1, a1, v1, p.lr, p.adagrad);
-                            wp[q0 + 1] = w1;
-                            if (p.adagrad) ap[q0 + 1] = a1;
-                        }
-                    }
-                } else {
-                    const float gv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = 4 * q0 + u;
-                        if (j < p.d) {
-                            const size_t idx = rowoff + j;
-                            if (p.emit) p.gA_dense[idx] = gv[u];
-                            if (p.apply) {
-                                float w = p.A[idx];
-                                if (p.adagrad) {
-                                    float a = p.accA[idx];
-                                    adagrad_apply(w, a, gv[u], p.lr);
-                                    p.accA[idx] = a;
-                                } else {
-                                    w -= p.lr * gv[u];
-                                }
-                                p.A[idx] = w;
-                            }
-                        }
-                    }
-                }
-            }
-        }
     }
 }
 
@@ -976,6 +735,25 @@ int count_unique(rae_engine* h, const uint32_t* keys_s, int64_t n, int32_t* out_
     return RAE_OK;
 }
 
+// level-1 launch shared by the three users of the sorted-occurrence update
+template <int MODE>
+static int launch_rows_chunk(rae_engine* h, RowsArgs& p, cudaStream_t st) {
+    const int64_t nchunks = ((int64_t)p.n + 31) / 32;
+    const int slab_cols = std::min(ROWS_TILE, (p.width + 3) & ~3);
+    const size_t smem = (size_t)8 * 32 * slab_cols * sizeof(float);
+    const bool vec = (p.width & 3) == 0;
+    auto kern = vec ? k_rows_chunk<MODE, true> : k_rows_chunk<MODE, false>;
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+    if (!attr_done[MODE][vec ? 1 : 0]) {
+        RAE_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * ROWS_TILE * (int)sizeof(float)));
+        attr_done[MODE][vec ? 1 : 0] = true;
+    }
+    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
+    kern<<<blocks, 256, smem, st>>>(p, slab_cols);
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
 int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t n_occ, bool emit_dense,
                          bool apply, cudaStream_t st) {
     if (n_occ <= 0) return RAE_OK;
@@ -990,14 +768,42 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
     int rc = ensure_part(h, &h->ent_part, &h->ent_part_cap, (size_t)(2 * nchunks) * (h->dp + 4));
     if (rc) return rc;
     p.part = h->ent_part;
-    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
-    const int dt = (h->d + 31) / 32;
-    (void)dt;
-    {
-        const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
-        k_entity_scan<<<blocks, 256, 0, st>>>(p);
-        k_entity_long2<<<blocks2, 256, sizeof(float) * 8 * (h->dp + 4), st>>>(p);
-    }
+    RowsArgs r{};
+    r.keys_s = keys_s; r.vals_s = vals_s; r.n = (int)n_occ;
+    r.payload = h->ev; r.width = h->d; r.pitch = h->dp + 4;
+    r.table = p.A; r.acc = p.accA; r.g_out = p.gA_dense; r.part = p.part;
+    r.lr = p.lr; r.adagrad = p.adagrad; r.emit = p.emit; r.apply = p.apply;
+    r.B = h->B; r.S = h->S; r.dp = h->dp; r.sc = h->sc; r.gn1 = h->gn1; r.gn2 = h->gn2;
+    r.tableb = p.Ab; r.accb = p.accAb; r.gb_out = p.gAb_dense;
+    if ((rc = launch_rows_chunk<1>(h, r, st))) return rc;
+    const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
+    k_entity_long2<<<blocks2, 256, sizeof(float) * 8 * (h->dp + 4), st>>>(p);
+    h->launches += 2;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+// feature rows (and the generic owner-side apply): table[row,:] updated with the sum of payload[val,:] over the row's
+// sorted occurrences
+static int rows_update(rae_engine* h, float* table, float* acc, float* g_out, int width, const uint32_t* keys_s,
+                       const uint32_t* vals_s, const float* payload, int64_t n, bool emit, bool apply, cudaStream_t st) {
+    if (n <= 0) return RAE_OK;
+    WArgs p{};
+    p.keys_s = keys_s; p.vals_s = vals_s;
+    p.dz = payload; p.W = table; p.accW = acc; p.gW_dense = g_out;
+    p.K = width; p.n = (int)n; p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = emit; p.apply = apply;
+    const int64_t nchunks = (n + 31) / 32;
+    int rc = ensure_part(h, &h->feat_part, &h->feat_part_cap, (size_t)(2 * nchunks) * width);
+    if (rc) return rc;
+    p.part = h->feat_part;
+    RowsArgs r{};
+    r.keys_s = keys_s; r.vals_s = vals_s; r.n = (int)n;
+    r.payload = payload; r.width = width; r.pitch = width;
+    r.table = table; r.acc = acc; r.g_out = g_out; r.part = p.part;
+    r.lr = p.lr; r.adagrad = p.adagrad; r.emit = emit; r.apply = apply;
+    if ((rc = launch_rows_chunk<0>(h, r, st))) return rc;
+    const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
+    k_w_long2<<<blocks2, 256, sizeof(float) * 8 * width, st>>>(p);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1005,37 +811,7 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
 
 int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t nnz, bool emit_dense,
                     bool apply, cudaStream_t st) {
-    if (nnz <= 0) return RAE_OK;
-    WArgs p{};
-    p.keys_s = keys_s; p.vals_s = vals_s;
-    p.dz = h->dz; p.W = h->P[RAE_P_W]; p.accW = h->ACC[RAE_P_W]; p.gW_dense = h->gW_dense;
-    p.K = h->K; p.n = (int)nnz; p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = emit_dense; p.apply = apply;
-    const int64_t nchunks = (nnz + 31) / 32;
-    int rc = ensure_part(h, &h->feat_part, &h->feat_part_cap, (size_t)(2 * nchunks) * h->K);
-    if (rc) return rc;
-    p.part = h->feat_part;
-    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
-    const int kt = (h->K + 31) / 32;
-#define RAE_WU(KT)                                     \
-    do {                                               \
-        k_w_chunks<KT><<<blocks, 256, 0, st>>>(p);     \
-        k_w_long<KT><<<blocks, 256, 0, st>>>(p);       \
-    } while (0)
-    if ((h->K & 3) == 0) {
-        const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
-        k_w_scan<<<blocks, 256, 0, st>>>(p);
-        k_w_long2<<<blocks2, 256, sizeof(float) * 8 * h->K, st>>>(p);
-    }
-    else if (kt <= 1) RAE_WU(1);
-    else if (kt <= 2) RAE_WU(2);
-    else if (kt <= 4) RAE_WU(4);
-    else if (kt <= 8) RAE_WU(8);
-    else if (kt <= 16) RAE_WU(16);
-    else RAE_WU(32);
-#undef RAE_WU
-    h->launches += 2;
-    RAE_CUDA(h, cudaGetLastError());
-    return RAE_OK;
+    return rows_update(h, h->P[RAE_P_W], h->ACC[RAE_P_W], h->gW_dense, h->K, keys_s, vals_s, h->dz, nnz, emit_dense, apply, st);
 }
 
 int build_row_keys(rae_engine* h, const int32_t* rows, int64_t n, cudaStream_t st) {
@@ -1061,37 +837,7 @@ int launch_gather_rows(rae_engine* h, const float* table, int64_t width, const i
 // sorted occurrences (the same kernels as the W update with dz := grads, K := width)
 int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const uint32_t* keys_s, const uint32_t* vals_s,
                       const float* grads, int64_t n, cudaStream_t st) {
-    if (n <= 0) return RAE_OK;
-    WArgs p{};
-    p.keys_s = keys_s; p.vals_s = vals_s;
-    p.dz = grads; p.W = table; p.accW = acc; p.gW_dense = nullptr;
-    p.K = width; p.n = (int)n; p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = 0; p.apply = 1;
-    const int64_t nchunks = (n + 31) / 32;
-    int rc = ensure_part(h, &h->feat_part, &h->feat_part_cap, (size_t)(2 * nchunks) * width);
-    if (rc) return rc;
-    p.part = h->feat_part;
-    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
-    const int kt = (width + 31) / 32;
-#define RAE_RA(KT)                                     \
-    do {                                               \
-        k_w_chunks<KT><<<blocks, 256, 0, st>>>(p);     \
-        k_w_long<KT><<<blocks, 256, 0, st>>>(p);       \
-    } while (0)
-    if ((width & 3) == 0) {
-        const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
-        k_w_scan<<<blocks, 256, 0, st>>>(p);
-        k_w_long2<<<blocks2, 256, sizeof(float) * 8 * width, st>>>(p);
-    }
-    else if (kt <= 1) RAE_RA(1);
-    else if (kt <= 2) RAE_RA(2);
-    else if (kt <= 4) RAE_RA(4);
-    else if (kt <= 8) RAE_RA(8);
-    else if (kt <= 16) RAE_RA(16);
-    else RAE_RA(32);
-#undef RAE_RA
-    h->launches += 2;
-    RAE_CUDA(h, cudaGetLastError());
-    return RAE_OK;
+    return rows_update(h, table, acc, nullptr, width, keys_s, vals_s, grads, n, false, true, st);
 }
 
 int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
