@@ -207,6 +207,22 @@ def _config(wl, args, world):
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args, wl, rank, world, local_rank):
+    # libraries (NCCL's version banner, ...) must not write to stdout: only the JSON line does
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args, wl, rank, world, local_rank)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+
+def _run_ours(args, wl, rank, world, local_rank):
     import torch
 
     from relation_autoencoder_b200.engine import Engine
@@ -282,6 +298,13 @@ def run_ours(args, wl, rank, world, local_rank):
     ms_e2e = max(ms_e2e, wall_e2e * 1e3)       # host-side staging counts
     # ---- (3) per-phase device times for the roofline of the dominant kernel ----
     phase_ms = None
+    dist_phase_ms = None
+    if world > 1:
+        eng.set_profiling(True)
+        for s in range(20):
+            eng.train_device((2 * (warmup + steps) + s) % nb, want_cost=False)
+        dist_phase_ms = eng.phase_times_ms()
+        eng.set_profiling(False)
     if world == 1:
         eng.set_profiling(True)
         acc = {}
@@ -298,7 +321,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
     pk = _peaks()
     ms_step = ms_dev / steps
     value = world * B * steps / (ms_dev * 1e-3)
@@ -322,6 +345,8 @@ def run_ours(args, wl, rank, world, local_rank):
                           "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"], "of": pk["source"],
                           "note": "whole step: SURVEY 8(d) algorithmic bytes / device time per step"},
     }
+    if dist_phase_ms:
+        line["dist_phase_ms"] = {k: round(v, 5) for k, v in dist_phase_ms.items()}
     if phase_ms is not None:
         line["phase_ms"] = {k: round(v, 5) for k, v in phase_ms.items()}
         line["roofline"] = _dominant_roofline(wl, st, phase_ms, pk)
@@ -339,7 +364,7 @@ def run_ours(args, wl, rank, world, local_rank):
                       "AdaGrad sweep (Theano not installable offline); %.2f s/step" % (done, B, sec),
             "sparse_row_variant": {"value": eps_sp, "sec_per_step": sec_sp,
                                    "note": "same math, touched rows only (what a tuned CPU port would do)"}}
-    print(json.dumps(line))
+    return line
 
 
 def _dominant_roofline(wl, st, phase_ms, pk):

@@ -193,6 +193,42 @@ int rae_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const
  * update is left to rae_train_step_end. */
 int rae_train_step_begin(rae_engine* h, int64_t batch_index, const int32_t* args1, const int32_t* args2, const int32_t* neg1,
                          const int32_t* neg2, int64_t neg_ld, void* stream);
+/* One row-sharded data-parallel step as TWO calls around the caller's dense-gradient all-reduce (everything the host
+ * side would otherwise issue one by one; the descriptor of a batch is built once per plan and reused every epoch):
+ *   rae_dist_step_begin : rae_fetch_rows for W / A / Ab into the compact tables, then rae_train_step_begin;
+ *   [caller: all-reduce of the flat dense gradient]
+ *   rae_dist_step_end   : rae_train_step_end, rae_pull_apply for W / A / Ab on the own shards, rae_copy_cost.
+ * All pointers are device pointers except the six HOST arrays of `world` device pointers. */
+typedef struct rae_dist_step {
+    int32_t world;
+    int32_t reserved;
+    const void* const* w_shards;  const void* const* a_shards;  const void* const* ab_shards;   /* every rank's table shard   */
+    const void* const* gw_bufs;   const void* const* ga_bufs;   const void* const* gab_bufs;    /* every rank's compact grads */
+    float* Wc; float* Ac; float* Abc;                      /* this rank's compact tables (bound as the engine's W / A / Ab) */
+    const int32_t* f_ids; int64_t n_f;                     /* distinct global feature rows of the batch, ascending          */
+    const int32_t* e_ids; int64_t n_e;                     /* distinct global entity rows of the batch, ascending           */
+    int64_t batch_index;
+    const int32_t* a1c; const int32_t* a2c; const int32_t* n1c; const int32_t* n2c; int64_t neg_ld;   /* compact entity slots */
+    float* W; float* accW; float* A; float* accA; float* Ab; float* accAb;                     /* own shards + accumulators */
+    const int32_t* fr_rows; const int32_t* fr_off; int64_t n_fr; const int32_t* f_src; const int32_t* f_slot;
+    const int32_t* er_rows; const int32_t* er_off; int64_t n_er; const int32_t* e_src; const int32_t* e_slot;
+    double* cost_dev;                                      /* receives the local cost (device)                              */
+    /* peer-memory synchronisation (optional: flag_bufs == NULL -> the caller orders the ranks with collectives) */
+    const void* const* flag_bufs;                          /* every rank's barrier flags, int32[RAE_MAX_PEERS] each          */
+    const void* const* dense_bufs;                         /* every rank's flat dense gradient [C | C1 | C2 | Wb], or NULL:   */
+    int32_t rank;                                          /*   NULL = the caller all-reduced the dense gradient itself      */
+    int32_t reserved2;
+} rae_dist_step;
+/* With flag_bufs set, rae_dist_step_end runs: barrier ("every rank has emitted") -> dense update, summing the ranks'
+ * dense gradients straight from dense_bufs in rank order when given -> the three pulls -> barrier ("every owner has
+ * applied").  The barrier is a one-warp kernel: release-store of the epoch into every peer's flag word, acquire-spin on the
+ * own flags (bounded: a rank that never arrives sets the status word instead of hanging the GPU, see rae_peer_status). */
+int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream);
+int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream);
+/* stand-alone barrier over the ranks' flag buffers (same kernel as inside rae_dist_step_end) */
+int rae_peer_barrier(rae_engine* h, const void* const* flag_bufs, int32_t world, int32_t rank, void* stream);
+/* synchronises and returns 0 if every peer barrier of this handle completed, RAE_ECUDA if one timed out */
+int rae_peer_status(rae_engine* h, void* stream);
 /* copy the last step's (local) cost into a DEVICE double (no synchronisation) */
 int rae_copy_cost(rae_engine* h, double* dst_device, void* stream);
 /* encoder on explicit device inputs (indptr has n_rows+1 entries; n_rows <= B): labels int64[n_rows], probs [n_rows, K] */

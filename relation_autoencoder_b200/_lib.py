@@ -38,6 +38,18 @@ class RaeConfig(C.Structure):
     ]
 
 
+class RaeDistStep(C.Structure):
+    _fields_ = ([("world", C.c_int32), ("reserved", C.c_int32)]
+                + [(n, C.c_void_p) for n in ("w_shards", "a_shards", "ab_shards", "gw_bufs", "ga_bufs", "gab_bufs", "Wc", "Ac", "Abc")]
+                + [("f_ids", C.c_void_p), ("n_f", C.c_int64), ("e_ids", C.c_void_p), ("n_e", C.c_int64), ("batch_index", C.c_int64)]
+                + [(n, C.c_void_p) for n in ("a1c", "a2c", "n1c", "n2c")] + [("neg_ld", C.c_int64)]
+                + [(n, C.c_void_p) for n in ("W", "accW", "A", "accA", "Ab", "accAb")]
+                + [("fr_rows", C.c_void_p), ("fr_off", C.c_void_p), ("n_fr", C.c_int64), ("f_src", C.c_void_p), ("f_slot", C.c_void_p)]
+                + [("er_rows", C.c_void_p), ("er_off", C.c_void_p), ("n_er", C.c_int64), ("e_src", C.c_void_p), ("e_slot", C.c_void_p)]
+                + [("cost_dev", C.c_void_p), ("flag_bufs", C.c_void_p), ("dense_bufs", C.c_void_p), ("rank", C.c_int32),
+                   ("reserved2", C.c_int32)])
+
+
 class RaeStepStats(C.Structure):
     _fields_ = [
         ("nnz", C.c_int64), ("unique_w_rows", C.c_int64), ("unique_e_rows", C.c_int64), ("entity_occ", C.c_int64),
@@ -78,6 +90,10 @@ _SIGNATURES = {
     "rae_fetch_rows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int64, _P, _P]),
     "rae_pull_apply": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P]),
     "rae_train_step_begin": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
+    "rae_dist_step_begin": (C.c_int, [_P, C.POINTER(RaeDistStep), _P]),
+    "rae_dist_step_end": (C.c_int, [_P, C.POINTER(RaeDistStep), _P]),
+    "rae_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
+    "rae_peer_status": (C.c_int, [_P, _P]),
     "rae_copy_cost": (C.c_int, [_P, _P, _P]),
     "rae_label_explicit": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "rae_set_profiling": (C.c_int, [_P, C.c_int32]),

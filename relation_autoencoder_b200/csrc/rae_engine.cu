@@ -129,6 +129,11 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = sort_pairs(h, h->feat, nnz, st, h->cub_tmp, h->cub_bytes))) return rc;
         f_keys_s = h->feat.keys_s; f_vals_s = h->feat.vals_s;
     }
+    if (h->pending_wait) {
+        // multi-GPU: the compact entity tables are being fetched on a side stream (rae_dist_step_begin)
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->pending_wait, 0));
+        h->pending_wait = nullptr;
+    }
     RAE_PHASE();   // 3 decoder forward
     if (h->use_tc) {
         if (overlap) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
@@ -394,9 +399,13 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join1, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_prepc, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_dfork, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_dfetch, cudaEventDisableTiming));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
+    RAE_CREATE_RC(dev_alloc(h, &h->peer_err_dev, 1));
+    RAE_CREATE_CUDA(cudaMemset(h->peer_err_dev, 0, sizeof(int32_t)));
     RAE_CREATE_RC(dev_alloc(h, &h->stat_dev, 2));
     RAE_CREATE_CUDA(cudaMemset(h->stat_dev, 0, 2 * sizeof(int32_t)));
     RAE_CREATE_RC(dev_alloc(h, &h->label_dev, (size_t)h->B));
@@ -412,7 +421,7 @@ void rae_destroy(rae_engine* h) {
     cudaFree(h->q); cudaFree(h->logq); cudaFree(h->dz); cudaFree(h->ev); cudaFree(h->sc); cudaFree(h->gn1); cudaFree(h->gn2);
     cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->own_dense);
     cudaFree(h->gC_part); cudaFree(h->own_gW); cudaFree(h->own_gA); cudaFree(h->own_gAb); cudaFree(h->cub_tmp);
-    cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev);
+    cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev); cudaFree(h->peer_err_dev);
     cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
     if (h->ev_created) for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
     if (h->s1) cudaStreamDestroy(h->s1);
@@ -422,6 +431,8 @@ void rae_destroy(rae_engine* h) {
     if (h->ev_join1) cudaEventDestroy(h->ev_join1);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->ev_prepc) cudaEventDestroy(h->ev_prepc);
+    if (h->ev_dfork) cudaEventDestroy(h->ev_dfork);
+    if (h->ev_dfetch) cudaEventDestroy(h->ev_dfetch);
     cudaFree(h->ent_cub_tmp);
     if (h->cost_pinned) cudaFreeHost(h->cost_pinned);
     if (h->pinned_neg) cudaFreeHost(h->pinned_neg);

@@ -123,7 +123,9 @@ struct rae_engine {
     void* cub_tmp; size_t cub_bytes;
     void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
     cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
-    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc;
+    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc, ev_dfork, ev_dfetch;
+    int barrier_epoch; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
+    cudaEvent_t pending_wait;                      // if set: the step's main stream waits for it before the decoder reads A
     // explicit-step staging
     int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
     int32_t* pinned_neg;                         // host pinned [2,S,B]
@@ -197,6 +199,8 @@ int launch_fetch_rows(rae_engine* h, const void* const* tables, int world, int64
 int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows_local, const int32_t* ent_off,
                       const int32_t* ent_src, const int32_t* ent_slot, int64_t n_rows, const void* const* grads, int world,
                       cudaStream_t st);
+int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st);
+int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser

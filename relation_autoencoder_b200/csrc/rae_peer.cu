@@ -103,12 +103,18 @@ __global__ void __launch_bounds__(256) k_pull_apply(float* __restrict__ table, f
                     w = reinterpret_cast<const float4*>(table + rowoff)[q0];
                     if (adagrad) a = reinterpret_cast<const float4*>(acc + rowoff)[q0];
                 }
-                for (int e = 0; e < ne; ++e) {                      // rank order: deterministic
-                    const int s = __shfl_sync(kFull, my_src, e), slot = __shfl_sync(kFull, my_slot, e);
-                    if (in) {
-                        const float4 x = ld_cv4(reinterpret_cast<const float4*>(grads.p[s] + (size_t)slot * width) + q0);
-                        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+                // contributions are read 4 at a time (remote loads over NVLink: ~2 us each, so they must be in flight
+                // together) and added in rank order: deterministic
+                for (int e0 = 0; e0 < ne; e0 += 4) {
+                    float4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int s = __shfl_sync(kFull, my_src, (e0 + u) & 31), slot = __shfl_sync(kFull, my_slot, (e0 + u) & 31);
+                        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (in && e0 + u < ne) x[u] = ld_cv4(reinterpret_cast<const float4*>(grads.p[s] + (size_t)slot * width) + q0);
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { g.x += x[u].x; g.y += x[u].y; g.z += x[u].z; g.w += x[u].w; }
                 }
                 if (in) {
                     if (adagrad) {
@@ -130,9 +136,15 @@ __global__ void __launch_bounds__(256) k_pull_apply(float* __restrict__ table, f
                     w = table[rowoff + k];
                     if (adagrad) a = acc[rowoff + k];
                 }
-                for (int e = 0; e < ne; ++e) {
-                    const int s = __shfl_sync(kFull, my_src, e), slot = __shfl_sync(kFull, my_slot, e);
-                    if (in) g += ld_cv(grads.p[s] + (size_t)slot * width + k);
+                for (int e0 = 0; e0 < ne; e0 += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int s = __shfl_sync(kFull, my_src, (e0 + u) & 31), slot = __shfl_sync(kFull, my_slot, (e0 + u) & 31);
+                        x[u] = (in && e0 + u < ne) ? ld_cv(grads.p[s] + (size_t)slot * width + k) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) g += x[u];
                 }
                 if (in) {
                     if (adagrad) {
@@ -156,7 +168,14 @@ __global__ void __launch_bounds__(256) k_pull_apply_scalars(float* __restrict__ 
                                                             float lr, int adagrad) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
         float g = 0.f;
-        for (int e = ent_off[i]; e < ent_off[i + 1]; ++e) g += ld_cv(grads.p[ent_src[e]] + ent_slot[e]);
+        const int e1 = ent_off[i + 1];
+        for (int e0 = ent_off[i]; e0 < e1; e0 += 4) {
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = (e0 + u < e1) ? ld_cv(grads.p[ent_src[e0 + u]] + ent_slot[e0 + u]) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g += x[u];
+        }
         const int r = rows_local[i];
         float w = table[r];
         if (adagrad) {
@@ -167,6 +186,70 @@ __global__ void __launch_bounds__(256) k_pull_apply_scalars(float* __restrict__ 
             w -= lr * g;
         }
         table[r] = w;
+    }
+}
+
+// ---- barrier over the ranks of the node -------------------------------------------------------------------------------
+// One warp.  Lane r publishes `epoch` in rank r's flag word [my rank] (release, system scope: everything this GPU wrote
+// before - emitted gradient rows, updated table rows - is visible to a peer that observes the flag) and then waits until
+// rank r has published >= epoch in OUR word [r] (acquire).  Epochs only grow, so a rank that is already one barrier ahead
+// still satisfies the wait.  The spin is bounded (~2 s): on timeout the status word is set and the kernel returns.
+struct FlagPtrs {
+    int32_t* p[RAE_MAX_PEERS];
+};
+
+__global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, int32_t* __restrict__ status) {
+    const int r = threadIdx.x;
+    __threadfence_system();
+    if (r < world) {
+        int32_t* dst = flags.p[r] + rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+        const int32_t* src = flags.p[rank] + r;
+        const long long t0 = clock64();
+        int32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 4000000000LL) {
+                *status = 1;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
+// dense optimiser step with the ranks' flat dense gradients summed on the fly, in rank order (identical on every rank):
+// replaces "all-reduce, then k_dense_apply" when the gradient is small enough to be read from every peer
+struct DenseSeg { float* p; float* acc; size_t begin, end; };      // [begin, end) of the flat gradient
+struct DenseSegs { DenseSeg s[4]; int count; };
+
+__global__ void __launch_bounds__(256) k_dense_apply_peers(DenseSegs segs, PeerPtrs grads, int world, size_t n, float* __restrict__ sum_out,
+                                                           float lr, int adagrad) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float x[RAE_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < RAE_MAX_PEERS; ++r) x[r] = r < world ? ld_cv(grads.p[r] + i) : 0.f;
+        float g = 0.f;
+#pragma unroll
+        for (int r = 0; r < RAE_MAX_PEERS; ++r) g += x[r];
+        if (sum_out) sum_out[i] = g;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < segs.count && i >= segs.s[k].begin && i < segs.s[k].end) {
+                const size_t j = i - segs.s[k].begin;
+                float w = segs.s[k].p[j];
+                if (adagrad) {
+                    float a = segs.s[k].acc[j];
+                    adagrad_apply(w, a, g, lr);
+                    segs.s[k].acc[j] = a;
+                } else {
+                    w -= lr * g;
+                }
+                segs.s[k].p[j] = w;
+            }
+        }
     }
 }
 
@@ -221,6 +304,45 @@ int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, co
         else
             k_pull_apply<false><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad);
     }
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st) {
+    if (world < 1 || world > RAE_MAX_PEERS || rank < 0 || rank >= world) return fail(h, RAE_EINVAL, "rae_peer_barrier: bad world / rank");
+    FlagPtrs fp;
+    memset(&fp, 0, sizeof(fp));
+    for (int r = 0; r < world; ++r) {
+        if (!flag_bufs[r]) return fail(h, RAE_EINVAL, "rae_peer_barrier: null flag buffer for rank %d", r);
+        fp.p[r] = static_cast<int32_t*>(const_cast<void*>(flag_bufs[r]));
+    }
+    h->barrier_epoch += 1;
+    k_peer_barrier<<<1, 32, 0, st>>>(fp, rank, world, h->barrier_epoch, h->peer_err_dev);
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st) {
+    PeerPtrs pp;
+    int rc = fill_peers(h, dense_bufs, world, &pp, "rae_dist_step_end(dense_bufs)");
+    if (rc) return rc;
+    if (h->dense_w) return fail(h, RAE_EINVAL, "peer dense update does not support l1 / l2 != 0");
+    DenseSegs segs{};
+    auto add = [&](int pid, int64_t begin, int64_t n) {
+        if (n <= 0) return;
+        DenseSeg& sg = segs.s[segs.count++];
+        sg.p = h->P[pid]; sg.acc = h->ACC[pid]; sg.begin = (size_t)begin; sg.end = (size_t)(begin + n);
+    };
+    const int64_t dd = h->hasM ? (int64_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (int64_t)h->d * h->K : 0;
+    add(RAE_P_C, h->off_gC, dd);
+    add(RAE_P_C1, h->off_gC1, dk);
+    add(RAE_P_C2, h->off_gC2, dk);
+    add(RAE_P_WB, h->off_gWb, h->K);
+    const size_t n = (size_t)h->n_dense;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 8);
+    k_dense_apply_peers<<<blocks, 256, 0, st>>>(segs, pp, world, n, nullptr, (float)h->cfg.lr, h->adagrad ? 1 : 0);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -294,6 +416,81 @@ int rae_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const
     if (h->adagrad && !acc) return fail(h, RAE_EINVAL, "rae_pull_apply: AdaGrad needs the accumulator table");
     if (n_rows > 0 && (!rows_local || !ent_off || !ent_src || !ent_slot)) return fail(h, RAE_EINVAL, "rae_pull_apply: null plan arrays");
     return launch_pull_apply(h, table, acc, width, rows_local, ent_off, ent_src, ent_slot, n_rows, grads, world, (cudaStream_t)stream);
+}
+
+int rae_peer_barrier(rae_engine* h, const void* const* flag_bufs, int32_t world, int32_t rank, void* stream) {
+    if (!h || !flag_bufs) return fail(h, RAE_EINVAL, "rae_peer_barrier: null argument");
+    return launch_peer_barrier(h, flag_bufs, world, rank, (cudaStream_t)stream);
+}
+
+int rae_peer_status(rae_engine* h, void* stream) {
+    if (!h) return RAE_EINVAL;
+    int32_t v = 0;
+    RAE_CUDA(h, cudaMemcpyAsync(&v, h->peer_err_dev, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RAE_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    if (v != 0) return fail(h, RAE_ECUDA, "a peer barrier timed out: a rank of the node did not arrive");
+    return RAE_OK;
+}
+
+int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
+    if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_begin: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const bool side = h->s1 != nullptr && !h->profiling;
+    if (side) {
+        // entity rows arrive on the side stream that sorts the entity occurrences next; the main stream (W rows ->
+        // encoder) only waits for them where the decoder first reads A
+        RAE_CUDA(h, cudaEventRecord(h->ev_dfork, st));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_dfork, 0));
+        if ((rc = rae_fetch_rows(h, d->a_shards, d->world, h->d, d->e_ids, d->n_e, d->Ac, h->s1))) return rc;
+        if ((rc = rae_fetch_rows(h, d->ab_shards, d->world, 1, d->e_ids, d->n_e, d->Abc, h->s1))) return rc;
+        RAE_CUDA(h, cudaEventRecord(h->ev_dfetch, h->s1));
+        h->pending_wait = h->ev_dfetch;
+    }
+    if ((rc = rae_fetch_rows(h, d->w_shards, d->world, h->K, d->f_ids, d->n_f, d->Wc, stream))) return rc;
+    if (!side) {
+        if ((rc = rae_fetch_rows(h, d->a_shards, d->world, h->d, d->e_ids, d->n_e, d->Ac, stream))) return rc;
+        if ((rc = rae_fetch_rows(h, d->ab_shards, d->world, 1, d->e_ids, d->n_e, d->Abc, stream))) return rc;
+    }
+    return rae_train_step_begin(h, d->batch_index, d->a1c, d->a2c, d->n1c, d->n2c, d->neg_ld, stream);
+}
+
+int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
+    if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_end: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const bool flags = d->flag_bufs != nullptr;
+    // (A) every rank has emitted its gradient rows and its dense gradient
+    if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
+    const bool side = h->s1 != nullptr && h->s2 != nullptr && !h->profiling;
+    if (side) {
+        // the three owner-side pulls are independent: entity rows and biases on the side streams, W rows + the dense update here
+        RAE_CUDA(h, cudaEventRecord(h->ev_dfork, st));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_dfork, 0));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_dfork, 0));
+    }
+    cudaStream_t sa = side ? h->s1 : st, sb = side ? h->s2 : st;
+    if (d->n_er > 0) {
+        if ((rc = rae_pull_apply(h, d->A, d->accA, h->d, d->er_rows, d->er_off, d->e_src, d->e_slot, d->n_er, d->ga_bufs, d->world, sa))) return rc;
+        if ((rc = rae_pull_apply(h, d->Ab, d->accAb, 1, d->er_rows, d->er_off, d->e_src, d->e_slot, d->n_er, d->gab_bufs, d->world, sb))) return rc;
+    }
+    if (d->n_fr > 0 && (rc = rae_pull_apply(h, d->W, d->accW, h->K, d->fr_rows, d->fr_off, d->f_src, d->f_slot, d->n_fr, d->gw_bufs,
+                                            d->world, stream))) return rc;
+    if (flags && d->dense_bufs != nullptr) {
+        if ((rc = launch_dense_apply_peers(h, d->dense_bufs, d->world, st))) return rc;
+    } else if ((rc = rae_train_step_end(h, stream))) {
+        return rc;
+    }
+    if (side) {
+        RAE_CUDA(h, cudaEventRecord(h->ev_join1, h->s1));
+        RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
+    }
+    // (B) every owner has applied: the next step may fetch, the compact gradient buffers may be overwritten
+    if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
+    if (d->cost_dev) return rae_copy_cost(h, d->cost_dev, stream);
+    return RAE_OK;
 }
 
 }  // extern "C"

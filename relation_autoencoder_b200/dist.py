@@ -181,7 +181,30 @@ class PeerBuffer:
             self.ptr = 0
 
 
-class CudaBackend:
+class GranularStep:
+    """``run_begin`` / ``run_end`` of a step spelled out call by call (the order is the contract; CudaBackend issues the same
+    sequence inside librae with one C call each)."""
+
+    def run_begin(self, de, b, a1c, a2c, n1c, n2c, neg_ld):
+        e_ids = de.eplan.ids_of(b)
+        self.fetch("W", de.fplan.ids_of(b))
+        self.fetch("A", e_ids)
+        self.fetch("Ab", e_ids)
+        self.local_step(b, a1c, a2c, n1c, n2c, neg_ld)
+
+    def run_end(self, de, b):
+        self.dense_apply()
+        for name, plan in (("W", de.fplan), ("A", de.eplan), ("Ab", de.eplan)):
+            lo, hi = plan.r_off[b], plan.r_off[b + 1]
+            self.pull_apply(name, de.shard[name], de.shard_acc[name], plan.rows_local[lo:hi], plan.ent_off[lo:hi + 1],
+                            plan.ent_src, plan.ent_slot)
+        return self.local_cost_tensor()
+
+    def plans_changed(self, de):
+        pass
+
+
+class CudaBackend(GranularStep):
     """Local numerical work on one GPU through librae.so (emit-only engine on compact tables) and the peer-memory
     fetch / pull kernels."""
 
@@ -239,8 +262,16 @@ class CudaBackend:
         self.compact = {"W": torch.zeros(f_cap, de.K, **f32), "A": torch.zeros(n_cap, de.d, **f32), "Ab": torch.zeros(n_cap, **f32)}
         self.grad_buf = {"W": PeerBuffer(self.lib, (f_cap, de.K), self.device), "A": PeerBuffer(self.lib, (n_cap, de.d), self.device),
                          "Ab": PeerBuffer(self.lib, (n_cap,), self.device)}
+        # the flat dense gradient and the barrier flags are peer-visible too: with them the step needs NO collective
+        n_dense = int(self.lib.rae_dense_grad_size(self.h))
+        self.grad_buf["dense"] = PeerBuffer(self.lib, (n_dense,), self.device)
+        self.grad_buf["flags"] = PeerBuffer(self.lib, (16,), self.device)          # int32[RAE_MAX_PEERS], zero-initialised
         self._exchange(self.grad_buf)
-        self.dense_grad = torch.zeros(int(self.lib.rae_dense_grad_size(self.h)), **f32)
+        self.dense_grad = self.grad_buf["dense"].tensor
+        self.peer_sync = True
+        # small dense gradients are summed straight from the peers' buffers inside the dense update; large ones (d = 128:
+        # 6.6 MB) go through NCCL's all-reduce, which moves 2(n-1)/n of the bytes instead of (n-1)
+        self.peer_dense = (de.world - 1) * n_dense * 4 <= (16 << 20)
 
     def bind_dense(self, dense: Dict[str, torch.Tensor], dense_acc: Dict[str, torch.Tensor]):
         g = lambda m, n: self._p(m.get(n))
@@ -284,6 +315,56 @@ class CudaBackend:
         self.eng._check(self.lib.rae_copy_cost(self.h, self._p(self.cost_t), self._stream), "rae_copy_cost")
         return self.cost_t
 
+    # -- fused step: one descriptor per batch, built when the plans change, two C calls per step
+    def plans_changed(self, de):
+        L = self.L
+        fp, ep = de.fplan, de.eplan
+        self.descs = []
+        if fp is None or ep is None:
+            return
+        self._peer_arrays = {k: b.peer_array() for k, b in list(self.shard_buf.items())}
+        self._grad_arrays = {k: b.peer_array() for k, b in list(self.grad_buf.items())}
+        vp = lambda arr: C.cast(arr, C.c_void_p)
+        el = lambda t, off: C.c_void_p(t.data_ptr() + 4 * int(off))
+        B, n_used = de.B, de.nb * de.B
+        for b in range(de.nb):
+            d = L.RaeDistStep()
+            d.world = de.world
+            d.w_shards, d.a_shards, d.ab_shards = vp(self._peer_arrays["W"]), vp(self._peer_arrays["A"]), vp(self._peer_arrays["Ab"])
+            d.gw_bufs, d.ga_bufs, d.gab_bufs = vp(self._grad_arrays["W"]), vp(self._grad_arrays["A"]), vp(self._grad_arrays["Ab"])
+            d.Wc, d.Ac, d.Abc = (self.compact[k].data_ptr() for k in ("W", "A", "Ab"))
+            d.f_ids, d.n_f = el(fp.u_ids, fp.u_off[b]), fp.u_off[b + 1] - fp.u_off[b]
+            d.e_ids, d.n_e = el(ep.u_ids, ep.u_off[b]), ep.u_off[b + 1] - ep.u_off[b]
+            d.batch_index = b
+            d.a1c, d.a2c = el(de.a1c, b * B), el(de.a2c, b * B)
+            d.n1c, d.n2c, d.neg_ld = el(de.n1c, b * B), el(de.n2c, b * B), n_used
+            d.W, d.accW = de.shard["W"].data_ptr(), de.shard_acc["W"].data_ptr()
+            d.A, d.accA = de.shard["A"].data_ptr(), de.shard_acc["A"].data_ptr()
+            d.Ab, d.accAb = de.shard["Ab"].data_ptr(), de.shard_acc["Ab"].data_ptr()
+            d.fr_rows, d.fr_off, d.n_fr = el(fp.rows_local, fp.r_off[b]), el(fp.ent_off, fp.r_off[b]), fp.r_off[b + 1] - fp.r_off[b]
+            d.f_src, d.f_slot = fp.ent_src.data_ptr(), fp.ent_slot.data_ptr()
+            d.er_rows, d.er_off, d.n_er = el(ep.rows_local, ep.r_off[b]), el(ep.ent_off, ep.r_off[b]), ep.r_off[b + 1] - ep.r_off[b]
+            d.e_src, d.e_slot = ep.ent_src.data_ptr(), ep.ent_slot.data_ptr()
+            d.cost_dev = self.cost_t.data_ptr()
+            d.flag_bufs = vp(self._grad_arrays["flags"])
+            d.dense_bufs = vp(self._grad_arrays["dense"]) if self.peer_dense else None
+            d.rank = de.rank
+            self.descs.append(d)
+
+    def run_begin(self, de, b, a1c, a2c, n1c, n2c, neg_ld):
+        d = self.descs[b]
+        if n1c is not None:                       # explicit compact negatives (train() with host ids): patched copy
+            d2 = self.L.RaeDistStep()
+            C.memmove(C.byref(d2), C.byref(d), C.sizeof(d))
+            d2.n1c, d2.n2c, d2.neg_ld = n1c.data_ptr(), n2c.data_ptr(), int(neg_ld)
+            self._keep_step = (d2, n1c, n2c)
+            d = d2
+        self.eng._check(self.lib.rae_dist_step_begin(self.h, C.byref(d), self._stream), "rae_dist_step_begin")
+
+    def run_end(self, de, b):
+        self.eng._check(self.lib.rae_dist_step_end(self.h, C.byref(self.descs[b]), self._stream), "rae_dist_step_end")
+        return self.cost_t
+
     def label(self, indptr: torch.Tensor, indices_compact: torch.Tensor):
         n = indptr.numel() - 1
         labels = torch.empty(n, dtype=torch.int64, device=self.device)
@@ -294,6 +375,7 @@ class CudaBackend:
 
     def close(self):
         if self.eng is not None:
+            self.eng._check(self.lib.rae_peer_status(self.h, self._stream), "peer barrier")
             torch.cuda.synchronize(self.device)
             if self.de.world > 1:
                 dist.barrier(group=self.de.group)      # nobody unmaps while a peer may still read
@@ -337,6 +419,8 @@ class DistributedEngine:
         self.nb = 0
         self._ready = False
         self._label_split = {}
+        self._profiling = False
+        self._phase_log = []
 
     def _rows_total(self, name):
         return self.F if name == "W" else self.N
@@ -361,6 +445,7 @@ class DistributedEngine:
                                      torch.as_tensor(np.ascontiguousarray(acc[n])).to(self.dev, dt).contiguous())
         if self._ready:
             self.backend.bind_dense(self.dense, self.dense_acc)
+            self.backend.plans_changed(self)          # shard / accumulator addresses are part of the step descriptors
         self._sync_all()
 
     def _sync_all(self):
@@ -460,27 +545,53 @@ class DistributedEngine:
         self.a2c = c[n_used:2 * n_used].contiguous()
         self.n1c = c[2 * n_used:(2 + S) * n_used].reshape(S, n_used).contiguous()
         self.n2c = c[(2 + S) * n_used:].reshape(S, n_used).contiguous()
+        self.backend.plans_changed(self)
         self._sync_all()
 
     # ------------------------------------------------------------------ the step
-    def _step(self, b, a1c, a2c, n1c, n2c, neg_ld, want_cost):
-        fp, ep, bk = self.fplan, self.eplan, self.backend
-        e_ids = ep.ids_of(b)
-        bk.fetch("W", fp.ids_of(b))
-        bk.fetch("A", e_ids)
-        bk.fetch("Ab", e_ids)
-        bk.local_step(b, a1c, a2c, n1c, n2c, neg_ld)
-        if self.world > 1:
+    def _step(self, b, n1c, n2c, neg_ld, want_cost):
+        """n1c / n2c None: the epoch's bound negatives (compact slots planned at bind time)."""
+        bk = self.backend
+        B = self.B
+        if n1c is None and not hasattr(bk, "descs"):
+            n1c, n2c, neg_ld = self.n1c[:, b * B:], self.n2c[:, b * B:], self.nb * B
+        ev = self._phase_events() if self._profiling else None
+        bk.run_begin(self, b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], n1c, n2c, neg_ld)
+        if ev: ev[1].record()
+        peer_sync = getattr(bk, "peer_sync", False)               # CUDA backend: flag barriers over peer memory inside run_end
+        if self.world > 1 and not getattr(bk, "peer_dense", False):
             dist.all_reduce(bk.dense_grad, group=self.group)      # sum of the ranks' dense gradients (C | C1 | C2 | Wb);
-        bk.dense_apply()                                          # also orders "every rank has emitted" before the pulls
-        for name, plan in (("W", fp), ("A", ep), ("Ab", ep)):
-            lo, hi = plan.r_off[b], plan.r_off[b + 1]
-            bk.pull_apply(name, self.shard[name], self.shard_acc[name], plan.rows_local[lo:hi], plan.ent_off[lo:hi + 1],
-                          plan.ent_src, plan.ent_slot)
-        cost = bk.local_cost_tensor()
-        if self.world > 1:
-            dist.all_reduce(cost, group=self.group)               # global cost; orders "every owner has applied"
+        if ev: ev[2].record()                                     # without peer_sync it also orders "every rank has emitted"
+        cost = bk.run_end(self, b)
+        if ev: ev[3].record()
+        if self.world > 1 and (want_cost or not peer_sync):
+            dist.all_reduce(cost, group=self.group)               # global cost; without peer_sync: "every owner has applied"
+        if ev:
+            ev[4].record()
+            self._phase_log.append(ev)
         return float(cost.item()) if want_cost else None
+
+    def _phase_events(self):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        return ev
+
+    def set_profiling(self, on: bool):
+        """Per-phase CUDA-event timing of the distributed step (fetch+local step | dense all-reduce | dense apply + pulls |
+        cost all-reduce / barrier).  Adds event records: never on for a timed run."""
+        self._profiling = bool(on) and self.dev.type == "cuda"
+        self._phase_log = []
+
+    def phase_times_ms(self) -> Dict[str, float]:
+        names = ("fetch_and_local_step", "dense_allreduce", "dense_apply_and_pull", "cost_allreduce_barrier")
+        if not self._phase_log:
+            return {}
+        torch.cuda.synchronize(self.dev)
+        acc = {n: 0.0 for n in names}
+        for ev in self._phase_log:
+            for i, n in enumerate(names):
+                acc[n] += ev[i].elapsed_time(ev[i + 1]) / len(self._phase_log)
+        return acc
 
     def train_device(self, batch_index: int, want_cost: bool = True):
         b, B = int(batch_index), self.B
@@ -488,9 +599,7 @@ class DistributedEngine:
             raise RuntimeError("batch_index %d out of range [0,%d)" % (b, self.nb))
         if self.eplan is None:
             raise RuntimeError("epoch negatives are not bound (bind_epoch_negatives)")
-        n_used = self.nb * B
-        return self._step(b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], self.n1c[:, b * B:], self.n2c[:, b * B:],
-                          n_used, want_cost)
+        return self._step(b, None, None, 0, want_cost)
 
     def train(self, batch_index: int, neg1, neg2) -> float:
         """func['train'](batch_index, neg1, neg2) with this rank's HOST negatives [S,B] (the columns of the bound epoch
@@ -506,7 +615,7 @@ class DistributedEngine:
             c = torch.searchsorted(u, t.reshape(-1)).clamp_(max=max(u.numel() - 1, 0))
             ok = ok & (u[c] == t.reshape(-1)).all()
             out.append(c.to(torch.int32).reshape(t.shape).contiguous())
-        cost = self._step(b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], out[0], out[1], B, True)
+        cost = self._step(b, out[0], out[1], B, True)
         if not bool(ok.item()):
             raise RuntimeError("train(): the negatives passed for batch %d are not the columns of the bound epoch negatives" % b)
         return cost
@@ -532,9 +641,6 @@ class DistributedEngine:
     def stats(self) -> dict:
         eng = getattr(self.backend, "eng", None)
         return eng.stats() if eng is not None else {}
-
-    def set_profiling(self, on: bool):
-        pass
 
     def close(self):
         self.backend.close()

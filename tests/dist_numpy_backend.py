@@ -7,9 +7,10 @@ import torch
 import torch.distributed as dist
 
 from oracle import rae_oracle as O
+from relation_autoencoder_b200.dist import GranularStep
 
 
-class NumpyBackend:
+class NumpyBackend(GranularStep):
     dtype = torch.float64
 
     def __init__(self, de):
