@@ -36,8 +36,10 @@ names.update({52: "DC entry", 53: "DC setup done", 55: "DC gen loop done", 54: "
 for i in range(3): names[56 + 2 * i] = "DC mma it%d a_full ok" % i; names[57 + 2 * i] = "DC mma it%d b_full ok" % i
 for i in range(4): names[44 + 2 * i] = "DC gen it%d computed" % i; names[45 + 2 * i] = "DC gen it%d published" % i
 for i in range(4): names[24 + 2 * i] = "epi it%d wait t_full" % i; names[25 + 2 * i] = "epi it%d t_full ok" % i
-for k in (36, 37, 38, 39): pass
-groups = {"FWD": [k for k in names if k < 32 or k >= 62], "DQ": [k for k in names if 32 <= k < 44 or 8 <= k < 14], "DC": [k for k in names if 44 <= k < 62]}
+for i in range(0, 8, 2): names[24 + i] = "epi it%d wait t_full" % i; names[25 + i] = "epi it%d t_full ok" % i
+names.update({16: "epi it4 ld0 done", 17: "epi it4 ld1 done", 18: "epi it4 chunk done", 20: "epi it6 ld0 done", 21: "epi it6 ld1 done", 22: "epi it6 chunk done"})
+for i in range(4): names[8 + 2 * i] = "mma it%d t_empty ok" % i; names[9 + 2 * i] = "mma it%d b_full ok" % i
+groups = {"FWD": [k for k in names if k < 32 or k >= 62]}
 for cta in (1, 127):
     r = t[cta]
     for gname, slots in groups.items():

@@ -25,6 +25,8 @@
 // Warp roles (all kernels): warp 0 = bulk-copy producer, 1 = MMA issuer (warp-uniform loop, elect.sync lane issues),
 // 2 = TMEM allocator, 3 = idle, 4.. = row-owning workers (epilogue / operand generators); worker warp w touches TMEM
 // lanes 32*(w%4)..+31 as the hardware requires.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "rae_common.cuh"
@@ -88,6 +90,42 @@ __device__ __forceinline__ void bulk_g2s_pieces(uint8_t* dst_smem, const uint8_t
     constexpr uint32_t PIECE = 8192;
     for (uint32_t off = 0; off < bytes; off += PIECE) bulk_g2s(dst_smem + off, src_gmem + off, min(PIECE, bytes - off), bar);
 }
+// ---- thread-block clusters: the B operand of a chunk is fetched ONCE per cluster (each CTA loads 1/cs of it and multicasts
+// the slice into every CTA's stage) instead of once per CTA: the contractions are bound by L2 -> SM operand traffic
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// slice `crank` of a chunk -> the same stage offset of every CTA of the cluster (cs == 1: plain copy of the whole chunk)
+__device__ __forceinline__ void bulk_g2s_chunk(uint8_t* stage, const uint8_t* chunk, uint32_t bytes, uint64_t* bar, uint32_t cs,
+                                               uint32_t crank) {
+    constexpr uint32_t PIECE = 8192;
+    const uint32_t slice = bytes / cs, base = slice * crank;
+    const uint16_t mask = (uint16_t)((1u << cs) - 1u);
+    for (uint32_t off = 0; off < slice; off += PIECE) {
+        const uint32_t nb = min(PIECE, slice - off);
+        if (cs == 1) bulk_g2s(stage + base + off, chunk + base + off, nb, bar);
+        else bulk_g2s_mc(stage + base + off, chunk + base + off, nb, bar, mask);
+    }
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
 // one lane of a converged warp (the loops around it stay warp-uniform, so descriptor math lives in uniform registers)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -322,13 +360,17 @@ struct TcArgs {
     int n_bil_chunks;       // chunks holding bilinear rows
     int n_sp_chunks;        // chunks holding C1/C2 rows (forward only)
     int NS;                 // splits of the bilinear chunk range per tile
+    int cs;                 // cluster size (1, 2 or 4): CTAs of a cluster = consecutive tiles of the SAME split
+    int ntile;
+    int dbg;                // measurement knobs (RAE_TC_DEBUG): 1 no operand copies after the first fills, 2 no MMAs, 4 no epilogue math
 };
 
 template <int DP>
 __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
+    const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;     // a cluster = cs consecutive tiles
+    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * p.KQ * TC_N * 16u;
     const uint32_t Kp = 4u * p.KQ;                          // relations padded to a multiple of 8
     uint8_t* smB = smem_raw;
@@ -354,7 +396,8 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 8);
-        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        // a stage is free once EVERY CTA of the cluster has consumed it (its next fill is multicast into all of them)
+        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], cs); }
         for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -364,6 +407,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();       // every CTA's barriers exist before a peer multicasts into them / arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TRACE(1);
@@ -378,9 +422,13 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 const int s = it % TC_BSTAGES;
                 const uint32_t ph = (it / TC_BSTAGES) & 1;
                 mbar_wait(&b_empty[s], ph ^ 1);
+                if ((p.dbg & 1) && it >= TC_BSTAGES) {      // measurement only: stage keeps its old contents
+                    mbar_arrive(&b_full[s]);
+                    continue;
+                }
                 mbar_expect_tx(&b_full[s], B_BYTES);
-                bulk_g2s_pieces(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
-                                B_BYTES, &b_full[s]);
+                bulk_g2s_chunk(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
+                               B_BYTES, &b_full[s], cs, crank);
                 if (it == 0) TC_TRACE(2);
             }
             TC_TRACE(3);
@@ -408,18 +456,18 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 const int s0 = it % TC_BSTAGES, ts0 = it % TC_TSTAGES;
                 const int s1 = (it + 1) % TC_BSTAGES, ts1 = (it + 1) % TC_TSTAGES;
                 mbar_wait(&t_empty[ts0], ((it / TC_TSTAGES) & 1) ^ 1);
-                if (lane == 0 && it < 6) TC_TRACE(8 + 2 * it);
+                if (lane == 0 && it < 4) TC_TRACE(8 + 2 * it);
                 mbar_wait(&b_full[s0], (it / TC_BSTAGES) & 1);
                 if (two) {
                     mbar_wait(&t_empty[ts1], (((it + 1) / TC_TSTAGES) & 1) ^ 1);
                     mbar_wait(&b_full[s1], ((it + 1) / TC_BSTAGES) & 1);
                 }
-                if (lane == 0 && it < 6) TC_TRACE(9 + 2 * it);
+                if (lane == 0 && it < 4) TC_TRACE(9 + 2 * it);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(ts0 * TC_N), d1 = tmem_base + (uint32_t)(ts1 * TC_N);
                 if (elect_one()) {
                     uint64_t h0 = dbh0[s0], l0 = dbl0[s0], h1 = dbh0[s1], l1 = dbl0[s1];
-                    for (int ks = 0; ks < ksteps; ++ks) {
+                    for (int ks = 0; ks < ((p.dbg & 2) ? 0 : ksteps); ++ks) {
                         const uint32_t acc = ks > 0 ? 1u : 0u;
                         tc_mma_tf32_ts(d0, a_hi + 8u * ks, h0, idesc, acc);                   // hi * hi
                         if (two) tc_mma_tf32_ts(d1, a_hi + 8u * ks, h1, idesc, acc);
@@ -432,10 +480,12 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                         h1 = desc_advance(h1, 2u * TC_N * 16u);
                         l1 = desc_advance(l1, 2u * TC_N * 16u);
                     }
-                    tc_commit(&b_empty[s0]);     // smem stages reusable once these MMAs have read them
+                    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+                    // smem stages reusable once these MMAs have read them (signalled to every CTA of the cluster)
+                    if (cs > 1) tc_commit_mc(&b_empty[s0], cmask); else tc_commit(&b_empty[s0]);
                     tc_commit(&t_full[ts0]);     // accumulators complete
                     if (two) {
-                        tc_commit(&b_empty[s1]);
+                        if (cs > 1) tc_commit_mc(&b_empty[s1], cmask); else tc_commit(&b_empty[s1]);
                         tc_commit(&t_full[ts1]);
                     }
                 }
@@ -509,9 +559,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 if (ok && i0 < p.d) L0 = evb[p.slotL * p.dp + i0];
                 if (DP == 32 && ok && i0 + 1 < p.d) L1 = evb[p.slotL * p.dp + i0 + 1];
             }
-            if (ew == 0 && lane == 0 && it < 4) TC_TRACE(24 + 2 * it);
+            if (ew == 0 && lane == 0 && it < 8) TC_TRACE(24 + it);
             mbar_wait(&t_full[ts], tph);
-            if (ew == 0 && lane == 0 && it < 4) TC_TRACE(25 + 2 * it);
+            if (ew == 0 && lane == 0 && it < 8) TC_TRACE(25 + it);
             tc_fence_after();
             const bool bil = c < p.n_bil_chunks;
             const int sc = c - p.n_bil_chunks;
@@ -522,11 +572,13 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
             for (int hf = 0; hf < 2; ++hf) {
                 float t[32];
                 tc_ld32(lane_base + (uint32_t)(ts * TC_N + 32 * hf), t);
+                if (ew == 0 && lane == 0 && (it == 4 || it == 6)) TC_TRACE(16 + 2 * (it - 4) + hf);
                 if (hf == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[ts]);     // accumulator stage free for the next MMA
                 }
+                if (p.dbg & 4) continue;
                 if (bil) {
                     if (DP >= 64) {
                         float v4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -567,6 +619,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 }
             }
             if (DP >= 64 && bil && ok && i0 < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0] = vsum;
+            if (ew == 0 && lane == 0 && (it == 4 || it == 6)) TC_TRACE(18 + 2 * (it - 4));
         }
         if (ew == 0 && lane == 0) TC_TRACE(6);
         if (ok) {
@@ -581,6 +634,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();       // nobody leaves while a peer may still write into its stages / barriers
     if (threadIdx.x == 0) TC_TRACE(62);
     if (warp == 2) {
         tc_fence_after();
@@ -1110,6 +1164,10 @@ int tc_init(rae_engine* h) {
     if (ns > pairs) ns = pairs;
     if (ns < 1) ns = 1;
     t.NS = ns;
+    // cluster of consecutive example tiles sharing the streamed operand (multicast): 4, 2 or none
+    t.cs = (t.ntile % 4 == 0) ? 4 : (t.ntile % 2 == 0 ? 2 : 1);
+    if (h->cfg.flags & RAE_FLAG_NO_CLUSTER) t.cs = 1;
+    if ((2 * t.KQ * TC_N * 16) % (16 * t.cs) != 0) t.cs = 1;
     t.smem = (size_t)TC_BSTAGES * 2 * t.KQ * TC_N * 16 + 256;
     // backward operands: NK = relations padded to a multiple of 16, reduction chunks of 32 rows
     t.NK = (h->K + 15) & ~15;
@@ -1185,9 +1243,30 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
     p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
     p.n_bil_chunks = t.n_bil_chunks; p.n_sp_chunks = with_sp ? t.n_sp_chunks : 0; p.NS = t.NS;
     const int grid = t.ntile * t.NS;
-    if (t.DP == 32) k_tc_bilinear<32><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
-    else if (t.DP == 64) k_tc_bilinear<64><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
-    else k_tc_bilinear<128><<<grid, TC_FWD_THREADS, t.smem, st>>>(p);
+    p.ntile = t.ntile;
+    p.cs = t.cs;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("RAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+    }
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_FWD_THREADS);
+        cfg.dynamicSmemBytes = t.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)t.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = t.cs > 1 ? 1 : 0;
+        cudaError_t e;
+        if (t.DP == 32) e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<32>, p);
+        else if (t.DP == 64) e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<64>, p);
+        else e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<128>, p);
+        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_bilinear launch (cluster %d): %s", t.cs, cudaGetErrorString(e));
+    }
     const size_t total = (size_t)h->B * h->dp;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.DP, t.NS, slotV, slotW);

@@ -66,7 +66,7 @@ struct TcState {
     int DP = 0;            // columns per row of M, padded: 32 / 64 / 128
     int KQ = 0;            // float4 planes along the relation axis (K padded to a multiple of 8, / 4)
     int n_bil_rows = 0, n_bil_chunks = 0, n_sp_chunks = 0, n_rows_total = 0;
-    int ntile = 0, NS = 0;
+    int ntile = 0, NS = 0, cs = 1;
     size_t smem = 0;
     float4* pop = nullptr; // P operand tiles  [tile][hi/lo][KQ][128]
     float4* bop = nullptr; // B operand chunks [chunk][hi/lo][KQ][64]

@@ -27,6 +27,8 @@ SHAPES = {
     "k100d30": dict(B=64, K=100, d=30, S=5, F=500, N=300, fbar=30),    # config 2 per-example shape
     "k100d128": dict(B=40, K=100, d=128, S=4, F=400, N=200, fbar=20),  # config 3 / target per-example shape
     "k130d70": dict(B=24, K=130, d=70, S=3, F=200, N=100, fbar=8),     # K chunked, d between tiles
+    "b512d128": dict(B=512, K=100, d=128, S=4, F=3000, N=900, fbar=20),  # 4 example tiles: cluster of 4, operand multicast
+    "b256d30": dict(B=256, K=100, d=30, S=5, F=2000, N=700, fbar=30),    # 2 example tiles: cluster of 2
 }
 
 
