@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librae.so")
+LIB_PATH = os.environ.get("RAE_LIB") or os.path.join(HERE, "librae.so")    # RAE_LIB: A/B measurement of two builds
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "rae.h")
 
 RAE_ABI_VERSION = 1

@@ -48,4 +48,23 @@ __device__ __forceinline__ void adagrad_apply(float& p, float& acc, float g, flo
     p = fmaf(-lr * g, inv, p);
 }
 
+// v[b,j], w[b,j] of the tensor-core contraction from its per-group / per-split partial buffers (rae_decoder_tc.cu):
+//   vg [2][B][dp]        DP=128: both epilogue groups hold a half-row partial; DP=64: group j%2; DP=32: group (j/2)%2
+//   wp [NS][2][B][dp]    sum over splits of the group partials (DP=128: only group j/64 holds column j)
+// The consumers (scoring, backward finish) read them directly: no separate combine pass.
+__device__ __forceinline__ void tc_combined_vw(const float* __restrict__ vg, const float* __restrict__ wp, int B, int dp, int DP,
+                                               int NS, int b, int j, float& v, float& w) {
+    const size_t total = (size_t)B * dp, idx = (size_t)b * dp + j;
+    if (DP == 128) v = vg[idx] + vg[total + idx];
+    else if (DP == 64) v = vg[(size_t)(j & 1) * total + idx];
+    else v = vg[(size_t)((j >> 1) & 1) * total + idx];
+    w = 0.f;
+    if (DP == 128) {
+        const int g = j >> 6;
+        for (int s = 0; s < NS; ++s) w += wp[(size_t)(2 * s + g) * total + idx];
+    } else {
+        for (int s = 0; s < 2 * NS; ++s) w += wp[(size_t)s * total + idx];
+    }
+}
+
 }  // namespace rae

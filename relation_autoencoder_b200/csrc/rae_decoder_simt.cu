@@ -479,6 +479,7 @@ struct ScoreArgs {
     double* loss_part;
     int B, S, d, dp, hasM, hasSP;
     float invZ;
+    const float* vg; const float* wp; int tcDP, tcNS;     // tensor path: v, w come from the contraction's partial buffers
 };
 
 // Two warps per example, one per side (side 0: neg1 / e1 slot, side 1: neg2 / e2 slot); 4 examples per CTA.  Both warps
@@ -500,8 +501,11 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
             const bool in = j < p.d;
             L[t] = in ? evb[E_L * p.dp + j] : 0.f;
             R[t] = in ? evb[E_R * p.dp + j] : 0.f;
-            const float v = (in && p.hasM) ? evb[E_V1 * p.dp + j] : 0.f;
-            const float w = (in && p.hasM) ? evb[E_V2 * p.dp + j] : 0.f;
+            float v = 0.f, w = 0.f;
+            if (in && p.hasM) {
+                if (p.vg != nullptr) tc_combined_vw(p.vg, p.wp, p.B, p.dp, p.tcDP, p.tcNS, b, j, v, w);
+                else { v = evb[E_V1 * p.dp + j]; w = evb[E_V2 * p.dp + j]; }
+            }
             const float c1 = (in && p.hasSP) ? evb[E_C1 * p.dp + j] : 0.f;
             const float c2 = (in && p.hasSP) ? evb[E_C2 * p.dp + j] : 0.f;
             const float V1 = v + c1, V2 = w + c2;
@@ -785,6 +789,7 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
     p.loss_part = h->loss_part;
     p.B = h->B; p.S = h->S; p.d = h->d; p.dp = h->dp; p.hasM = h->hasM; p.hasSP = h->hasSP;
     p.invZ = (float)(1.0 / h->Z);
+    if (h->use_tc) { p.vg = h->tc.vg; p.wp = h->tc.wp; p.tcDP = h->tc.DP; p.tcNS = h->tc.NS; }
     const int blocks = (h->B + 3) / 4;
     if (blocks > h->n_loss_part) return fail(h, RAE_EINVAL, "internal: loss_part too small");
     const int dt = (h->d + 31) / 32;

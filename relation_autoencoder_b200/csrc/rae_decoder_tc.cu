@@ -1088,17 +1088,26 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
 __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
                                                        const float* __restrict__ logq, const float* __restrict__ dqp, float* __restrict__ dz,
                                                        float* __restrict__ dzsum_part, int B, int K, int NK, int NS, int d, int dp,
-                                                       int hasSP, float ent_coef) {
+                                                       int hasSP, float ent_coef, const float* __restrict__ vg, const float* __restrict__ wp,
+                                                       int tcDP, int tcNS) {
     extern __shared__ float dzs[];     // [8][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * 8 + warp;
     if (b < B) {
         float* evb = ev + (size_t)b * E_NV * dp;
-        if (hasSP) {
+        {
+            // d cost / d L = M c (+ SP term), d cost / d R = M^T a (+ SP term): the recompute pass left M c and M^T a in
+            // the contraction's partial buffers
             const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
             for (int j = lane; j < d; j += 32) {
-                evb[E_GA1 * dp + j] = fmaf(gp + g2, evb[E_C1 * dp + j], evb[E_GA1 * dp + j]);
-                evb[E_GA2 * dp + j] = fmaf(gp + g1, evb[E_C2 * dp + j], evb[E_GA2 * dp + j]);
+                float ga1, ga2;
+                tc_combined_vw(vg, wp, B, dp, tcDP, tcNS, b, j, ga1, ga2);
+                if (hasSP) {
+                    ga1 = fmaf(gp + g2, evb[E_C1 * dp + j], ga1);
+                    ga2 = fmaf(gp + g1, evb[E_C2 * dp + j], ga2);
+                }
+                evb[E_GA1 * dp + j] = ga1;
+                evb[E_GA2 * dp + j] = ga2;
             }
         }
         float dot = 0.f;
@@ -1235,6 +1244,18 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
     return RAE_OK;
 }
 
+// the q-dependent operand alone (only the dC contraction at the end of the step needs it: prepared off the critical path)
+int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
+    TcState& t = h->tc;
+    const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
+    const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
+    k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
+                                                   h->quirk ? 1 : 0, h->ev);
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
 // one contraction pass: (slotL, slotR) in -> (slotV = M R [+SP rows to E_C1/E_C2 when with_sp], slotW = M^T L) out
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st) {
     TcState& t = h->tc;
@@ -1267,10 +1288,9 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
         else e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<128>, p);
         if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_bilinear launch (cluster %d): %s", t.cs, cudaGetErrorString(e));
     }
-    const size_t total = (size_t)h->B * h->dp;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_combine<<<blocks, 256, 0, st>>>(t.vg, t.wp, h->ev, h->B, h->d, h->dp, t.DP, t.NS, slotV, slotW);
-    h->launches += 2;
+    // no combine pass: k_score (forward) and k_tc_bwd_finish (backward) read the partial buffers directly
+    (void)slotV; (void)slotW;
+    h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
@@ -1294,7 +1314,7 @@ int tc_backward(rae_engine* h, cudaStream_t st) {
     h->dz_part_used = blocks;
     k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
                                                                   t.NK, t.NS2, h->d, h->dp, h->hasSP ? 1 : 0,
-                                                                  (float)(2.0 * h->cfg.alpha / h->Z));
+                                                                  (float)(2.0 * h->cfg.alpha / h->Z), t.vg, t.wp, t.DP, t.NS);
     h->launches += 3;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

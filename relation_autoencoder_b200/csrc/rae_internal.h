@@ -123,7 +123,7 @@ struct rae_engine {
     void* cub_tmp; size_t cub_bytes;
     void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
     cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
-    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc, ev_dfork, ev_dfetch;
+    cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc, ev_dfork, ev_dfetch, ev_q, ev_qt;
     int barrier_epoch; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
     cudaEvent_t pending_wait;                      // if set: the step's main stream waits for it before the decoder reads A
     // explicit-step staging
@@ -171,6 +171,8 @@ int tc_init(rae_engine* h);
 void tc_free(rae_engine* h);
 int tc_prepare_c(rae_engine* h, cudaStream_t st);
 int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // q^T operand + gather L, R
+int tc_prepare_qt(rae_engine* h, cudaStream_t st);                                      // q^T operand only
+int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // L, R only
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
 int tc_backward(rae_engine* h, cudaStream_t st);
 int tc_grad_dense(rae_engine* h, cudaStream_t st);
