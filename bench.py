@@ -349,7 +349,7 @@ def _run_ours(args, wl, rank, world, local_rank):
         line["dist_phase_ms"] = {k: round(v, 5) for k, v in dist_phase_ms.items()}
     if phase_ms is not None:
         line["phase_ms"] = {k: round(v, 5) for k, v in phase_ms.items()}
-        line["roofline"] = _dominant_roofline(wl, st, phase_ms, pk)
+        line["roofline"] = _dominant_roofline(wl, st, phase_ms, pk, args.workload)
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = min(data.n // B, 3) * B
         sub = SY.SyntheticData(data.indptr[: n_cpu + 1], data.indices[: data.indptr[n_cpu]], data.args1[:n_cpu],
@@ -367,8 +367,28 @@ def _run_ours(args, wl, rank, world, local_rank):
     return line
 
 
-def _dominant_roofline(wl, st, phase_ms, pk):
-    """Roofline of the phase with the largest share of the step (SURVEY 8d per-kernel algorithmic bytes / flops)."""
+PHASE_KERNELS = {      # phase -> the kernel it times (rae.h: one phase = one kernel of the step plus small helpers)
+    "encoder_forward": "k_encoder_forward_v4", "entity_sort": "cub::DeviceRadixSort (entity occurrences)",
+    "operand_prep": "k_tc_prep_c + k_tc_prep_qt", "contract_forward": "k_tc_bilinear", "score": "k_score",
+    "entity_update": "k_rows_chunk<1> + k_entity_long2", "w_update": "k_rows_chunk<0> + k_w_long2",
+    "contract_recompute": "k_tc_bilinear", "contract_dq": "k_tc_dq", "backward_finish": "k_tc_bwd_finish",
+    "contract_dc": "k_tc_dc", "dense_finalize": "k_dense_finalize", "cost": "k_cost", "dense_apply": "k_dense_apply",
+}
+
+
+def _traffic(workload, phase):
+    """DRAM bytes per launch of the phase's kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json,
+    made by profiles/make_traffic.py); None when that kernel was not captured for this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return t.get(workload, {}).get(phase, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def _dominant_roofline(wl, st, phase_ms, pk, workload):
+    """Roofline of the kernel with the largest share of the step: SURVEY 8(d) algorithmic bytes / flops of one launch
+    divided by its duration (CUDA events around the kernel on its stream, averaged over the profiled steps)."""
     K, d, S, B = wl["K"], wl["d"], wl["S"], wl["B"]
     nnz, UW, UE = st["nnz"], st["unique_w_rows"], st["unique_e_rows"]
     hasM = wl["model"] in ("rescal", "rescal+sp")
@@ -376,31 +396,31 @@ def _dominant_roofline(wl, st, phase_ms, pk):
     units = (d if hasM else 0) + (2 if hasSP else 0)
     bytes_of = {
         "encoder_forward": 4.0 * nnz * K + 4.0 * nnz + 8.0 * B * K,
-        "w_update": 16.0 * UW * K + 4.0 * nnz + 4.0 * nnz * K,
-        "entity_update": 16.0 * UE * (d + 1) + 8.0 * (2 + 2 * S) * B,
+        "w_update": 16.0 * UW * K + 8.0 * nnz + 4.0 * nnz * K,
+        "entity_update": 16.0 * UE * (d + 1) + 8.0 * (2 + 2 * S) * B + 4.0 * (2 + 2 * S) * B * d,
         "score": 4.0 * (2 * S) * B * (d + 1) + 4.0 * 2 * S * B,
         "dense_apply": 16.0 * (units * d * K + K),
+        "dense_finalize": 8.0 * (units * d * K + K),
     }
-    flops_of = {
-        "decoder_forward": 2.0 * B * units * d * K,
-        "decoder_backward": 4.0 * B * units * d * K,
-        "grad_dense": 2.0 * B * units * d * K,
-    }
-    name = max(phase_ms, key=lambda k: phase_ms[k])
+    gemm = 2.0 * B * units * d * K
+    flops_of = {"contract_forward": gemm, "contract_recompute": gemm, "contract_dq": gemm, "contract_dc": gemm}
+    cand = {k: v for k, v in phase_ms.items() if k in bytes_of or k in flops_of}
+    name = max(cand, key=lambda k: cand[k])
     t = phase_ms[name] * 1e-3
     total = sum(phase_ms.values())
+    common = {"kernel": PHASE_KERNELS.get(name, name), "phase": name, "ms_per_launch": phase_ms[name],
+              "share_of_step": phase_ms[name] / total, "of": pk["source"], "traffic": _traffic(workload, name)}
     if name in flops_of:
         ach = flops_of[name] / t / 1e12
-        # the contraction must be fp32-accurate; the tensor roofline denominator is the measured bf16 cuBLAS peak
-        # (TF32 dense is half of it nominally; 3xTF32 costs another 3x) - stated, not hidden
-        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_sustained"], "traffic": None, "share_of_step": phase_ms[name] / total,
-                "of": pk["source"], "algorithmic_flops_per_launch": flops_of[name],
-                "note": "fp32-accurate contraction flops / measured bf16 cuBLAS peak (sustained)"}
-    ach = bytes_of.get(name, 0.0) / t / 1e9
-    return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": None, "share_of_step": phase_ms[name] / total, "of": pk["source"],
-            "algorithmic_bytes_per_launch": bytes_of.get(name, 0.0)}
+        # fp32-accurate contraction (3 TF32 MMAs per product); the denominator is the measured bf16 cuBLAS peak of
+        # MEASURED_PEAKS.json (no TF32 figure there; dense TF32 is nominally half of it) - stated, not hidden
+        return dict(common, bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_sustained"],
+                    algorithmic_flops_per_launch=flops_of[name],
+                    note="algorithmic flops 2*B*(d+2)*d*K per launch / measured bf16 cuBLAS peak (sustained); the kernel issues 3x "
+                         "that in TF32")
+    ach = bytes_of[name] / t / 1e9
+    return dict(common, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                algorithmic_bytes_per_launch=bytes_of[name])
 
 
 def main():

@@ -236,6 +236,15 @@ int rae_copy_cost(rae_engine* h, double* dst_device, void* stream);
 int rae_label_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, int64_t n_rows, int64_t* labels,
                        float* probs, void* stream);
 
+/* ---- negative sampling on the device (replaces NegativeExampleGenerator.get_negative_samples, NegativeExampleGenerator.py:14-32)
+ * out[i] = searchsorted(cum, uniform(0, cum_last)) for i in [0, n), bit-exact with the reference's host recipe on a legacy
+ * numpy RandomState: mt_state is the generator state on the device (uint32 key[624] followed by pos, as from
+ * rng.get_state()) and is ADVANCED in place exactly as numpy would (2 words per draw), so it can be handed back with
+ * rng.set_state().  cum: device float64[n_cum] (OieData.py:57-59), cum_last = cum[n_cum-1] (host copy).
+ * scratch_words: device uint32[2n].  The caller reshapes out to (S, n_examples) (NegativeExampleGenerator.py:24). */
+int rae_sample_negatives(rae_engine* h, uint32_t* mt_state, const double* cum, int64_t n_cum, double cum_last, int32_t* out,
+                         int64_t n, uint32_t* scratch_words, void* stream);
+
 /* ---- func['label_<split>'] ------------------------------------------------------------------------------ */
 /* labels = argmax of the scores, first max wins (RelationClassifier.py:45-47); probs = softmax.  Device outputs. */
 int rae_label(rae_engine* h, int32_t split_id, int64_t batch_index, int64_t* labels, float* probs, void* stream);
@@ -255,10 +264,19 @@ int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted
                             int64_t* n_occ, int64_t* n_seg, void* stream);
 int rae_get_step_stats(rae_engine* h, rae_step_stats* out);
 
-/* per-phase device timing of a step (CUDA events on the step's stream; bench.py's roofline leg).  Phases:
- * 0 encoder_forward 1 entity_sort 2 feature_sort 3 decoder_forward 4 score 5 decoder_backward 6 grad_dense 7 cost
- * 8 entity_update 9 w_update 10 dense_apply.  Profiling adds event records between kernels: never on for a timed run. */
-#define RAE_NUM_PHASES 11
+/* per-phase device timing of a step (CUDA events on the step's stream; bench.py's roofline leg).  One phase = one kernel of
+ * the step (plus its small helpers), in stream order:
+ *  0 encoder_forward   k_encoder_forward*                      8 contract_recompute  k_tc_bilinear (M c, M^T a)
+ *  1 entity_sort       k_entity_keys + CUB radix sort          9 contract_dq         k_tc_transpose_al + k_tc_dq
+ *  2 feature_sort      (cached at bind time: ~0)              10 backward_finish     k_tc_bwd_finish
+ *  3 operand_prep      k_tc_prep_c + k_tc_prep_qt             11 contract_dc         k_tc_dc
+ *  4 contract_forward  k_tc_bilinear                          12 dense_finalize      k_dense_finalize
+ *  5 score             k_score                                13 cost                k_cost (+ k_reg_norms)
+ *  6 entity_update     k_rows_chunk<1> + k_entity_long2       14 dense_apply         k_dense_apply
+ *  7 w_update          k_rows_chunk<0> + k_w_long2
+ * (SIMT contraction path: 4 = k_bilinear_forward, 8-10 = k_bilinear_backward, 11 = k_grad_dense.)
+ * Profiling serialises the side streams and adds event records between kernels: never on for a timed run. */
+#define RAE_NUM_PHASES 15
 int rae_set_profiling(rae_engine* h, int32_t on);
 /* milliseconds of each phase of the last profiled step (synchronises); ms must hold RAE_NUM_PHASES floats */
 int rae_get_phase_times(rae_engine* h, float* ms);

@@ -27,7 +27,7 @@ RAE_FLAG_NO_FEATURE_CACHE = 16
 RAE_FLAG_EMIT_ONLY = 32
 RAE_FLAG_NO_CLUSTER = 64
 RAE_ENODEVICE = -5
-RAE_NUM_PHASES = 11
+RAE_NUM_PHASES = 15
 
 
 class RaeConfig(C.Structure):
@@ -97,6 +97,7 @@ _SIGNATURES = {
     "rae_peer_status": (C.c_int, [_P, _P]),
     "rae_copy_cost": (C.c_int, [_P, _P, _P]),
     "rae_label_explicit": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    "rae_sample_negatives": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, C.c_int64, _P, _P]),
     "rae_set_profiling": (C.c_int, [_P, C.c_int32]),
     "rae_get_phase_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rae_phase_name": (C.c_char_p, [C.c_int32]),

@@ -1296,10 +1296,12 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
 }
 
 // backward on the tensor path: dL, dR (through the forward kernel with L := a, R := c), dq, softmax backward -> dz
-int tc_backward(rae_engine* h, cudaStream_t st) {
+// backward on the tensor path, three parts (separately timed phases): (1) M c and M^T a through the forward kernel with
+// L := a, R := c; (2) dq contraction; (3) per-example finish: dL, dR, entropy term, softmax backward -> dz
+int tc_backward_recompute(rae_engine* h, cudaStream_t st) { return tc_contract(h, E_A, E_CV, E_GA1, E_GA2, false, st); }
+
+int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    int rc = tc_contract(h, E_A, E_CV, E_GA1, E_GA2, false, st);
-    if (rc) return rc;
     k_tc_transpose_al<<<dim3((h->B + 31) / 32, (h->dp + 31) / 32), 256, 0, st>>>(h->ev, h->B, h->d, h->dp, t.aT, t.LT);
     TcDqArgs p{};
     p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.dqp = t.dqp;
@@ -1309,13 +1311,20 @@ int tc_backward(rae_engine* h, cudaStream_t st) {
     if (t.DP == 32) k_tc_dq<32><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     else if (t.DP == 64) k_tc_dq<64><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     else k_tc_dq<128><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    h->launches += 2;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+
+int tc_backward_finish(rae_engine* h, cudaStream_t st) {
+    TcState& t = h->tc;
     const int blocks = (h->B + 7) / 8;
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
     k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
                                                                   t.NK, t.NS2, h->d, h->dp, h->hasSP ? 1 : 0,
                                                                   (float)(2.0 * h->cfg.alpha / h->Z), t.vg, t.wp, t.DP, t.NS);
-    h->launches += 3;
+    h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }

@@ -150,7 +150,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         RAE_CUDA(h, cudaStreamWaitEvent(st, h->pending_wait, 0));
         h->pending_wait = nullptr;
     }
-    RAE_PHASE();   // 3 decoder forward
+    RAE_PHASE();   // 3 dense / q-dependent operand preparation of the tensor path
     if (h->use_tc) {
         if (overlap) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
         else if ((rc = tc_prepare_c(h, st))) return rc;
@@ -159,18 +159,27 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         } else if ((rc = tc_prepare_p(h, a1, a2, st))) {
             return rc;
         }
+    }
+    RAE_PHASE();   // 4 forward contraction: v = M R, w = M^T L, c1, c2
+    if (h->use_tc) {
         if ((rc = tc_contract(h, E_L, E_R, E_V1, E_V2, true, st))) return rc;
     } else {
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
     }
-    RAE_PHASE();   // 4 scoring / loss / d cost / d score
+    RAE_PHASE();   // 5 scoring / loss / d cost / d score
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
-    RAE_PHASE();   // 5 decoder backward
+    RAE_PHASE();   // 6 (profiling / no-overlap order only) entity-row update, see below
+    RAE_PHASE();   // 7
+    RAE_PHASE();   // 8 backward: recompute M c, M^T a
     if (h->use_tc) {
-        if ((rc = tc_backward(h, st))) return rc;
+        if ((rc = tc_backward_recompute(h, st))) return rc;
     } else {
         if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
     }
+    RAE_PHASE();   // 9 backward: dq contraction
+    if (h->use_tc && (rc = tc_backward_dq(h, st))) return rc;
+    RAE_PHASE();   // 10 backward: per-example finish -> dz
+    if (h->use_tc && (rc = tc_backward_finish(h, st))) return rc;
     if (overlap) {
         // dz and the per-example vectors are final: the sparse-row updates can start on their own streams
         RAE_CUDA(h, cudaEventRecord(h->ev_fork1, st));
@@ -181,18 +190,19 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->emit_only, sw))) return rc;
         RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
     }
-    RAE_PHASE();   // 6 dense-parameter gradients
+    RAE_PHASE();   // 11 dense-parameter gradients: dC contraction
     if (h->use_tc) {
         if (sprep) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_qt, 0));
         if ((rc = tc_grad_dense(h, st))) return rc;
     } else {
         if ((rc = launch_grad_dense_simt(h, st))) return rc;
     }
+    RAE_PHASE();   // 12 sum of the batch-split partials
     if ((rc = launch_dense_finalize(h, st))) return rc;
-    RAE_PHASE();   // 7 cost (uses the pre-update parameters for the regulariser value)
+    RAE_PHASE();   // 13 cost (uses the pre-update parameters for the regulariser value)
     if ((rc = launch_cost(h, st))) return rc;
     // emit-only (row-sharded multi-GPU): the tables are per-step compact copies whose every row is touched, so the
-    // emitted gradient buffers need no clearing and nothing is applied here (the owner shard applies, rae_sparse_rows_apply)
+    // emitted gradient buffers need no clearing and nothing is applied here (the owner shard applies, rae_pull_apply)
     if (emit && !h->emit_only) {
         if ((rc = launch_zero(h, h->gW_dense, sizeof(float) * (size_t)h->cfg.F * h->K, st))) return rc;
     }
@@ -200,15 +210,15 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = launch_zero(h, h->gA_dense, sizeof(float) * (size_t)h->cfg.N * h->d, st))) return rc;
         if ((rc = launch_zero(h, h->gAb_dense, sizeof(float) * (size_t)h->cfg.N, st))) return rc;
     }
-    RAE_PHASE();   // 8 sparse-row updates (segment-reduce in sorted order, one RMW per unique row)
     if (!overlap) {
+        // sparse-row updates in stream order; their phase slots (6, 7) are timed separately below
+        if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_upd[0], st));
         if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->debug_dense || h->emit_only, !h->emit_only, st))) return rc;
-    }
-    RAE_PHASE();   // 9
-    if (!overlap) {
+        if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_upd[1], st));
         if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->dense_w && !h->emit_only, st))) return rc;
+        if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_upd[2], st));
     }
-    RAE_PHASE();   // 10
+    RAE_PHASE();   // 14 dense-parameter optimiser step
     if (finish_dense && (rc = launch_dense_apply(h, st))) return rc;
     if (overlap) {
         RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
@@ -446,7 +456,10 @@ void rae_destroy(rae_engine* h) {
     cudaFree(h->gC_part); cudaFree(h->own_gW); cudaFree(h->own_gA); cudaFree(h->own_gAb); cudaFree(h->cub_tmp);
     cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev); cudaFree(h->peer_err_dev);
     cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
-    if (h->ev_created) for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
+    if (h->ev_created) {
+        for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_upd[i]);
+    }
     if (h->s1) cudaStreamDestroy(h->s1);
     if (h->s2) cudaStreamDestroy(h->s2);
     if (h->ev_fork0) cudaEventDestroy(h->ev_fork0);
@@ -747,9 +760,9 @@ int rae_get_entity_segments(rae_engine* h, int32_t* sorted_rows, int32_t* sorted
     return RAE_OK;
 }
 
-static const char* kPhaseNames[RAE_NUM_PHASES] = {"encoder_forward", "entity_sort", "feature_sort", "decoder_forward", "score",
-                                                   "decoder_backward", "grad_dense", "cost", "entity_update", "w_update",
-                                                   "dense_apply"};
+static const char* kPhaseNames[RAE_NUM_PHASES] = {"encoder_forward", "entity_sort", "feature_sort", "operand_prep", "contract_forward",
+                                                   "score", "entity_update", "w_update", "contract_recompute", "contract_dq",
+                                                   "backward_finish", "contract_dc", "dense_finalize", "cost", "dense_apply"};
 
 const char* rae_phase_name(int32_t phase) { return (phase >= 0 && phase < RAE_NUM_PHASES) ? kPhaseNames[phase] : ""; }
 
@@ -757,6 +770,7 @@ int rae_set_profiling(rae_engine* h, int32_t on) {
     if (!h) return RAE_EINVAL;
     if (on && !h->ev_created) {
         for (int i = 0; i <= RAE_NUM_PHASES; ++i) RAE_CUDA(h, cudaEventCreate(&h->ev_phase[i]));
+        for (int i = 0; i < 3; ++i) RAE_CUDA(h, cudaEventCreate(&h->ev_upd[i]));
         h->ev_created = true;
     }
     h->profiling = on != 0;
@@ -768,6 +782,13 @@ int rae_get_phase_times(rae_engine* h, float* ms) {
     if (!h->ev_created) return fail(h, RAE_EINVAL, "rae_get_phase_times: profiling was never enabled");
     RAE_CUDA(h, cudaEventSynchronize(h->ev_phase[RAE_NUM_PHASES]));
     for (int i = 0; i < RAE_NUM_PHASES; ++i) RAE_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev_phase[i], h->ev_phase[i + 1]));
+    // the sparse-row updates run after the cost kernel in the profiled (single-stream) order: their own events
+    float eu = 0.f, wu = 0.f;
+    RAE_CUDA(h, cudaEventElapsedTime(&eu, h->ev_upd[0], h->ev_upd[1]));
+    RAE_CUDA(h, cudaEventElapsedTime(&wu, h->ev_upd[1], h->ev_upd[2]));
+    ms[13] -= eu + wu;        // they sit between the cost kernel and the dense update
+    ms[6] = eu;
+    ms[7] = wu;
     return RAE_OK;
 }
 

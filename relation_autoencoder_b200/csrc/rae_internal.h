@@ -132,7 +132,7 @@ struct rae_engine {
     int64_t* label_dev; float* prob_dev;         // label_host staging
     // bookkeeping
     rae_step_stats stats;
-    bool profiling; cudaEvent_t ev_phase[RAE_NUM_PHASES + 1]; bool ev_created;
+    bool profiling; cudaEvent_t ev_phase[RAE_NUM_PHASES + 1]; cudaEvent_t ev_upd[3]; bool ev_created;
     const uint32_t* last_f_keys_s; int64_t last_f_n;   // sorted feature keys of the last step (statistics)
     int32_t* stat_dev;   // [2] device scratch for unique-row counts
     int launches;
@@ -174,7 +174,9 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
 int tc_prepare_qt(rae_engine* h, cudaStream_t st);                                      // q^T operand only
 int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // L, R only
 int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
-int tc_backward(rae_engine* h, cudaStream_t st);
+int tc_backward_recompute(rae_engine* h, cudaStream_t st);
+int tc_backward_dq(rae_engine* h, cudaStream_t st);
+int tc_backward_finish(rae_engine* h, cudaStream_t st);
 int tc_grad_dense(rae_engine* h, cudaStream_t st);
 
 // ---- sort / segment / updates (rae_update.cu) ----
