@@ -66,7 +66,8 @@ extern "C" {
 #define RAE_FLAG_FORCE_SIMT 4u      /* never take the tcgen05 contraction path */
 #define RAE_FLAG_FORCE_TENSOR 8u    /* fail instead of falling back when the tcgen05 path does not support the shape */
 #define RAE_FLAG_NO_FEATURE_CACHE 16u /* re-sort the batch's (feature, example) pairs every step instead of once at bind */
-#define RAE_FLAG_NO_CLUSTER 64u     /* tcgen05 path: no thread-block clusters / operand multicast (A/B measurement)            */
+#define RAE_FLAG_CLUSTER_MULTICAST 64u /* tcgen05 path: thread-block clusters, streamed operand fetched once per cluster (multicast).
+                                         * Measured on B200: no gain (the kernels are not operand-traffic bound) -> off by default */
 #define RAE_FLAG_EMIT_ONLY 32u      /* row-sharded multi-GPU: W/A/Ab are per-step compact copies; emit per-row gradients, apply nothing */
 
 typedef struct rae_config {

@@ -25,7 +25,7 @@ RAE_FLAG_FORCE_SIMT = 4
 RAE_FLAG_FORCE_TENSOR = 8
 RAE_FLAG_NO_FEATURE_CACHE = 16
 RAE_FLAG_EMIT_ONLY = 32
-RAE_FLAG_NO_CLUSTER = 64
+RAE_FLAG_CLUSTER_MULTICAST = 64
 RAE_ENODEVICE = -5
 RAE_NUM_PHASES = 15
 

@@ -47,6 +47,8 @@ __device__ unsigned long long* g_tc_trace = nullptr;
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
+__device__ int g_tc_bwd_dbg = 0;   // measurement knobs of the backward kernels (RAE_TC_DEBUG bits 8: no MMAs, 16: generators do not store)
+
 constexpr int TC_M = 128;          // rows per CTA (TMEM lanes)
 constexpr int TC_N = 64;           // forward: B-operand rows per chunk (TMEM columns per accumulator stage)
 constexpr int TC_TSTAGES = 4;      // forward: accumulator stages in TMEM
@@ -87,7 +89,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 __device__ __forceinline__ void bulk_g2s_pieces(uint8_t* dst_smem, const uint8_t* src_gmem, uint32_t bytes, uint64_t* bar) {
-    constexpr uint32_t PIECE = 8192;
+    constexpr uint32_t PIECE = 1u << 16;    // one instruction per stage: each bulk copy costs ~85 cycles + bytes / 130 B per cycle (profiles/microbench)
     for (uint32_t off = 0; off < bytes; off += PIECE) bulk_g2s(dst_smem + off, src_gmem + off, min(PIECE, bytes - off), bar);
 }
 // ---- thread-block clusters: the B operand of a chunk is fetched ONCE per cluster (each CTA loads 1/cs of it and multicasts
@@ -111,7 +113,7 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem
 // slice `crank` of a chunk -> the same stage offset of every CTA of the cluster (cs == 1: plain copy of the whole chunk)
 __device__ __forceinline__ void bulk_g2s_chunk(uint8_t* stage, const uint8_t* chunk, uint32_t bytes, uint64_t* bar, uint32_t cs,
                                                uint32_t crank) {
-    constexpr uint32_t PIECE = 8192;
+    constexpr uint32_t PIECE = 1u << 16;    // one instruction per stage: each bulk copy costs ~85 cycles + bytes / 130 B per cycle (profiles/microbench)
     const uint32_t slice = bytes / cs, base = slice * crank;
     const uint16_t mask = (uint16_t)((1u << cs) - 1u);
     for (uint32_t off = 0; off < slice; off += PIECE) {
@@ -689,6 +691,7 @@ __global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ 
 // generated operand  G[b,n]:  bilinear row n=(i,j): a_bi R_bj + L_bi Y2_bj ;  C1 row j: a_bj + G2_b L_bj ;  C2 row j: c_bj + G1_b R_bj
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t TC_BWD_ACOL = 128;
+constexpr int TC_ASTAGES = 4;          // generated-operand stages in TMEM (64 columns each: hi 32 + lo 32); 128 + 4*64 = 384 <= 512
 
 // transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
 __global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
@@ -718,6 +721,7 @@ struct TcDqArgs {
     float* dqp;             // [NS][B][NK]
     int B, d, dp, K, NK;
     int n_bil_rows, n_chunks32, NS;
+    int cs, ntile;          // cluster size; CTAs of a cluster = consecutive example tiles of the SAME split (same streamed chunks)
 };
 
 // shared skeleton pieces of the two backward kernels ------------------------------------------------------------
@@ -725,43 +729,47 @@ struct BwdBars {
     uint64_t* a_full; uint64_t* a_empty; uint64_t* b_full; uint64_t* b_empty; uint64_t* acc_full; uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t B_BYTES, int warp, uint32_t& tmem_base) {
+__device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t B_BYTES, int warp, uint32_t& tmem_base, uint32_t cs) {
     BwdBars br;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * B_BYTES);
-    br.a_full = bars;                         // [2] 16 generator-warp arrivals
-    br.a_empty = bars + 2;                    // [2] tcgen05.commit
-    br.b_full = bars + 4;                     // [TC_BSTAGES] bulk-copy tx
+    br.a_full = bars;                         // [TC_ASTAGES] 16 generator-warp arrivals
+    br.a_empty = bars + TC_ASTAGES;           // [TC_ASTAGES] tcgen05.commit
+    br.b_full = bars + 2 * TC_ASTAGES;        // [TC_BSTAGES] bulk-copy tx
     br.b_empty = br.b_full + TC_BSTAGES;      // [TC_BSTAGES] tcgen05.commit
     br.acc_full = br.b_empty + TC_BSTAGES;
     br.tmem_slot = reinterpret_cast<uint32_t*>(br.acc_full + 1);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&br.a_full[s], 16); mbar_init(&br.a_empty[s], 1); }
-        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&br.b_full[s], 1); mbar_init(&br.b_empty[s], 1); }
+        for (int s = 0; s < TC_ASTAGES; ++s) { mbar_init(&br.a_full[s], 16); mbar_init(&br.a_empty[s], 1); }
+        // a stage is free once EVERY CTA of the cluster has consumed it (its next fill is multicast into all of them)
+        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&br.b_full[s], 1); mbar_init(&br.b_empty[s], cs); }
         mbar_init(br.acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(br.tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(br.tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();
     tc_fence_after();
     tmem_base = *br.tmem_slot;
     return br;
 }
 
-__device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, const uint8_t* src, uint32_t B_BYTES, int c_begin, int nit) {
+__device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, const uint8_t* src, uint32_t B_BYTES, int c_begin, int nit,
+                                             uint32_t cs, uint32_t crank) {
     for (int it = 0; it < nit; ++it) {
         const int s = it % TC_BSTAGES;
         const uint32_t ph = (it / TC_BSTAGES) & 1;
         mbar_wait(&br.b_empty[s], ph ^ 1);
         mbar_expect_tx(&br.b_full[s], B_BYTES);
-        bulk_g2s_pieces(smB + (size_t)s * B_BYTES, src + (size_t)(c_begin + it) * B_BYTES, B_BYTES, &br.b_full[s]);
+        bulk_g2s_chunk(smB + (size_t)s * B_BYTES, src + (size_t)(c_begin + it) * B_BYTES, B_BYTES, &br.b_full[s], cs, crank);
     }
 }
 
-__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base) {
+__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base,
+                                        uint32_t cs) {
     const uint32_t idesc = make_idesc_tf32(TC_M, NK);
     uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
 #pragma unroll
@@ -771,8 +779,8 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
         dbl0[s] = make_desc(b_hi + 8u * (uint32_t)NK * 16u, (uint32_t)NK * 16u, 128u);
     }
     for (int it = 0; it < nit; ++it) {
-        const int s = it % TC_BSTAGES, as = it & 1;
-        const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it >> 1) & 1;
+        const int s = it % TC_BSTAGES, as = it % TC_ASTAGES;
+        const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it / TC_ASTAGES) & 1;
         mbar_wait(&br.a_full[as], aph);
         if ((threadIdx.x & 31) == 0 && it < 3) TC_TRACE(trace_base + 2 * it);
         mbar_wait(&br.b_full[s], ph);
@@ -782,7 +790,7 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
             const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
             uint64_t dbh = dbh0[s], dbl = dbl0[s];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < ((g_tc_bwd_dbg & 8) ? 0 : 4); ++ks) {
                 tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                 tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbl, idesc, 1u);
                 tc_mma_tf32_ts(tmem_base, a_lo + 8u * ks, dbh, idesc, 1u);
@@ -790,7 +798,7 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
                 dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
             }
             tc_commit(&br.a_empty[as]);
-            tc_commit(&br.b_empty[s]);
+            if (cs > 1) tc_commit_mc(&br.b_empty[s], (uint16_t)((1u << cs) - 1u)); else tc_commit(&br.b_empty[s]);
             if (it == nit - 1) tc_commit(br.acc_full);
         }
         __syncwarp();
@@ -802,9 +810,11 @@ __device__ __forceinline__ void bwd_publish(const BwdBars& br, uint32_t lane_bas
     float hi[8], lo[8];
     split8(g, hi, lo);
     const uint32_t col = lane_base + TC_BWD_ACOL + 64u * as + 8u * cg;
-    tc_st8(col, hi);
-    tc_st8(col + 32u, lo);
-    tc_wait_st();
+    if (!(g_tc_bwd_dbg & 16)) {
+        tc_st8(col, hi);
+        tc_st8(col + 32u, lo);
+        tc_wait_st();
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&br.a_full[as]);
@@ -816,12 +826,13 @@ template <int DP>
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / p.NS, split = blockIdx.x - tile * p.NS;
+    const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;
+    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     uint32_t tmem_base;
     if (threadIdx.x == 0) TC_TRACE(32);
-    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);
+    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base, cs);
     if (threadIdx.x == 0) TC_TRACE(33);
     constexpr int JQ = DP / 32;                 // chunks per bilinear row i
     // split the chunk range at row-i boundaries
@@ -833,9 +844,9 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     }
     if (warp == 0) {
-        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), B_BYTES, c_begin, nit);
+        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), B_BYTES, c_begin, nit, cs, crank);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 8);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 8, cs);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column octet
@@ -845,65 +856,69 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
         const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
-        // register cache: for chunk jq of a row i this thread needs j = 32 jq + 8 cg + 0..7
+        // register cache: for chunk jq of a row i this thread needs j = 32 jq + 8 cg + 0..7 (two 16-byte loads each)
         float X[JQ][8], Y[JQ][8];
 #pragma unroll
-        for (int jq = 0; jq < JQ; ++jq)
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = 32 * jq + 8 * cg + u;
-                const bool in = ok && j < p.dp;
-                X[jq][u] = in ? evb[E_R * p.dp + j] : 0.f;
-                Y[jq][u] = in ? evb[E_Y2 * p.dp + j] : 0.f;
+        for (int jq = 0; jq < JQ; ++jq) {
+            const int j = 32 * jq + 8 * cg;
+            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, y0 = x0, y1 = x0;
+            if (ok && j < p.dp) {              // dp is a multiple of 4 and rows of ev are 16-byte aligned
+                x0 = *reinterpret_cast<const float4*>(evb + E_R * p.dp + j);
+                y0 = *reinterpret_cast<const float4*>(evb + E_Y2 * p.dp + j);
             }
-        const int n_bil_chunks = p.n_bil_rows / TC_NC;
-        // a_bi / L_bi of bilinear row i: loaded one row AHEAD of their use so the load latency hides behind the chunks
-        // of the current row (the split ranges start at row boundaries)
-        float ai = 0.f, li = 0.f, ai_n = 0.f, li_n = 0.f;
-        {
-            const int i0 = c_begin / JQ;
-            if (nit > 0 && c_begin < n_bil_chunks && ok && i0 < p.dp) {
-                ai_n = p.aT[(size_t)i0 * p.B + b];
-                li_n = p.LT[(size_t)i0 * p.B + b];
+            if (ok && j + 4 < p.dp) {
+                x1 = *reinterpret_cast<const float4*>(evb + E_R * p.dp + j + 4);
+                y1 = *reinterpret_cast<const float4*>(evb + E_Y2 * p.dp + j + 4);
             }
+            X[jq][0] = x0.x; X[jq][1] = x0.y; X[jq][2] = x0.z; X[jq][3] = x0.w; X[jq][4] = x1.x; X[jq][5] = x1.y; X[jq][6] = x1.z; X[jq][7] = x1.w;
+            Y[jq][0] = y0.x; Y[jq][1] = y0.y; Y[jq][2] = y0.z; Y[jq][3] = y0.w; Y[jq][4] = y1.x; Y[jq][5] = y1.y; Y[jq][6] = y1.z; Y[jq][7] = y1.w;
         }
-        for (int it = 0; it < nit; ++it) {
-            const int as = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
-            const int c = c_begin + it;
-            float g[8];
-            if (c < n_bil_chunks) {
-                const int i = c / JQ, jq = c - i * JQ;
-                if (jq == 0 || it == 0) {
-                    ai = ai_n; li = li_n;
-                    const int in = i + 1;
-                    const bool more = ok && in < p.dp && in * JQ < min(c_end, n_bil_chunks);
-                    ai_n = more ? p.aT[(size_t)in * p.B + b] : 0.f;
-                    li_n = more ? p.LT[(size_t)in * p.B + b] : 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < JQ; ++q)
-                    if (q == jq) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) g[u] = fmaf(ai, X[q][u], li * Y[q][u]);
-                    }
-            } else {
-                // selectional-preference rows (a few chunks per tile): direct loads
-                const int m = c * TC_NC - p.n_bil_rows;
-                const int which = m / DP, j0 = m - which * DP + 8 * cg;
-                const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
-                const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = j0 + u;
-                    g[u] = (ok && j < p.dp) ? fmaf(s2, evb[sy * p.dp + j], evb[sx * p.dp + j]) : 0.f;
-                }
-            }
+        const int n_bil_chunks = p.n_bil_rows / TC_NC;
+        auto emit = [&](const float (&g)[8], int it) {
+            const int as = it % TC_ASTAGES;
+            const uint32_t aph = (it / TC_ASTAGES) & 1;
             if (gw == 0 && lane == 0 && it < 4) TC_TRACE(36 + 2 * it);
             mbar_wait(&br.a_empty[as], aph ^ 1);
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
             if (gw == 0 && lane == 0 && it < 4) TC_TRACE(37 + 2 * it);
+        };
+        // bilinear rows: the CTA's range starts and ends at row boundaries, so every row i contributes its JQ chunks in
+        // order (static indexing of the register cache).  a_bi / L_bi are loaded one row AHEAD of their use.
+        const int nbil = max(0, min(c_end, n_bil_chunks) - c_begin);
+        int it = 0;
+        float ai_n = 0.f, li_n = 0.f;
+        if (nbil > 0 && ok && c_begin / JQ < p.dp) {
+            ai_n = p.aT[(size_t)(c_begin / JQ) * p.B + b];
+            li_n = p.LT[(size_t)(c_begin / JQ) * p.B + b];
+        }
+        for (int i = c_begin / JQ; it < nbil; ++i) {
+            const float ai = ai_n, li = li_n;
+            const bool more = ok && i + 1 < p.dp && it + JQ < nbil;
+            ai_n = more ? p.aT[(size_t)(i + 1) * p.B + b] : 0.f;
+            li_n = more ? p.LT[(size_t)(i + 1) * p.B + b] : 0.f;
+#pragma unroll
+            for (int jq = 0; jq < JQ; ++jq, ++it) {
+                float g[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) g[u] = fmaf(ai, X[jq][u], li * Y[jq][u]);
+                emit(g, it);
+            }
+        }
+        // selectional-preference rows (a few chunks per tile): direct loads
+        for (; it < nit; ++it) {
+            const int c = c_begin + it;
+            const int m = c * TC_NC - p.n_bil_rows;
+            const int which = m / DP, j0 = m - which * DP + 8 * cg;
+            const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
+            const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
+            float g[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u;
+                g[u] = (ok && j < p.dp) ? fmaf(s2, evb[sy * p.dp + j], evb[sx * p.dp + j]) : 0.f;
+            }
+            emit(g, it);
         }
         if (gw == 0 && lane == 0) TC_TRACE(34);
         if (gw < 4) {
@@ -927,10 +942,11 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();
     if (threadIdx.x == 0) TC_TRACE(35);
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -942,12 +958,15 @@ struct TcDcArgs {
     int B, d, dp, K, NK, DP;
     int n_bil_rows, n_rows_total, n_bchunks, NSb, hasM;
     size_t split_stride;    // units*d*K
+    int cs, n_ntiles_pad;   // cluster size; CTAs of a cluster = consecutive ROW tiles of the same batch split; the row-tile count
+                            // is padded to a multiple of cs (tiles past n_rows_total hold padding rows only)
 };
 
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x / p.NSb, split = blockIdx.x - ntile * p.NSb;
+    const int split = blockIdx.x / p.n_ntiles_pad, ntile = blockIdx.x - split * p.n_ntiles_pad;
+    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     const int per = (p.n_bchunks + p.NSb - 1) / p.NSb;
@@ -979,16 +998,16 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     }
     if (threadIdx.x == 0) TC_TRACE(52);
     uint32_t tmem_base;
-    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base);      // __syncthreads inside: staging visible
+    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base, cs);  // __syncthreads inside: staging visible
     if (threadIdx.x == 0) TC_TRACE(53);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     }
     if (warp == 0) {
-        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit);
+        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit, cs, crank);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 56);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 56, cs);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
@@ -1026,8 +1045,8 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
             }
         };
         auto process = [&](int it, const float (&x)[8], const float (&y)[8]) {
-            const int as = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int as = it % TC_ASTAGES;
+            const uint32_t aph = (it / TC_ASTAGES) & 1;
             const int b0 = (c_begin + it) * TC_NC + 8 * cg;
             const float4 pa = *reinterpret_cast<const float4*>(s1 + it * TC_NC), pb = *reinterpret_cast<const float4*>(s1 + it * TC_NC + 4);
             const float4 qa = *reinterpret_cast<const float4*>(s2 + it * TC_NC), qb = *reinterpret_cast<const float4*>(s2 + it * TC_NC + 4);
@@ -1077,10 +1096,11 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();
     if (threadIdx.x == 0) TC_TRACE(54);
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1175,7 +1195,7 @@ int tc_init(rae_engine* h) {
     t.NS = ns;
     // cluster of consecutive example tiles sharing the streamed operand (multicast): 4, 2 or none
     t.cs = (t.ntile % 4 == 0) ? 4 : (t.ntile % 2 == 0 ? 2 : 1);
-    if (h->cfg.flags & RAE_FLAG_NO_CLUSTER) t.cs = 1;
+    if (!(h->cfg.flags & RAE_FLAG_CLUSTER_MULTICAST)) t.cs = 1;
     if ((2 * t.KQ * TC_N * 16) % (16 * t.cs) != 0) t.cs = 1;
     t.smem = (size_t)TC_BSTAGES * 2 * t.KQ * TC_N * 16 + 256;
     // backward operands: NK = relations padded to a multiple of 16, reduction chunks of 32 rows
@@ -1268,7 +1288,11 @@ int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool 
     p.cs = t.cs;
     {
         static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("RAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        if (dbg < 0) {
+            const char* e = getenv("RAE_TC_DEBUG");
+            dbg = e ? atoi(e) : 0;
+            cudaMemcpyToSymbol(g_tc_bwd_dbg, &dbg, sizeof(int));
+        }
         p.dbg = dbg;
     }
     {
@@ -1308,9 +1332,25 @@ int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
     p.n_bil_rows = t.n_bil_rows; p.n_chunks32 = t.n_chunks32; p.NS = t.NS2;
     const int grid = t.ntile * t.NS2;
-    if (t.DP == 32) k_tc_dq<32><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
-    else if (t.DP == 64) k_tc_dq<64><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
-    else k_tc_dq<128><<<grid, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    p.cs = ((2 * 8 * t.NK * 16) % (16 * t.cs) == 0) ? t.cs : 1;
+    p.ntile = t.ntile;
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_BWD_THREADS);
+        cfg.dynamicSmemBytes = t.smem_dq;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = p.cs > 1 ? 1 : 0;
+        cudaError_t e;
+        if (t.DP == 32) e = cudaLaunchKernelEx(&cfg, k_tc_dq<32>, p);
+        else if (t.DP == 64) e = cudaLaunchKernelEx(&cfg, k_tc_dq<64>, p);
+        else e = cudaLaunchKernelEx(&cfg, k_tc_dq<128>, p);
+        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_dq launch (cluster %d): %s", p.cs, cudaGetErrorString(e));
+    }
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1337,7 +1377,24 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
     p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
     p.split_stride = (size_t)h->off_gWb;
-    k_tc_dc<<<t.n_ntiles * t.NSb, TC_BWD_THREADS, t.smem_dc, st>>>(p);
+    {
+        int cs = (h->cfg.flags & RAE_FLAG_CLUSTER_MULTICAST) ? 4 : 1;
+        while (cs > 1 && (2 * 8 * t.NK * 16) % (16 * cs) != 0) cs >>= 1;
+        p.cs = cs;
+        p.n_ntiles_pad = (t.n_ntiles + cs - 1) / cs * cs;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p.n_ntiles_pad * t.NSb);
+        cfg.blockDim = dim3(TC_BWD_THREADS);
+        cfg.dynamicSmemBytes = t.smem_dc;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = cs > 1 ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_tc_dc, p);
+        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_dc launch (cluster %d): %s", cs, cudaGetErrorString(e));
+    }
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

@@ -91,6 +91,12 @@ def test_step_matches_oracle(model, shape):
     _check_step(model, SHAPES[shape], seed=1)
 
 
+@pytest.mark.parametrize("shape", ["b512d128", "b256d30"])
+def test_cluster_multicast_variant_matches_oracle(shape):
+    """RAE_FLAG_CLUSTER_MULTICAST (64): clusters of 4 / 2 CTAs, the streamed operand multicast into every CTA's stages."""
+    _check_step("rescal+sp", SHAPES[shape], seed=2, flags=FLAG_DENSE | 64)
+
+
 @pytest.mark.parametrize("model", O.MODELS)
 def test_duplicate_rows_are_summed_before_squaring(model):
     """Duplicates (same entity as e1, e2 and several negatives) accumulate first (AdvancedIncSubtensor1), then AdaGrad
