@@ -87,7 +87,7 @@ class ReconstructInducer(object):
     def __init__(self, data, gold_standard, rng, nb_epochs, learning_rate, batch_size, embed_size, nb_relations,
                  nb_neg_samples, lambda1, lambda2, optimization, model_name, decoder_model, external_embeddings,
                  extended_regularizer, frequent_eval, alpha, backend: Optional[Callable] = None, device: int = 0,
-                 out=None):
+                 out=None, device_sampler: bool = False):
         if decoder_model not in MODEL_ALIASES:
             raise ValueError("unknown decoder %r (expected rescal | sp | rescal+sp)" % (decoder_model,))
         self.data = data
@@ -115,7 +115,14 @@ class ReconstructInducer(object):
             raise NotImplementedError("--ext-emb (word2vec initialisation through gensim, OieModel.py:112-128) is out of scope")
         if optimization not in ('adagrad', 'sgd'):
             raise Exception("Optimizer '{}' not implemented".format(optimization))          # OieInduction.py:269
-        self.negativeSampler = NegativeExampleGenerator(rng, data.negSamplingCum)            # OieInduction.py:82
+        # OieInduction.py:82.  device_sampler: same ids (same MT19937 stream), drawn and kept on the GPU; the epoch then
+        # binds them once and steps with rae_train_step instead of passing host slices (cuda backend only)
+        self.device_sampler = bool(device_sampler)
+        if self.device_sampler:
+            from .sampler import DeviceNegativeExampleGenerator
+            self.negativeSampler = DeviceNegativeExampleGenerator(rng, data.negSamplingCum, device=device)
+        else:
+            self.negativeSampler = NegativeExampleGenerator(rng, data.negSamplingCum)
         self.modelID = decoder_model + '_' + model_name + '_maxepoch' + str(nb_epochs) + '_lr' + str(learning_rate) + \
             '_embedsize' + str(embed_size) + '_l1' + str(lambda1) + '_l2' + str(lambda2) + '_opt' + str(optimization) + \
             '_rel_num' + str(self.relationNum) + '_batch' + str(batch_size) + '_negs' + str(self.neg_sample_num)
@@ -183,10 +190,15 @@ class ReconstructInducer(object):
             neg_samples1 = self.negativeSampler.get_negative_samples(self.data.split['train'].args1.shape[0], self.neg_sample_num)
             neg_samples2 = self.negativeSampler.get_negative_samples(self.data.split['train'].args2.shape[0], self.neg_sample_num)
             B = self.batch_size
+            if self.device_sampler:
+                self.engine.bind_epoch_negatives(neg_samples1, neg_samples2)
             for batch_ind in range(self.batch_reps['train']):
-                neg1 = neg_samples1[:, batch_ind * B:(batch_ind + 1) * B]
-                neg2 = neg_samples2[:, batch_ind * B:(batch_ind + 1) * B]
-                err += self.func['train'](batch_ind, neg1, neg2)
+                if self.device_sampler:
+                    err += self.engine.train_device(batch_ind)
+                else:
+                    neg1 = neg_samples1[:, batch_ind * B:(batch_ind + 1) * B]
+                    neg2 = neg_samples2[:, batch_ind * B:(batch_ind + 1) * B]
+                    err += self.func['train'](batch_ind, neg1, neg2)
                 if self.frequentEval:
                     if self._mode() == 1:
                         self._print(batch_ind * B, batch_ind, '############################################################')
@@ -322,6 +334,8 @@ def get_command_args(program_name, argv=None):
     p.add_argument('--alpha', type=float, default=1.0, help='the alpha coefficient for scaling the entropy term')
     p.add_argument('--seed', type=int, default=2, help='a seed number')
     p.add_argument('--device', type=int, default=0, help='CUDA device index')
+    p.add_argument('--device-sampler', dest='device_sampler', action='store_true',
+                   help='draw the negative samples on the GPU (bit-identical ids, same random stream)')
     if argv is None:
         argv = sys.argv[1:]
     if len(argv) == 0:
@@ -354,7 +368,7 @@ def main(argv=None, backend=None):
     inducer = ReconstructInducer(indexed_data, gold_standard, rand, args.epochs, args.learning_rate, args.batch_size,
                                  args.embed_size, args.relations, args.neg_samples, args.l1, args.l2, args.optimizer,
                                  args.model_name, args.decoder, args.ext_emb, args.ext_reg, args.freq_eval, args.alpha,
-                                 backend=backend, device=args.device)
+                                 backend=backend, device=args.device, device_sampler=args.device_sampler)
     inducer.train()
     path = inducer.save()
     print('Saved', path)
