@@ -209,11 +209,14 @@ __device__ __forceinline__ float tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// hot-loop split (operand generators, 16 warps per SM, instruction-bound): hi = round-to-nearest-away TF32 of a FINITE x as
+// two integer ops (cvt.rna.tf32 compiles to three: it also guards inf / nan), lo = x - hi (exact) with its low 13 bits
+// cleared (truncation: |error| < 2^-23 |x|, below the dropped lo*lo term)
 __device__ __forceinline__ void split8(const float (&x)[8], float (&hi)[8], float (&lo)[8]) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        hi[u] = tf32_hi(x[u]);
-        lo[u] = tf32_hi(x[u] - hi[u]);
+        hi[u] = __uint_as_float((__float_as_uint(x[u]) + 0x1000u) & 0xffffe000u);
+        lo[u] = __uint_as_float(__float_as_uint(x[u] - hi[u]) & 0xffffe000u);
     }
 }
 __device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& lo) {

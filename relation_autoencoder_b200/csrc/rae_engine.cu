@@ -107,12 +107,15 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     static int side_prep = -1;
     if (side_prep < 0) { const char* e = getenv("RAE_SIDE_PREP"); side_prep = e ? atoi(e) : 0; }
     const bool sprep = overlap && h->use_tc && side_prep != 0;
+    static int prepc_main = -1;      // RAE_PREPC_MAIN=1: dense-operand prep on the main stream (A/B measurement)
+    if (prepc_main < 0) { const char* e = getenv("RAE_PREPC_MAIN"); prepc_main = e ? atoi(e) : 0; }
+    const bool prepc_side = overlap && h->use_tc && prepc_main == 0;
     cudaStream_t se = overlap ? h->s1 : st, sw = overlap ? h->s2 : st;
     const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
     if (overlap) {
         RAE_CUDA(h, cudaEventRecord(h->ev_fork0, st));
         RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_fork0, 0));
-        if (h->use_tc) {
+        if (prepc_side) {
             // the pre-split dense operands depend only on the parameters: prepared beside the encoder
             RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork0, 0));
             if ((rc = tc_prepare_c(h, h->s2))) return rc;
@@ -152,7 +155,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 3 dense / q-dependent operand preparation of the tensor path
     if (h->use_tc) {
-        if (overlap) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
+        if (prepc_side) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
         else if ((rc = tc_prepare_c(h, st))) return rc;
         if (sprep) {
             if (lr_on_main && (rc = tc_gather_lr(h, a1, a2, st))) return rc;
