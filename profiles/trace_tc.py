@@ -39,7 +39,18 @@ for i in range(4): names[24 + 2 * i] = "epi it%d wait t_full" % i; names[25 + 2 
 for i in range(0, 8, 2): names[24 + i] = "epi it%d wait t_full" % i; names[25 + i] = "epi it%d t_full ok" % i
 names.update({16: "epi it4 ld0 done", 17: "epi it4 ld1 done", 18: "epi it4 chunk done", 20: "epi it6 ld0 done", 21: "epi it6 ld1 done", 22: "epi it6 chunk done"})
 for i in range(4): names[8 + 2 * i] = "mma it%d t_empty ok" % i; names[9 + 2 * i] = "mma it%d b_full ok" % i
-groups = {"FWD": [k for k in names if k < 32 or k >= 62]}
+for k in list(names):
+    if 32 <= k < 62: del names[k]
+names.update({32: "DQ entry", 33: "DQ setup done", 34: "DQ gen loop done", 35: "DQ final sync"})
+for i in range(4):
+    names[36 + 3 * i] = "DQ gen it%d computed" % (40 + i); names[37 + 3 * i] = "DQ gen it%d a_empty ok" % (40 + i); names[38 + 3 * i] = "DQ gen it%d published" % (40 + i)
+dqm = {}
+for i in range(3):
+    dqm[8 + 2 * i] = "DQ mma it%d a_full ok" % (40 + i); dqm[9 + 2 * i] = "DQ mma it%d b_full ok" % (40 + i); dqm[14 + i] = "DQ mma it%d issued" % (40 + i)
+groups = {"FWD": [k for k in names if k < 32 or k >= 62], "DQ": [k for k in names if 32 <= k < 48]}
+if os.environ.get("TRACE_DQ"):
+    names.update(dqm)
+    groups = {"DQ": [k for k in names if 32 <= k < 48] + list(dqm)}
 for cta in (1, 127):
     r = t[cta]
     for gname, slots in groups.items():

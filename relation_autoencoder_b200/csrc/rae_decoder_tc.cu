@@ -39,11 +39,15 @@ namespace {
 // optional in-kernel timeline (build with -DRAE_TRACE): SM cycle counter of CTA-local milestones, [CTA][64] slots
 #ifdef RAE_TRACE
 __device__ unsigned long long* g_tc_trace = nullptr;
+// TC_TRACE_INIT() once per thread (reads the buffer pointer into a register: a timestamp then costs one clock read and
+// one asynchronous store, not a dependent global load)
+#define TC_TRACE_INIT() unsigned long long* const tc_trace_ptr_ = g_tc_trace
 #define TC_TRACE(slot)                                                                                         \
     do {                                                                                                       \
-        if (g_tc_trace != nullptr && (slot) < 64) g_tc_trace[(size_t)blockIdx.x * 64 + (slot)] = clock64();    \
+        if (tc_trace_ptr_ != nullptr && (slot) < 64) tc_trace_ptr_[(size_t)blockIdx.x * 64 + (slot)] = clock64(); \
     } while (0)
 #else
+#define TC_TRACE_INIT() do { } while (0)
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
@@ -374,6 +378,7 @@ template <int DP>
 __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_TRACE_INIT();
     const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;     // a cluster = cs consecutive tiles
     const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * p.KQ * TC_N * 16u;
@@ -773,6 +778,7 @@ __device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, co
 
 __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base,
                                         uint32_t cs) {
+    TC_TRACE_INIT();
     const uint32_t idesc = make_idesc_tf32(TC_M, NK);
     uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
 #pragma unroll
@@ -785,9 +791,9 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
         const int s = it % TC_BSTAGES, as = it % TC_ASTAGES;
         const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it / TC_ASTAGES) & 1;
         mbar_wait(&br.a_full[as], aph);
-        if ((threadIdx.x & 31) == 0 && it < 3) TC_TRACE(trace_base + 2 * it);
+        if ((threadIdx.x & 31) == 0 && it >= 40 && it < 43) TC_TRACE(trace_base + 2 * (it - 40));
         mbar_wait(&br.b_full[s], ph);
-        if ((threadIdx.x & 31) == 0 && it < 3) TC_TRACE(trace_base + 2 * it + 1);
+        if ((threadIdx.x & 31) == 0 && it >= 40 && it < 43) TC_TRACE(trace_base + 2 * (it - 40) + 1);
         tc_fence_after();
         if (elect_one()) {
             const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
@@ -800,6 +806,7 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
                 dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
                 dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
             }
+            if (it >= 40 && it < 43) TC_TRACE(trace_base + 6 + (it - 40));     // MMAs of chunk `it` issued
             tc_commit(&br.a_empty[as]);
             if (cs > 1) tc_commit_mc(&br.b_empty[s], (uint16_t)((1u << cs) - 1u)); else tc_commit(&br.b_empty[s]);
             if (it == nit - 1) tc_commit(br.acc_full);
@@ -829,6 +836,7 @@ template <int DP>
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_TRACE_INIT();
     const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;
     const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
@@ -880,11 +888,13 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
         auto emit = [&](const float (&g)[8], int it) {
             const int as = it % TC_ASTAGES;
             const uint32_t aph = (it / TC_ASTAGES) & 1;
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(36 + 2 * it);
+            const bool tr = gw == 0 && lane == 0 && it >= 40 && it < 44;      // steady state (not the first fills)
+            if (tr) TC_TRACE(36 + 3 * (it - 40));
             mbar_wait(&br.a_empty[as], aph ^ 1);
+            if (tr) TC_TRACE(37 + 3 * (it - 40));
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(37 + 2 * it);
+            if (tr) TC_TRACE(38 + 3 * (it - 40));
         };
         // bilinear rows: the CTA's range starts and ends at row boundaries, so every row i contributes its JQ chunks in
         // order (static indexing of the register cache).  a_bi / L_bi are loaded one row AHEAD of their use.
@@ -968,6 +978,7 @@ struct TcDcArgs {
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_TRACE_INIT();
     const int split = blockIdx.x / p.n_ntiles_pad, ntile = blockIdx.x - split * p.n_ntiles_pad;
     const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
@@ -1010,7 +1021,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     if (warp == 0) {
         if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit, cs, crank);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 56, cs);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 100, cs);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
@@ -1058,11 +1069,11 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
             float g[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], x[u], p2[u] * y[u]) : 0.f;
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(44 + 2 * it);
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(100 + 2 * it);      // (slots >= 64 are dropped: dq owns 36..47 now)
             mbar_wait(&br.a_empty[as], aph ^ 1);
             tc_fence_after();
             bwd_publish(br, lane_base, as, cg, g, lane);
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(45 + 2 * it);
+            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(101 + 2 * it);
         };
         float xa[8], ya[8], xb[8], yb[8];
         if (nit > 0) load(0, xa, ya);
