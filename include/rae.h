@@ -126,12 +126,20 @@ int rae_bind_epoch_negatives(rae_engine* h, const int32_t* neg1, const int32_t* 
 
 /* ---- func['train'] -------------------------------------------------------------------------------------- */
 /* device-resident form: rows [b*B,(b+1)*B) of the bound train split + bound epoch negatives.  cost_host may be NULL
- * (fully asynchronous); otherwise the call synchronises the stream and stores the regularised batch cost. */
+ * (fully asynchronous); otherwise the call waits until the regularised batch cost is known and stores it.  The cost
+ * depends on the forward pass only: the call may return while the backward pass and the parameter updates of this
+ * step are still running - every later call on the handle (and rae_destroy) is ordered after them. */
 int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* stream);
 /* drop-in form of func['train'](batch_index, neg1, neg2): neg1/neg2 are HOST int32[S,B] (what learn() passes,
- * OieInduction.py:187-189); copies them to the device, runs the step, returns the cost (synchronous). */
+ * OieInduction.py:187-189); copies them to the device, runs the step, returns the cost (same ordering as above; the
+ * host arrays have been consumed when the call returns). */
 int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, const int32_t* neg2_host,
                         double* cost_host, void* stream);
+/* same with a row stride (in elements) per array: the driver passes column slices neg[:, b*B:(b+1)*B] of the epoch's
+ * [S, n] arrays (OieInduction.py:187-188), which are read in place.  Page-locked host memory is copied straight to the
+ * device (one strided DMA per array); pageable memory goes through the handle's pinned staging buffer. */
+int rae_train_step_host_ld(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, int64_t ld1,
+                           const int32_t* neg2_host, int64_t ld2, double* cost_host, void* stream);
 /* fully explicit form for parity tests with injected indices: all DEVICE pointers; indptr has B+1 entries and may
  * start at any offset into indices (indices is indexed by indptr values); neg_ld = row stride of neg1/neg2. */
 int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, const int32_t* args1,

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "rae_bind_epoch_negatives": (C.c_int, [_P, _P, _P, C.c_int64]),
     "rae_train_step": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_double), _P]),
     "rae_train_step_host": (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_double), _P]),
+    "rae_train_step_host_ld": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_double), _P]),
     "rae_train_step_explicit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_double), _P]),
     "rae_label": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "rae_label_host": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),

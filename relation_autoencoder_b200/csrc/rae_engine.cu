@@ -170,7 +170,23 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
     }
     RAE_PHASE();   // 5 scoring / loss / d cost / d score
+    if (h->neg_wait) {
+        // rae_train_step_host: the negatives were copied on the entity stream, beside the encoder
+        RAE_CUDA(h, cudaStreamWaitEvent(st, h->neg_wait, 0));
+        h->neg_wait = nullptr;
+    }
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+    h->cost_on_event = false;
+    if (overlap) {
+        // The cost needs the score partials and the pre-update parameters only: it is reduced beside the backward pass
+        // (off the critical path) and signalled by its own event, so a caller that wants the number (func['train']
+        // returns it) gets it while the rest of the step still runs - the updates stay ordered on the streams.
+        RAE_CUDA(h, cudaEventRecord(h->ev_score, st));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_score, 0));
+        if ((rc = launch_cost(h, h->s2))) return rc;
+        RAE_CUDA(h, cudaEventRecord(h->ev_cost, h->s2));
+        h->cost_on_event = true;
+    }
     RAE_PHASE();   // 6 (profiling / no-overlap order only) entity-row update, see below
     RAE_PHASE();   // 7
     RAE_PHASE();   // 8 backward: recompute M c, M^T a
@@ -202,8 +218,8 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 12 sum of the batch-split partials
     if ((rc = launch_dense_finalize(h, st))) return rc;
-    RAE_PHASE();   // 13 cost (uses the pre-update parameters for the regulariser value)
-    if ((rc = launch_cost(h, st))) return rc;
+    RAE_PHASE();   // 13 cost (uses the pre-update parameters for the regulariser value); overlapped order: see phase 5
+    if (!overlap && (rc = launch_cost(h, st))) return rc;
     // emit-only (row-sharded multi-GPU): the tables are per-step compact copies whose every row is touched, so the
     // emitted gradient buffers need no clearing and nothing is applied here (the owner shard applies, rae_pull_apply)
     if (emit && !h->emit_only) {
@@ -242,9 +258,14 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
 
 static int finish_cost(rae_engine* h, double* cost_host, cudaStream_t st) {
     if (cost_host == nullptr) return RAE_OK;
-    RAE_CUDA(h, cudaMemcpyAsync(h->cost_pinned, h->cost_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-    RAE_CUDA(h, cudaStreamSynchronize(st));
-    *cost_host = *h->cost_pinned;
+    if (h->cost_on_event) {
+        // the cost kernel stored the value in the pinned word itself; the parameter updates behind it keep running and
+        // every later call on this handle is ordered after them by the streams
+        RAE_CUDA(h, cudaEventSynchronize(h->ev_cost));
+    } else {
+        RAE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    *cost_host = *(volatile double*)h->cost_pinned;
     return RAE_OK;
 }
 
@@ -437,8 +458,10 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_qt, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_dfork, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_dfetch, cudaEventDisableTiming));
-    RAE_CREATE_RC(dev_alloc(h, &h->stage_neg1, (size_t)h->S * h->B));
-    RAE_CREATE_RC(dev_alloc(h, &h->stage_neg2, (size_t)h->S * h->B));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_score, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_cost, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_neg, cudaEventDisableTiming));
+    RAE_CREATE_RC(dev_alloc(h, &h->stage_neg, 4 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->peer_err_dev, 1));
     RAE_CREATE_CUDA(cudaMemset(h->peer_err_dev, 0, sizeof(int32_t)));
@@ -458,7 +481,7 @@ void rae_destroy(rae_engine* h) {
     cudaFree(h->loss_part); cudaFree(h->reg_part); cudaFree(h->cost_dev); cudaFree(h->dzsum_part); cudaFree(h->own_dense);
     cudaFree(h->gC_part); cudaFree(h->own_gW); cudaFree(h->own_gA); cudaFree(h->own_gAb); cudaFree(h->cub_tmp);
     cudaFree(h->ent_part); cudaFree(h->feat_part); cudaFree(h->stat_dev); cudaFree(h->peer_err_dev);
-    cudaFree(h->stage_neg1); cudaFree(h->stage_neg2); cudaFree(h->label_dev); cudaFree(h->prob_dev);
+    cudaFree(h->stage_neg); cudaFree(h->label_dev); cudaFree(h->prob_dev);
     if (h->ev_created) {
         for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_upd[i]);
@@ -469,6 +492,9 @@ void rae_destroy(rae_engine* h) {
     if (h->ev_fork1) cudaEventDestroy(h->ev_fork1);
     if (h->ev_join1) cudaEventDestroy(h->ev_join1);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+    if (h->ev_score) cudaEventDestroy(h->ev_score);
+    if (h->ev_cost) cudaEventDestroy(h->ev_cost);
+    if (h->ev_neg) cudaEventDestroy(h->ev_neg);
     if (h->ev_prepc) cudaEventDestroy(h->ev_prepc);
     if (h->ev_q) cudaEventDestroy(h->ev_q);
     if (h->ev_qt) cudaEventDestroy(h->ev_qt);
@@ -571,21 +597,55 @@ int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* 
     return finish_cost(h, cost_host, st);
 }
 
-int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, const int32_t* neg2_host,
-                        double* cost_host, void* stream) {
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int rae_train_step_host_ld(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host,
+                           int64_t ld2, double* cost_host, void* stream) {
     int rc = check_ready(h, true, false);
     if (rc) return rc;
     if ((!neg1_host || !neg2_host) && h->S > 0) return fail(h, RAE_EINVAL, "rae_train_step_host: null negatives");
+    if (h->S > 1 && (ld1 < h->B || ld2 < h->B)) return fail(h, RAE_EINVAL, "rae_train_step_host: row stride below B");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)h->S * h->B;
-    // the pinned staging buffer is reused: wait until the previous step's copy has been consumed
-    RAE_CUDA(h, cudaStreamSynchronize(st));
-    memcpy(h->pinned_neg, neg1_host, n * sizeof(int32_t));
-    memcpy(h->pinned_neg + n, neg2_host, n * sizeof(int32_t));
-    RAE_CUDA(h, cudaMemcpyAsync(h->stage_neg1, h->pinned_neg, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    RAE_CUDA(h, cudaMemcpyAsync(h->stage_neg2, h->pinned_neg + n, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if ((rc = train_batch(h, batch_index, h->stage_neg1, h->stage_neg2, h->B, st))) return rc;
+    const size_t n = (size_t)h->S * h->B, row = sizeof(int32_t) * (size_t)h->B;
+    // Same predicate as run_step's `overlap`: the copy then rides on the entity stream, beside the encoder - its first
+    // consumers are the entity keys (same stream) and the scoring kernel (waits for ev_neg).
+    const bool side = !h->dense_w && !h->debug_dense && !h->profiling && h->s1 != nullptr;
+    cudaStream_t sc = side ? h->s1 : st;
+    // double-buffered device staging: the previous step's tail (entity keys / update) may still read its half
+    int32_t* d1 = h->stage_neg + (size_t)h->stage_flip * 2 * n;
+    int32_t* d2 = d1 + n;
+    h->stage_flip ^= 1;
+    if (n > 0) {
+        if (is_pinned_host(neg1_host) && is_pinned_host(neg2_host)) {
+            // page-locked caller memory: strided rows straight to the device, no host staging
+            RAE_CUDA(h, cudaMemcpy2DAsync(d1, row, neg1_host, sizeof(int32_t) * (size_t)ld1, row, h->S, cudaMemcpyHostToDevice, sc));
+            RAE_CUDA(h, cudaMemcpy2DAsync(d2, row, neg2_host, sizeof(int32_t) * (size_t)ld2, row, h->S, cudaMemcpyHostToDevice, sc));
+        } else {
+            // the pinned staging buffer is reused: wait until the previous step's copy has left it
+            if (h->neg_staged) RAE_CUDA(h, cudaEventSynchronize(h->ev_neg));
+            for (int s = 0; s < h->S; ++s) {
+                memcpy(h->pinned_neg + (size_t)s * h->B, neg1_host + (size_t)s * ld1, row);
+                memcpy(h->pinned_neg + n + (size_t)s * h->B, neg2_host + (size_t)s * ld2, row);
+            }
+            RAE_CUDA(h, cudaMemcpyAsync(d1, h->pinned_neg, 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
+            h->neg_staged = true;
+        }
+        RAE_CUDA(h, cudaEventRecord(h->ev_neg, sc));
+        if (side) h->neg_wait = h->ev_neg;
+    }
+    rc = train_batch(h, batch_index, d1, d2, h->B, st);
+    h->neg_wait = nullptr;
+    if (rc) return rc;
     return finish_cost(h, cost_host, st);
+}
+
+int rae_train_step_host(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, const int32_t* neg2_host,
+                        double* cost_host, void* stream) {
+    return rae_train_step_host_ld(h, batch_index, neg1_host, h ? h->B : 0, neg2_host, h ? h->B : 0, cost_host, stream);
 }
 
 int rae_train_step_explicit(rae_engine* h, const int32_t* indptr, const int32_t* indices, const int32_t* args1,

@@ -124,10 +124,15 @@ struct rae_engine {
     void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
     cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
     cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc, ev_dfork, ev_dfetch, ev_q, ev_qt;
+    cudaEvent_t ev_score, ev_cost, ev_neg;
+    cudaEvent_t neg_wait;       // host-negatives copy in flight on a side stream: the scoring kernel waits for it
+    bool cost_on_event;         // the last step recorded ev_cost behind its cost kernel
+    bool neg_staged;            // ev_neg has been recorded at least once (pinned_neg may still be in flight)
+    int stage_flip;             // which half of the double-buffered device staging the next host step fills
     int barrier_epoch; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
     cudaEvent_t pending_wait;                      // if set: the step's main stream waits for it before the decoder reads A
     // explicit-step staging
-    int32_t* stage_neg1; int32_t* stage_neg2;   // device [S,B]
+    int32_t* stage_neg;                          // device [2 (flip)][2 (neg1, neg2)][S,B]
     int32_t* pinned_neg;                         // host pinned [2,S,B]
     int64_t* label_dev; float* prob_dev;         // label_host staging
     // bookkeeping

@@ -641,7 +641,8 @@ __global__ void k_reg_norms(const float* __restrict__ p, size_t n, double* __res
 // one CTA; thread t owns elements t, t+256, ... and the tree below has a fixed shape -> deterministic
 __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ loss_part, int n_loss,
                                               const double* __restrict__ reg_part, int n_reg, double invZ,
-                                              double adj_l1, double adj_l2, double* __restrict__ cost) {
+                                              double adj_l1, double adj_l2, double* __restrict__ cost,
+                                              double* __restrict__ cost_mapped) {
     __shared__ double s0[256], s1[256], s2[256];
     double a = 0.0, b = 0.0, c = 0.0;
     for (int i = threadIdx.x; i < n_loss; i += 256) a += loss_part[i];
@@ -656,7 +657,11 @@ __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ loss_pa
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *cost = -s0[0] * invZ + adj_l1 * s1[0] + adj_l2 * s2[0];
+    if (threadIdx.x == 0) {
+        const double v = -s0[0] * invZ + adj_l1 * s1[0] + adj_l2 * s2[0];
+        *cost = v;
+        *cost_mapped = v;      // pinned host word (UVA): the caller reads it after the event behind this kernel, no D2H copy
+    }
 }
 
 int ensure_part(rae_engine* h, float** buf, size_t* cap, size_t need) {
@@ -909,7 +914,7 @@ int launch_cost(rae_engine* h, cudaStream_t st) {
     }
     const int n_loss = h->n_loss_part;
     k_cost<<<1, 256, 0, st>>>(h->loss_part, n_loss, h->reg_part, n_reg, 1.0 / h->Z, h->cfg.adj * h->cfg.l1,
-                              h->cfg.adj * h->cfg.l2, h->cost_dev);
+                              h->cfg.adj * h->cfg.l2, h->cost_dev, h->cost_pinned);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

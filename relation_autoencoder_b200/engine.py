@@ -66,6 +66,7 @@ class Engine:
         self.acc: Dict[str, torch.Tensor] = {}
         self._keep = {}          # device tensors borrowed by the library
         self._cost = C.c_double(0.0)
+        self._cost_ref = C.byref(self._cost)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -158,17 +159,28 @@ class Engine:
         self._check(self.lib.rae_bind_epoch_negatives(self._h, _ptr(n1), _ptr(n2), n1.shape[1]), "rae_bind_epoch_negatives")
 
     # ------------------------------------------------------------------ func['train']
+    def _host_negatives(self, neg):
+        """(array kept alive, address, row stride in elements) of an int32 [S, B] host array; column slices of the
+        epoch's [S, n] arrays (what the driver passes, OieInduction.py:187-188) are used in place."""
+        if not (isinstance(neg, np.ndarray) and neg.dtype == np.int32 and neg.ndim == 2):
+            neg = np.ascontiguousarray(neg, dtype=np.int32)
+        if neg.shape != (self.S, self.B):
+            raise ValueError("neg1/neg2 must have shape (S, B) = (%d, %d)" % (self.S, self.B))
+        s0, s1 = neg.strides
+        if self.S and self.B and (s1 != 4 or s0 % 4 or s0 < 4 * self.B):
+            neg = np.ascontiguousarray(neg)
+            s0 = 4 * self.B
+        return neg, neg.__array_interface__["data"][0], s0 // 4
+
     def train(self, batch_index: int, neg1: np.ndarray, neg2: np.ndarray) -> float:
         """Drop-in for ``func['train'](batch_index, neg1, neg2)`` (OieInduction.py:146-149,189): host int32 [S,B]
-        negatives in, regularised batch cost out, parameters updated in place."""
-        n1 = np.ascontiguousarray(neg1, dtype=np.int32)
-        n2 = np.ascontiguousarray(neg2, dtype=np.int32)
-        if n1.shape != (self.S, self.B) or n2.shape != (self.S, self.B):
-            raise ValueError("neg1/neg2 must have shape (S, B) = (%d, %d)" % (self.S, self.B))
-        self._check(self.lib.rae_train_step_host(self._h, int(batch_index), n1.ctypes.data_as(C.c_void_p),
-                                                 n2.ctypes.data_as(C.c_void_p), C.byref(self._cost), self._stream),
+        negatives in, regularised batch cost out, parameters updated in place (the cost is returned as soon as the
+        forward pass has produced it; the updates complete in stream order before anything else reads them)."""
+        n1, p1, ld1 = self._host_negatives(neg1)
+        n2, p2, ld2 = self._host_negatives(neg2)
+        self._check(self.lib.rae_train_step_host_ld(self._h, int(batch_index), p1, ld1, p2, ld2, self._cost_ref, self._stream),
                     "rae_train_step_host")
-        return float(self._cost.value)
+        return self._cost.value
 
     def train_device(self, batch_index: int, want_cost: bool = True) -> Optional[float]:
         """Same step with the epoch negatives already bound on the device; asynchronous when ``want_cost`` is False."""

@@ -217,6 +217,43 @@ def test_bound_split_api_matches_reference_callables(model):
         eng.close()
 
 
+@pytest.mark.parametrize("model", ["rescal", "rescal+sp"])
+def test_host_negatives_pinned_pageable_and_pipelined_steps_agree(model):
+    """func['train'] returns the cost as soon as the forward pass has it and the next call is issued behind the running
+    backward pass.  Page-locked column slices (strided DMA, no staging), pageable slices (pinned staging) and
+    contiguous copies with a full synchronisation between steps must give bit-identical costs and parameters."""
+    import torch
+    sh = dict(SHAPES["readme"])
+    B, S = sh["B"], sh["S"]
+    nb = 6
+    pr = make_problem(model, seed=21, **{**sh, "B": nb * B})
+    p0 = _to32(pr["p"])
+    neg = [np.ascontiguousarray(pr[k], dtype=np.int32) for k in ("neg1", "neg2")]
+    pinned = [torch.from_numpy(a.copy()).pin_memory().numpy() for a in neg]
+    outs = []
+    for mode in ("pinned", "pageable", "synchronised"):
+        eng = _engine(model, sh, flags=0, n_train=nb * B)
+        eng.set_params_numpy(p0)
+        eng.bind_split("train", pr["indptr"], pr["indices"], pr["a1"], pr["a2"])
+        src = pinned if mode == "pinned" else neg
+        costs = []
+        for e in range(2):
+            for b in range(nb):
+                n1, n2 = (a[:, b * B:(b + 1) * B] for a in src)
+                if mode == "synchronised":
+                    n1, n2 = n1.copy(), n2.copy()
+                costs.append(eng.train(b, n1, n2))
+                if mode == "synchronised":
+                    torch.cuda.synchronize()
+        outs.append((costs, eng.get_params_numpy(), eng.get_acc_numpy()))
+        eng.close()
+    for costs, p, acc in outs[1:]:
+        assert costs == outs[0][0]
+        for n in p:
+            assert np.array_equal(p[n], outs[0][1][n]), n
+            assert np.array_equal(acc[n], outs[0][2][n]), n
+
+
 def test_label_ties_first_max_wins():
     from relation_autoencoder_b200.engine import Engine
     K, F, B = 40, 8, 4
