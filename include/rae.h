@@ -180,6 +180,7 @@ int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width
  * gradient buffers, sum them in rank order (deterministic) and apply the optimiser once per row.  The routing (which
  * rows, which slots) depends only on the ids and is planned once per split / epoch by the host side. */
 #define RAE_MAX_PEERS 16
+#define RAE_FLAG_WORDS 32      /* a rank's flag buffer: RAE_MAX_PEERS barrier epochs, then its local cost (double), padding */
 #define RAE_IPC_HANDLE_BYTES 64
 /* zero-initialised device allocation + its IPC handle (handle_out: RAE_IPC_HANDLE_BYTES bytes, may be NULL) */
 int rae_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out);
@@ -224,17 +225,27 @@ typedef struct rae_dist_step {
     const int32_t* er_rows; const int32_t* er_off; int64_t n_er; const int32_t* e_src; const int32_t* e_slot;
     double* cost_dev;                                      /* receives the local cost (device)                              */
     /* peer-memory synchronisation (optional: flag_bufs == NULL -> the caller orders the ranks with collectives) */
-    const void* const* flag_bufs;                          /* every rank's barrier flags, int32[RAE_MAX_PEERS] each          */
+    const void* const* flag_bufs;                          /* every rank's flags, int32[RAE_MAX_PEERS] (RAE_FLAG_WORDS w/ cost) */
     const void* const* dense_bufs;                         /* every rank's flat dense gradient [C | C1 | C2 | Wb], or NULL:   */
     int32_t rank;                                          /*   NULL = the caller all-reduced the dense gradient itself      */
-    int32_t reserved2;
-} rae_dist_step;
+    int32_t global_cost;                                   /* 1: flag buffers are int32[RAE_FLAG_WORDS]; the ranks' costs are  */
+} rae_dist_step;                                           /*    summed in rank order (cost_dev, rae_dist_read_cost)           */
 /* With flag_bufs set, rae_dist_step_end runs: barrier ("every rank has emitted") -> dense update, summing the ranks'
  * dense gradients straight from dense_bufs in rank order when given -> the three pulls -> barrier ("every owner has
  * applied").  The barrier is a one-warp kernel: release-store of the epoch into every peer's flag word, acquire-spin on the
  * own flags (bounded: a rank that never arrives sets the status word instead of hanging the GPU, see rae_peer_status). */
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream);
 int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream);
+/* func['train'](batch_index, neg1, neg2) form of rae_dist_step_begin: this rank's HOST negatives int32[S,B] with row strides
+ * (as rae_train_step_host_ld) are copied to the device and checked against the planned compact slots
+ * (e_ids[n1c[s,j]] == neg1[s,j]); a mismatch is reported by rae_dist_read_cost.  The step itself runs on the plan. */
+int rae_dist_step_begin_host(rae_engine* h, const rae_dist_step* d, const int32_t* neg1_host, int64_t ld1,
+                             const int32_t* neg2_host, int64_t ld2, void* stream);
+/* global_cost = 1: every rank stores its local cost in words [RAE_MAX_PEERS, RAE_MAX_PEERS+2) of its flag buffer before the
+ * first barrier; after it each rank sums them in rank order (no collective).  rae_dist_read_cost waits for that sum only -
+ * the pulls and the second barrier of the step keep running behind it - and returns RAE_EINVAL if a host-negatives check
+ * failed since the last call. */
+int rae_dist_read_cost(rae_engine* h, double* cost_host);
 /* stand-alone barrier over the ranks' flag buffers (same kernel as inside rae_dist_step_end) */
 int rae_peer_barrier(rae_engine* h, const void* const* flag_bufs, int32_t world, int32_t rank, void* stream);
 /* synchronises and returns 0 if every peer barrier of this handle completed, RAE_ECUDA if one timed out */

@@ -28,6 +28,7 @@ RAE_FLAG_EMIT_ONLY = 32
 RAE_FLAG_CLUSTER_MULTICAST = 64
 RAE_ENODEVICE = -5
 RAE_NUM_PHASES = 15
+RAE_FLAG_WORDS = 32
 
 
 class RaeConfig(C.Structure):
@@ -48,7 +49,7 @@ class RaeDistStep(C.Structure):
                 + [("fr_rows", C.c_void_p), ("fr_off", C.c_void_p), ("n_fr", C.c_int64), ("f_src", C.c_void_p), ("f_slot", C.c_void_p)]
                 + [("er_rows", C.c_void_p), ("er_off", C.c_void_p), ("n_er", C.c_int64), ("e_src", C.c_void_p), ("e_slot", C.c_void_p)]
                 + [("cost_dev", C.c_void_p), ("flag_bufs", C.c_void_p), ("dense_bufs", C.c_void_p), ("rank", C.c_int32),
-                   ("reserved2", C.c_int32)])
+                   ("global_cost", C.c_int32)])
 
 
 class RaeStepStats(C.Structure):
@@ -94,6 +95,8 @@ _SIGNATURES = {
     "rae_train_step_begin": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
     "rae_dist_step_begin": (C.c_int, [_P, C.POINTER(RaeDistStep), _P]),
     "rae_dist_step_end": (C.c_int, [_P, C.POINTER(RaeDistStep), _P]),
+    "rae_dist_step_begin_host": (C.c_int, [_P, C.POINTER(RaeDistStep), _P, C.c_int64, _P, C.c_int64, _P]),
+    "rae_dist_read_cost": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "rae_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "rae_peer_status": (C.c_int, [_P, _P]),
     "rae_copy_cost": (C.c_int, [_P, _P, _P]),

@@ -314,6 +314,43 @@ int build_feature_cache(rae_engine* h, cudaStream_t st) {
     return RAE_OK;
 }
 
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Host int32 [S,B] negatives (row strides ld1 / ld2 elements) -> the next half of the double-buffered device staging, on
+// stream sc; records ev_neg behind the copy.  The previous step's tail may still read the other half.
+int stage_host_negatives(rae_engine* h, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host, int64_t ld2,
+                         cudaStream_t sc, int32_t** d1_out, int32_t** d2_out) {
+    if ((!neg1_host || !neg2_host) && h->S > 0) return fail(h, RAE_EINVAL, "host negatives: null pointer");
+    if (h->S > 1 && (ld1 < h->B || ld2 < h->B)) return fail(h, RAE_EINVAL, "host negatives: row stride below B");
+    const size_t n = (size_t)h->S * h->B, row = sizeof(int32_t) * (size_t)h->B;
+    int32_t* d1 = h->stage_neg + (size_t)h->stage_flip * 2 * n;
+    int32_t* d2 = d1 + n;
+    h->stage_flip ^= 1;
+    *d1_out = d1;
+    *d2_out = d2;
+    if (n == 0) return RAE_OK;
+    if (is_pinned_host(neg1_host) && is_pinned_host(neg2_host)) {
+        // page-locked caller memory: strided rows straight to the device, no host staging
+        RAE_CUDA(h, cudaMemcpy2DAsync(d1, row, neg1_host, sizeof(int32_t) * (size_t)ld1, row, h->S, cudaMemcpyHostToDevice, sc));
+        RAE_CUDA(h, cudaMemcpy2DAsync(d2, row, neg2_host, sizeof(int32_t) * (size_t)ld2, row, h->S, cudaMemcpyHostToDevice, sc));
+    } else {
+        // the pinned staging buffer is reused: wait until the previous step's copy has left it
+        if (h->neg_staged) RAE_CUDA(h, cudaEventSynchronize(h->ev_neg));
+        for (int s = 0; s < h->S; ++s) {
+            memcpy(h->pinned_neg + (size_t)s * h->B, neg1_host + (size_t)s * ld1, row);
+            memcpy(h->pinned_neg + n + (size_t)s * h->B, neg2_host + (size_t)s * ld2, row);
+        }
+        RAE_CUDA(h, cudaMemcpyAsync(d1, h->pinned_neg, 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
+        h->neg_staged = true;
+    }
+    RAE_CUDA(h, cudaEventRecord(h->ev_neg, sc));
+    return RAE_OK;
+}
+
 }  // namespace rae
 
 using namespace rae;
@@ -420,7 +457,10 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     h->n_reg_part = 64 * 4;
     RAE_CREATE_RC(dev_alloc(h, &h->reg_part, (size_t)2 * h->n_reg_part));
     RAE_CREATE_RC(dev_alloc(h, &h->cost_dev, 1));
-    RAE_CREATE_CUDA(cudaMallocHost((void**)&h->cost_pinned, sizeof(double)));
+    RAE_CREATE_CUDA(cudaMallocHost((void**)&h->cost_pinned, 4 * sizeof(double)));
+    memset(h->cost_pinned, 0, 4 * sizeof(double));
+    h->gcost_pinned = h->cost_pinned + 1;                                  // same page-locked block: [cost | global cost | flag]
+    h->neg_err_pinned = reinterpret_cast<int32_t*>(h->cost_pinned + 2);
     h->n_dz_part = h->B;   // upper bound on CTAs of the backward kernel (>= 8 examples per CTA)
     RAE_CREATE_RC(dev_alloc(h, &h->dzsum_part, (size_t)h->n_dz_part * h->K));
     const int64_t dd = h->hasM ? (int64_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (int64_t)h->d * h->K : 0;
@@ -461,6 +501,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_score, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_cost, cudaEventDisableTiming));
     RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_neg, cudaEventDisableTiming));
+    RAE_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_gcost, cudaEventDisableTiming));
     RAE_CREATE_RC(dev_alloc(h, &h->stage_neg, 4 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->pinned_neg, sizeof(int32_t) * 2 * (size_t)(h->S > 0 ? h->S : 1) * h->B));
     RAE_CREATE_RC(dev_alloc(h, &h->peer_err_dev, 1));
@@ -495,6 +536,7 @@ void rae_destroy(rae_engine* h) {
     if (h->ev_score) cudaEventDestroy(h->ev_score);
     if (h->ev_cost) cudaEventDestroy(h->ev_cost);
     if (h->ev_neg) cudaEventDestroy(h->ev_neg);
+    if (h->ev_gcost) cudaEventDestroy(h->ev_gcost);
     if (h->ev_prepc) cudaEventDestroy(h->ev_prepc);
     if (h->ev_q) cudaEventDestroy(h->ev_q);
     if (h->ev_qt) cudaEventDestroy(h->ev_qt);
@@ -597,46 +639,17 @@ int rae_train_step(rae_engine* h, int64_t batch_index, double* cost_host, void* 
     return finish_cost(h, cost_host, st);
 }
 
-static bool is_pinned_host(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
-
 int rae_train_step_host_ld(rae_engine* h, int64_t batch_index, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host,
                            int64_t ld2, double* cost_host, void* stream) {
     int rc = check_ready(h, true, false);
     if (rc) return rc;
-    if ((!neg1_host || !neg2_host) && h->S > 0) return fail(h, RAE_EINVAL, "rae_train_step_host: null negatives");
-    if (h->S > 1 && (ld1 < h->B || ld2 < h->B)) return fail(h, RAE_EINVAL, "rae_train_step_host: row stride below B");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)h->S * h->B, row = sizeof(int32_t) * (size_t)h->B;
     // Same predicate as run_step's `overlap`: the copy then rides on the entity stream, beside the encoder - its first
     // consumers are the entity keys (same stream) and the scoring kernel (waits for ev_neg).
     const bool side = !h->dense_w && !h->debug_dense && !h->profiling && h->s1 != nullptr;
-    cudaStream_t sc = side ? h->s1 : st;
-    // double-buffered device staging: the previous step's tail (entity keys / update) may still read its half
-    int32_t* d1 = h->stage_neg + (size_t)h->stage_flip * 2 * n;
-    int32_t* d2 = d1 + n;
-    h->stage_flip ^= 1;
-    if (n > 0) {
-        if (is_pinned_host(neg1_host) && is_pinned_host(neg2_host)) {
-            // page-locked caller memory: strided rows straight to the device, no host staging
-            RAE_CUDA(h, cudaMemcpy2DAsync(d1, row, neg1_host, sizeof(int32_t) * (size_t)ld1, row, h->S, cudaMemcpyHostToDevice, sc));
-            RAE_CUDA(h, cudaMemcpy2DAsync(d2, row, neg2_host, sizeof(int32_t) * (size_t)ld2, row, h->S, cudaMemcpyHostToDevice, sc));
-        } else {
-            // the pinned staging buffer is reused: wait until the previous step's copy has left it
-            if (h->neg_staged) RAE_CUDA(h, cudaEventSynchronize(h->ev_neg));
-            for (int s = 0; s < h->S; ++s) {
-                memcpy(h->pinned_neg + (size_t)s * h->B, neg1_host + (size_t)s * ld1, row);
-                memcpy(h->pinned_neg + n + (size_t)s * h->B, neg2_host + (size_t)s * ld2, row);
-            }
-            RAE_CUDA(h, cudaMemcpyAsync(d1, h->pinned_neg, 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
-            h->neg_staged = true;
-        }
-        RAE_CUDA(h, cudaEventRecord(h->ev_neg, sc));
-        if (side) h->neg_wait = h->ev_neg;
-    }
+    int32_t *d1 = nullptr, *d2 = nullptr;
+    if ((rc = stage_host_negatives(h, neg1_host, ld1, neg2_host, ld2, side ? h->s1 : st, &d1, &d2))) return rc;
+    if (side && h->S > 0) h->neg_wait = h->ev_neg;
     rc = train_batch(h, batch_index, d1, d2, h->B, st);
     h->neg_wait = nullptr;
     if (rc) return rc;

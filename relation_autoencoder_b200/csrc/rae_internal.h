@@ -124,7 +124,10 @@ struct rae_engine {
     void* ent_cub_tmp; size_t ent_cub_bytes;      // the entity sort runs on its own stream: own temp storage
     cudaStream_t s1, s2;                           // side streams (entity sort + entity update; W update)
     cudaEvent_t ev_fork0, ev_fork1, ev_join1, ev_join2, ev_prepc, ev_dfork, ev_dfetch, ev_q, ev_qt;
-    cudaEvent_t ev_score, ev_cost, ev_neg;
+    cudaEvent_t ev_score, ev_cost, ev_neg, ev_gcost;
+    double* gcost_pinned;       // multi-GPU: the global cost (sum of the ranks' costs) lands here, behind ev_gcost
+    int32_t* neg_err_pinned;    // multi-GPU: set by the check of host negatives against the routing plan
+    bool gcost_pending;
     cudaEvent_t neg_wait;       // host-negatives copy in flight on a side stream: the scoring kernel waits for it
     bool cost_on_event;         // the last step recorded ev_cost behind its cost kernel
     bool neg_staged;            // ev_neg has been recorded at least once (pinned_neg may still be in flight)
@@ -212,6 +215,8 @@ int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, 
 int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
+int stage_host_negatives(rae_engine* h, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host, int64_t ld2,
+                         cudaStream_t sc, int32_t** d1_out, int32_t** d2_out);   // host [S,B] ids -> device staging, records ev_neg
 int launch_cost(rae_engine* h, cudaStream_t st);            // deterministic loss reduce + regulariser
 int launch_zero(rae_engine* h, void* p, size_t bytes, cudaStream_t st);
 

@@ -220,6 +220,37 @@ __global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, i
     __threadfence_system();
 }
 
+// global cost = sum of the ranks' local costs in rank order (the same double on every rank); each rank published its own
+// in its flag buffer (words [RAE_MAX_PEERS, RAE_MAX_PEERS+2)) before the "every rank has emitted" barrier
+__global__ void k_global_cost(FlagPtrs flags, int world, double* __restrict__ out_dev, double* __restrict__ out_mapped) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const double* p = reinterpret_cast<const double*>(flags.p[r] + RAE_MAX_PEERS);
+            double v;
+            asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+            s += v;
+        }
+        if (out_dev) *out_dev = s;
+        *out_mapped = s;
+    }
+}
+
+// func['train'] hands the step its negatives although their routing was planned when the epoch's negatives were bound:
+// they must be the planned ones.  ids[slot[s, j]] == given[s, j] for both arrays, else the (mapped, sticky) flag is set.
+__global__ void __launch_bounds__(256) k_check_negatives(const int32_t* __restrict__ ids, int64_t n_ids, const int32_t* __restrict__ s1,
+                                                         const int32_t* __restrict__ s2, int64_t slot_ld, const int32_t* __restrict__ g1,
+                                                         const int32_t* __restrict__ g2, int S, int B, int32_t* __restrict__ err_mapped) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)S * B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i / B, j = i - s * B;
+        const int32_t c1 = s1[s * slot_ld + j], c2 = s2[s * slot_ld + j];
+        bad |= c1 < 0 || c1 >= n_ids || c2 < 0 || c2 >= n_ids;
+        if (!bad) bad |= ids[c1] != g1[i] || ids[c2] != g2[i];
+    }
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) *err_mapped = 1;
+}
+
 // dense optimiser step with the ranks' flat dense gradients summed on the fly, in rank order (identical on every rank):
 // replaces "all-reduce, then k_dense_apply" when the gradient is small enough to be read from every peer
 struct DenseSeg { float* p; float* acc; size_t begin, end; };      // [begin, end) of the flat gradient
@@ -455,13 +486,60 @@ int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
     return rae_train_step_begin(h, d->batch_index, d->a1c, d->a2c, d->n1c, d->n2c, d->neg_ld, stream);
 }
 
+int rae_dist_step_begin_host(rae_engine* h, const rae_dist_step* d, const int32_t* neg1_host, int64_t ld1,
+                             const int32_t* neg2_host, int64_t ld2, void* stream) {
+    if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_begin_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the copy and the check ride on the W-update stream, which is idle until the step forks: off the critical path
+    cudaStream_t sc = (h->s2 != nullptr && !h->profiling) ? h->s2 : st;
+    int32_t *g1 = nullptr, *g2 = nullptr;
+    int rc = stage_host_negatives(h, neg1_host, ld1, neg2_host, ld2, sc, &g1, &g2);
+    if (rc) return rc;
+    const int64_t n = (int64_t)h->S * h->B;
+    if (n > 0) {
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms);
+        k_check_negatives<<<blocks, 256, 0, sc>>>(d->e_ids, d->n_e, d->n1c, d->n2c, d->neg_ld, g1, g2, h->S, h->B, h->neg_err_pinned);
+        RAE_CUDA(h, cudaGetLastError());
+    }
+    return rae_dist_step_begin(h, d, stream);
+}
+
+int rae_dist_read_cost(rae_engine* h, double* cost_host) {
+    if (!h || !cost_host) return fail(h, RAE_EINVAL, "rae_dist_read_cost: null argument");
+    if (!h->gcost_pending) return fail(h, RAE_ENOTBOUND, "rae_dist_read_cost: no step with global_cost set has been issued");
+    RAE_CUDA(h, cudaEventSynchronize(h->ev_gcost));
+    *cost_host = *(volatile double*)h->gcost_pinned;
+    if (*(volatile int32_t*)h->neg_err_pinned != 0) {
+        *(volatile int32_t*)h->neg_err_pinned = 0;
+        return fail(h, RAE_EINVAL, "the negatives passed for this batch are not the columns of the bound epoch negatives");
+    }
+    return RAE_OK;
+}
+
 int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_end: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool flags = d->flag_bufs != nullptr;
+    const bool gcost = flags && d->global_cost != 0;
+    FlagPtrs fp;
+    if (gcost) {
+        if (d->world > RAE_MAX_PEERS || d->rank < 0 || d->rank >= d->world) return fail(h, RAE_EINVAL, "rae_dist_step_end: bad world / rank");
+        memset(&fp, 0, sizeof(fp));
+        for (int r = 0; r < d->world; ++r) fp.p[r] = static_cast<int32_t*>(const_cast<void*>(d->flag_bufs[r]));
+        // the local cost goes into the own flag buffer before the barrier publishes this rank's arrival
+        if ((rc = rae_copy_cost(h, reinterpret_cast<double*>(fp.p[d->rank] + RAE_MAX_PEERS), stream))) return rc;
+    }
     // (A) every rank has emitted its gradient rows and its dense gradient
     if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
+    if (gcost) {
+        // the caller gets the global cost here, while the pulls below still run (rae_dist_read_cost)
+        k_global_cost<<<1, 32, 0, st>>>(fp, d->world, d->cost_dev, h->gcost_pinned);
+        h->launches++;
+        RAE_CUDA(h, cudaGetLastError());
+        RAE_CUDA(h, cudaEventRecord(h->ev_gcost, st));
+        h->gcost_pending = true;
+    }
     const bool side = h->s1 != nullptr && h->s2 != nullptr && !h->profiling;
     if (side) {
         // the three owner-side pulls are independent: entity rows and biases on the side streams, W rows + the dense update here
@@ -489,7 +567,7 @@ int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
     }
     // (B) every owner has applied: the next step may fetch, the compact gradient buffers may be overwritten
     if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
-    if (d->cost_dev) return rae_copy_cost(h, d->cost_dev, stream);
+    if (d->cost_dev && !gcost) return rae_copy_cost(h, d->cost_dev, stream);
     return RAE_OK;
 }
 

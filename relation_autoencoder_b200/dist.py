@@ -265,7 +265,7 @@ class CudaBackend(GranularStep):
         # the flat dense gradient and the barrier flags are peer-visible too: with them the step needs NO collective
         n_dense = int(self.lib.rae_dense_grad_size(self.h))
         self.grad_buf["dense"] = PeerBuffer(self.lib, (n_dense,), self.device)
-        self.grad_buf["flags"] = PeerBuffer(self.lib, (16,), self.device)          # int32[RAE_MAX_PEERS], zero-initialised
+        self.grad_buf["flags"] = PeerBuffer(self.lib, (L.RAE_FLAG_WORDS,), self.device)   # barrier epochs + local cost, zeroed
         self._exchange(self.grad_buf)
         self.dense_grad = self.grad_buf["dense"].tensor
         self.peer_sync = True
@@ -349,6 +349,7 @@ class CudaBackend(GranularStep):
             d.flag_bufs = vp(self._grad_arrays["flags"])
             d.dense_bufs = vp(self._grad_arrays["dense"]) if self.peer_dense else None
             d.rank = de.rank
+            d.global_cost = 1                     # the ranks' costs are summed over peer memory too: no collective in the step
             self.descs.append(d)
 
     def run_begin(self, de, b, a1c, a2c, n1c, n2c, neg_ld):
@@ -361,9 +362,21 @@ class CudaBackend(GranularStep):
             d = d2
         self.eng._check(self.lib.rae_dist_step_begin(self.h, C.byref(d), self._stream), "rae_dist_step_begin")
 
+    def run_begin_host(self, de, b, neg1, neg2):
+        """func['train'] form: this rank's host negatives are copied and checked against the plan inside the C call."""
+        n1, p1, ld1 = self.eng._host_negatives(neg1)
+        n2, p2, ld2 = self.eng._host_negatives(neg2)
+        self.eng._check(self.lib.rae_dist_step_begin_host(self.h, C.byref(self.descs[b]), p1, ld1, p2, ld2, self._stream),
+                        "rae_dist_step_begin_host")
+
     def run_end(self, de, b):
         self.eng._check(self.lib.rae_dist_step_end(self.h, C.byref(self.descs[b]), self._stream), "rae_dist_step_end")
         return self.cost_t
+
+    def read_global_cost(self) -> float:
+        """The sum of the ranks' costs of the last step, as soon as every rank has emitted (the pulls keep running)."""
+        self.eng._check(self.lib.rae_dist_read_cost(self.h, self.eng._cost_ref), "train()")
+        return self.eng._cost.value
 
     def label(self, indptr: torch.Tensor, indices_compact: torch.Tensor):
         n = indptr.numel() - 1
@@ -549,14 +562,18 @@ class DistributedEngine:
         self._sync_all()
 
     # ------------------------------------------------------------------ the step
-    def _step(self, b, n1c, n2c, neg_ld, want_cost):
-        """n1c / n2c None: the epoch's bound negatives (compact slots planned at bind time)."""
+    def _step(self, b, n1c, n2c, neg_ld, want_cost, host_neg=None):
+        """n1c / n2c None: the epoch's bound negatives (compact slots planned at bind time); host_neg: the caller's host
+        arrays, checked against that plan on the device (CUDA backend)."""
         bk = self.backend
         B = self.B
         if n1c is None and not hasattr(bk, "descs"):
             n1c, n2c, neg_ld = self.n1c[:, b * B:], self.n2c[:, b * B:], self.nb * B
         ev = self._phase_events() if self._profiling else None
-        bk.run_begin(self, b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], n1c, n2c, neg_ld)
+        if host_neg is not None:
+            bk.run_begin_host(self, b, host_neg[0], host_neg[1])
+        else:
+            bk.run_begin(self, b, self.a1c[b * B:(b + 1) * B], self.a2c[b * B:(b + 1) * B], n1c, n2c, neg_ld)
         if ev: ev[1].record()
         peer_sync = getattr(bk, "peer_sync", False)               # CUDA backend: flag barriers over peer memory inside run_end
         if self.world > 1 and not getattr(bk, "peer_dense", False):
@@ -564,6 +581,12 @@ class DistributedEngine:
         if ev: ev[2].record()                                     # without peer_sync it also orders "every rank has emitted"
         cost = bk.run_end(self, b)
         if ev: ev[3].record()
+        if peer_sync and hasattr(bk, "read_global_cost"):
+            # the ranks' costs were summed over peer memory inside run_end: nothing collective, nothing to wait for but the sum
+            if ev:
+                ev[4].record()
+                self._phase_log.append(ev)
+            return bk.read_global_cost() if (want_cost or host_neg is not None) else None
         if self.world > 1 and (want_cost or not peer_sync):
             dist.all_reduce(cost, group=self.group)               # global cost; without peer_sync: "every owner has applied"
         if ev:
@@ -605,8 +628,12 @@ class DistributedEngine:
         """func['train'](batch_index, neg1, neg2) with this rank's HOST negatives [S,B] (the columns of the bound epoch
         negatives, as the reference's driver passes them, OieInduction.py:187-189); returns the GLOBAL batch cost."""
         b, B = int(batch_index), self.B
+        if not (0 <= b < self.nb):
+            raise RuntimeError("batch_index %d out of range [0,%d)" % (b, self.nb))
         if self.eplan is None:
             raise RuntimeError("epoch negatives are not bound (bind_epoch_negatives)")
+        if hasattr(self.backend, "run_begin_host") and getattr(self.backend, "descs", None):
+            return self._step(b, None, None, 0, True, host_neg=(neg1, neg2))
         u = self.eplan.ids_of(b).to(torch.int64)
         out = []
         ok = torch.ones((), dtype=torch.bool, device=self.dev)

@@ -83,6 +83,17 @@ def main():
     lab_ref, q_ref = om.label("train", 1)
     ok &= np.array_equal(lab, lab_ref[rank * B:(rank + 1) * B])
     ok &= np.abs(probs - q_ref[rank * B:(rank + 1) * B]).max() < max(tol, 1e-12) * q_ref.max()
+    if cuda:
+        # negatives that are not the bound epoch's columns are refused (the routing plan was built from the bound ones)
+        bad = np.array(pr["neg1"][:, rows[:B]], dtype=np.int32)
+        bad[0, 0] = (bad[0, 0] + 1) % N
+        try:
+            de.train(0, bad, pr["neg2"][:, rows[:B]])
+            ok = False
+        except RuntimeError:
+            pass
+        c = de.train(0, pr["neg1"][:, rows[:B]], pr["neg2"][:, rows[:B]])       # the flag is cleared by the report
+        ok &= bool(np.isfinite(c))
     flag = torch.tensor([1 if ok else 0], device="cuda" if cuda else "cpu")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
