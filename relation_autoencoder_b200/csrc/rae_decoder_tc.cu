@@ -700,6 +700,13 @@ __global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t TC_BWD_ACOL = 128;
 constexpr int TC_ASTAGES = 4;          // generated-operand stages in TMEM (64 columns each: hi 32 + lo 32); 128 + 4*64 = 384 <= 512
+// Second accumulator of the dC contraction at [384, 512).  tcgen05.mma adds into the fp32 accumulator with truncation, so
+// a long chain of MMAs into ONE accumulator drifts towards zero by ~2e-8 of the sum per MMA (measured at the target shape,
+// profiles/r01_accum_chain.md: 1536 MMAs -> 3.4e-5 of ||dC||_inf, 180 MMAs -> 3.2e-6).  The reduction over examples is
+// therefore dealt over two accumulators (even / odd chunks, summed with a rounded fp32 add in the epilogue) and over
+// enough batch splits (tc_init) that no accumulator takes more than TC_DC_MAX_CHAIN chunks of 12 MMAs.
+constexpr uint32_t TC_BWD_ACC2 = 384;
+constexpr int TC_DC_MAX_CHAIN = 32;    // chunks (of 32 examples, 12 MMAs each) per accumulator
 
 // transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
 __global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
@@ -777,7 +784,7 @@ __device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, co
 }
 
 __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base,
-                                        uint32_t cs) {
+                                        uint32_t cs, int nacc = 1) {
     TC_TRACE_INIT();
     const uint32_t idesc = make_idesc_tf32(TC_M, NK);
     uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
@@ -797,12 +804,14 @@ __device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_
         tc_fence_after();
         if (elect_one()) {
             const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
+            // chunk `it` accumulates into accumulator it % nacc; the first chunk of each accumulator overwrites it
+            const uint32_t acc = tmem_base + ((nacc == 2 && (it & 1)) ? TC_BWD_ACC2 : 0u);
             uint64_t dbh = dbh0[s], dbl = dbl0[s];
 #pragma unroll
             for (int ks = 0; ks < ((g_tc_bwd_dbg & 8) ? 0 : 4); ++ks) {
-                tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                tc_mma_tf32_ts(tmem_base, a_hi + 8u * ks, dbl, idesc, 1u);
-                tc_mma_tf32_ts(tmem_base, a_lo + 8u * ks, dbh, idesc, 1u);
+                tc_mma_tf32_ts(acc, a_hi + 8u * ks, dbh, idesc, (it >= nacc || ks > 0) ? 1u : 0u);
+                tc_mma_tf32_ts(acc, a_hi + 8u * ks, dbl, idesc, 1u);
+                tc_mma_tf32_ts(acc, a_lo + 8u * ks, dbh, idesc, 1u);
                 dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
                 dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
             }
@@ -970,6 +979,7 @@ struct TcDcArgs {
     float* out;             // gC_part [NSb][units*d*K]
     int B, d, dp, K, NK, DP;
     int n_bil_rows, n_rows_total, n_bchunks, NSb, hasM;
+    int nacc;               // TMEM accumulators the example chunks are dealt over (1 or 2)
     size_t split_stride;    // units*d*K
     int cs, n_ntiles_pad;   // cluster size; CTAs of a cluster = consecutive ROW tiles of the same batch split; the row-tile count
                             // is padded to a multiple of cs (tiles past n_rows_total hold padding rows only)
@@ -1021,7 +1031,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     if (warp == 0) {
         if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit, cs, crank);
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 100, cs);
+        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 100, cs, p.nacc);
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
@@ -1100,6 +1110,12 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                 float t[32];
                 if (nit > 0) {
                     tc_ld32(lane_base + (uint32_t)c0, t);
+                    if (p.nacc == 2 && nit > 1) {            // odd chunks went to the second accumulator
+                        float t2[32];
+                        tc_ld32(lane_base + TC_BWD_ACC2 + (uint32_t)c0, t2);
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) t[x] += t2[x];
+                    }
                 } else {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) t[x] = 0.f;
@@ -1216,10 +1232,22 @@ int tc_init(rae_engine* h) {
     t.NK = (h->K + 15) & ~15;
     t.n_chunks32 = t.n_rows_total / TC_NC;
     t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), h->num_sms / t.ntile));
+    if (const char* e = getenv("RAE_TC_DQ_SPLITS")) {          // A/B knob: reduction splits of the dq contraction
+        const int v = atoi(e);
+        if (v > 0) t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), v));
+    }
     t.smem_dq = (size_t)TC_BSTAGES * (2 * 8 * t.NK * 16) + 256;
     t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
     t.n_bchunks = (h->B + TC_NC - 1) / TC_NC;
     t.NSb = std::max(1, std::min(t.n_bchunks, h->num_sms / t.n_ntiles));
+    // accuracy bound (see TC_DC_MAX_CHAIN): at most TC_DC_MAX_CHAIN chunks per TMEM accumulator
+    t.dc_nacc = 2;
+    if (const char* e = getenv("RAE_TC_DC_ACCS")) t.dc_nacc = atoi(e) == 1 ? 1 : 2;     // A/B knob
+    t.NSb = std::max(t.NSb, (t.n_bchunks + t.dc_nacc * TC_DC_MAX_CHAIN - 1) / (t.dc_nacc * TC_DC_MAX_CHAIN));
+    if (const char* e = getenv("RAE_TC_DC_SPLITS")) {          // A/B knob: batch splits of the dC contraction
+        const int v = atoi(e);
+        if (v > 0) t.NSb = std::max(1, std::min(t.n_bchunks, v));
+    }
     for (;;) {
         const int per = (t.n_bchunks + t.NSb - 1) / t.NSb;       // batch chunks per CTA of the dC kernel
         t.smem_dc = t.smem_dq + (size_t)(TC_M / DP) * 2 * per * TC_NC * sizeof(float);
@@ -1390,6 +1418,7 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
     p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
+    p.nacc = t.dc_nacc;
     p.split_stride = (size_t)h->off_gWb;
     {
         int cs = (h->cfg.flags & RAE_FLAG_CLUSTER_MULTICAST) ? 4 : 1;

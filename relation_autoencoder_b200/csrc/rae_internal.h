@@ -75,7 +75,7 @@ struct TcState {
     int NK = 0, n_chunks32 = 0, NS2 = 0; size_t smem_dq = 0, smem_dc = 0;
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
     float* dqp = nullptr;   // [NS2][B][NK]
-    int n_ntiles = 0, n_bchunks = 0, NSb = 0;
+    int n_ntiles = 0, n_bchunks = 0, NSb = 0, dc_nacc = 2;
     float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
     float* aT = nullptr; float* LT = nullptr;   // transposed a, L: [dp][B]
 };
