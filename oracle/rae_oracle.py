@@ -8,7 +8,9 @@ PARITY UNPINNED: the reference's arithmetic lives in Theano (un-vendored, versio
 which cannot be installed in this environment (no wheel, no network, Python-2 sources), and the reference's own
 tests (``test.py:29-52``) hold no golden vector or numeric assertion for this path.  This oracle is therefore
 pinned only by (i) a torch-float64 autograd run of an independent op-by-op transcription of the decoders,
-(ii) central finite differences and (iii) dense-vs-sparse-row update equivalence (see ``tests/test_oracle.py``).
+(ii) central finite differences, (iii) dense-vs-sparse-row update equivalence (see ``tests/test_oracle.py``) and
+(iv) the committed golden fixtures ``tests/golden/*.npz`` / ``readme_run*.json`` it must keep reproducing
+(``tests/test_golden.py``, ``tests/test_driver.py``).
 
 Every function cites the reference file:line it follows (paths relative to the reference root).
 

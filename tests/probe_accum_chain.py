@@ -4,7 +4,7 @@ oracle as a function of how many tensor-core MMAs accumulate into one TMEM accum
     python tests/probe_accum_chain.py T "default" "RAE_TC_DC_SPLITS=9" "RAE_TC_DC_SPLITS=9,RAE_TC_DQ_SPLITS=9"
 
 Writes one JSON line per variant (stdout and gpurun_out/accum_chain.jsonl).  The error is read from the AdaGrad
-accumulators after a first step from zero (acc' = g*g), see tests/test_fullsize.py.
+accumulators after a first step from zero (acc' = g*g), see tests/test_scale_fullsize.py.
 """
 import json
 import os
@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import rae_oracle as O                      # noqa: E402
-from tests import test_fullsize as TF                   # noqa: E402
+from tests import test_scale_fullsize as TF                   # noqa: E402
 
 
 def errors(p1, acc1, g_ref, touched):
