@@ -3,20 +3,22 @@ counterpart; the partitioning follows from its objective: examples are independe
 a sum over examples divided by the global Z (learning/OieModel.py:90).
 
 * batch: every rank owns B examples of each global batch of world*B; Z and adj are global.
-* dense parameters C/R, C1, C2, Wb: replicated; the local gradients are summed with ONE NCCL all-reduce per step (flat
-  buffer), then every rank applies the identical optimiser step (Optimizers.py:29-32).
+* dense parameters C/R, C1, C2, Wb: replicated; every rank applies the identical optimiser step (Optimizers.py:29-32) to
+  the SUM of the ranks' dense gradients, which the dense-update kernel reads from the peers' flat gradient buffers in
+  rank order (above 16 MB of remote reads per rank one NCCL all-reduce of the flat buffer is used instead).
 * sparse tables W[F,K], A[N,d], Ab[N] (+ AdaGrad accumulators): row-sharded, owner(row) = row mod world, local index =
-  row // world, in CUDA-IPC memory every rank of the node maps.  There is NO collective in the sparse data path:
+  row // world, in CUDA-IPC memory every rank of the node maps.  The steady-state step issues NO collective:
     (1) fetch   - a rank's kernel reads the distinct rows its batch touches straight from their owners' HBM over
                   NVLink into compact tables (``rae_fetch_rows``); ids are remapped to compact slots (ascending id);
     (2) step    - the fused step runs on the compact tables with RAE_FLAG_EMIT_ONLY: one reduced gradient row per compact
                   row (duplicates inside the rank already summed, in sorted order);
-    (3) pull    - after the dense all-reduce (which also orders "every rank has emitted"), each OWNER reads the gradient
-                  rows of its rows from all ranks' compact gradient buffers, sums them in rank order and applies ONE
-                  optimiser read-modify-write per row (``rae_pull_apply``);
-    (4) barrier - a one-element all-reduce (it carries the global cost) orders "every owner has applied" before the next
-                  step's fetch.
-  Fixed orders everywhere: bitwise reproducible for a given world size.
+    (3) barrier - flag words in peer memory (``rae_peer_barrier``, bounded spin) order "every rank has emitted"; the
+                  ranks' costs are summed over peer memory behind it and handed to ``train()`` before the pulls finish;
+    (4) pull    - each OWNER reads the gradient rows of its rows from all ranks' compact gradient buffers, sums them in
+                  rank order and applies ONE optimiser read-modify-write per row (``rae_pull_apply``);
+    (5) barrier - "every owner has applied", before the next step's fetch.
+  Fixed orders everywhere: bitwise reproducible for a given world size.  (Backends without peer memory - the NumPy
+  backend of the CPU tests - order (3) and (5) with the dense all-reduce and a one-element cost all-reduce.)
 * routing (which rows, which slots, who owns what) depends only on the ids: the plans of ALL batches are built at bind
   time (features) / once per epoch (entities) with a handful of vectorised tensor ops and two all-gathers, so the step
   itself needs no host synchronisation and no id exchange.
