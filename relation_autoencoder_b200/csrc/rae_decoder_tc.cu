@@ -707,6 +707,7 @@ constexpr int TC_ASTAGES = 4;          // generated-operand stages in TMEM (64 c
 // enough batch splits (tc_init) that no accumulator takes more than TC_DC_MAX_CHAIN chunks of 12 MMAs.
 constexpr uint32_t TC_BWD_ACC2 = 384;
 constexpr int TC_DC_MAX_CHAIN = 32;    // chunks (of 32 examples, 12 MMAs each) per accumulator
+constexpr int TC_DQ_MAX_CHAIN = 130;   // dq: chunks (of 32 reduction rows, 12 MMAs each) per CTA; random-sign terms drift less
 
 // transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
 __global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
@@ -1232,6 +1233,9 @@ int tc_init(rae_engine* h) {
     t.NK = (h->K + 15) & ~15;
     t.n_chunks32 = t.n_rows_total / TC_NC;
     t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), h->num_sms / t.ntile));
+    // accuracy bound for large batches (many example tiles leave few splits per tile): the measured-safe chain of the dq
+    // reduction is 130 chunks = 1560 MMAs into one accumulator (4.5e-6 of ||dW||_inf at the target shape)
+    t.NS2 = std::max(t.NS2, std::min(t.n_chunks32 / (DP / 32), (t.n_chunks32 + TC_DQ_MAX_CHAIN - 1) / TC_DQ_MAX_CHAIN));
     if (const char* e = getenv("RAE_TC_DQ_SPLITS")) {          // A/B knob: reduction splits of the dq contraction
         const int v = atoi(e);
         if (v > 0) t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), v));
