@@ -48,9 +48,10 @@ __device__ __forceinline__ void adagrad_apply(float& p, float& acc, float g, flo
     p = fmaf(-lr * g, inv, p);
 }
 
-// v[b,j], w[b,j] of the tensor-core contraction from its per-group / per-split partial buffers (rae_decoder_tc.cu):
-//   vg [2][B][dp]        DP=128: both epilogue groups hold a half-row partial; DP=64: group j%2; DP=32: group (j/2)%2
-//   wp [NS][2][B][dp]    sum over splits of the group partials (DP=128: only group j/64 holds column j)
+// v[b,j], w[b,j] of the tensor-core contraction from its partial buffers (rae_decoder_tc.cu):
+//   vg [2][B][dp]          DP=128: both epilogue groups hold a half-row partial; DP=64: group j%2; DP=32: group (j/2)%2
+//   wp [slot][2][B][dp]    sum over the NS = tcs_nslots(schedule, b / 128) slots of the example's tile of the group
+//                          partials (DP=128: only group j/64 holds column j)
 // The consumers (scoring, backward finish) read them directly: no separate combine pass.
 __device__ __forceinline__ void tc_combined_vw(const float* __restrict__ vg, const float* __restrict__ wp, int B, int dp, int DP,
                                                int NS, int b, int j, float& v, float& w) {

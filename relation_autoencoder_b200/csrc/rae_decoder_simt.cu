@@ -479,7 +479,7 @@ struct ScoreArgs {
     double* loss_part;
     int B, S, d, dp, hasM, hasSP;
     float invZ;
-    const float* vg; const float* wp; int tcDP, tcNS;     // tensor path: v, w come from the contraction's partial buffers
+    const float* vg; const float* wp; int tcDP; TcSched tcSch;   // tensor path: v, w come from the contraction's partial buffers
 };
 
 // Two warps per example, one per side (side 0: neg1 / e1 slot, side 1: neg2 / e2 slot); 4 examples per CTA.  Both warps
@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
         float* evb = p.ev + (size_t)b * E_NV * p.dp;
         float L[DT], R[DT], V[DT];      // V: direction the negatives of this side are scored against (v + c1 | w + c2)
         float sp1 = 0.f, sp2 = 0.f, pos = 0.f;
+        const int tcNS = p.vg != nullptr ? tcs_nslots(p.tcSch, b >> 7) : 0;     // partial slots of this example's tile
 #pragma unroll
         for (int t = 0; t < DT; ++t) {
             const int j = lane + 32 * t;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
             R[t] = in ? evb[E_R * p.dp + j] : 0.f;
             float v = 0.f, w = 0.f;
             if (in && p.hasM) {
-                if (p.vg != nullptr) tc_combined_vw(p.vg, p.wp, p.B, p.dp, p.tcDP, p.tcNS, b, j, v, w);
+                if (p.vg != nullptr) tc_combined_vw(p.vg, p.wp, p.B, p.dp, p.tcDP, tcNS, b, j, v, w);
                 else { v = evb[E_V1 * p.dp + j]; w = evb[E_V2 * p.dp + j]; }
             }
             const float c1 = (in && p.hasSP) ? evb[E_C1 * p.dp + j] : 0.f;
@@ -789,7 +790,7 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
     p.loss_part = h->loss_part;
     p.B = h->B; p.S = h->S; p.d = h->d; p.dp = h->dp; p.hasM = h->hasM; p.hasSP = h->hasSP;
     p.invZ = (float)(1.0 / h->Z);
-    if (h->use_tc) { p.vg = h->tc.vg; p.wp = h->tc.wp; p.tcDP = h->tc.DP; p.tcNS = h->tc.NS; }
+    if (h->use_tc) { p.vg = h->tc.vg; p.wp = h->tc.wp; p.tcDP = h->tc.DP; p.tcSch = h->tc.sch_fwd; }
     const int blocks = (h->B + 3) / 4;
     if (blocks > h->n_loss_part) return fail(h, RAE_EINVAL, "internal: loss_part too small");
     const int dt = (h->d + 31) / 32;

@@ -14,13 +14,18 @@
 // fp32 parity: every operand x is split x = hi + lo (both TF32-exact) and each k-step issues hi.hi + hi.lo + lo.hi
 // (3 tcgen05.mma kind::tf32, fp32 accumulation in TMEM; dropped lo.lo ~ 2^-22 relative).
 //
-// Operand placement is dictated by the measured shared-memory -> tensor-core feed (~64 B/cycle/SM): with M = 128 an SS
-// MMA re-reads 4 KB of A per 8-deep k-step and runs at a third of the math rate.  So the M-side (A) operand lives in
-// TMEM (TS mode): the threads that own a TMEM lane (= an example row b, or an output row n) write their row with
-// tcgen05.st - q rows once per CTA for the forward, the generated operand G chunk by chunk for the backward - and only the
-// small N-side (B) operand streams through shared memory.  B operands are pre-split and pre-arranged in HBM as the exact
-// shared-memory image of the no-swizzle K-major canonical layout (float4 planes T[kq][row]; LBO = rows*16 B, SBO = 128 B),
-// so a stage is filled by 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier.
+// The M-side (A) operand lives in TMEM (TS mode): the threads that own a TMEM lane (= an example row b, or an output row
+// n) write their row with tcgen05.st - q rows once per segment for the forward, the generated operand G stage by stage for
+// the backward - and only the small N-side (B) operand streams through shared memory.  B operands are pre-split and
+// pre-arranged in HBM as the exact shared-memory image of the no-swizzle K-major canonical layout (float4 planes
+// T[kq][row]; LBO = rows*16 B, SBO = 128 B), so a stage is filled by ONE 1-D bulk copy (cp.async.bulk -> UBLKCP)
+// completing on an mbarrier.
+//
+// Sizes follow the measured MMA cadence (profiles/microbench/RESULTS.md): one tcgen05.mma cannot issue faster than every
+// ~45 cycles, so every MMA here has N >= 112 accumulator columns (56 / 64 cycles, at the floor 128*N/256): the forward
+// streams 128-row chunks (one N = 128 MMA per k-step and split term), the backward reduces over 64-row stages against the
+// NK = K rounded up to 16 relation columns.  Work is dealt over the SMs by the balanced schedule of rae_internal.h
+// (TcSched): every CTA gets the same number of MMAs; its range is cut into per-tile segments.
 //
 // Warp roles (all kernels): warp 0 = bulk-copy producer, 1 = MMA issuer (warp-uniform loop, elect.sync lane issues),
 // 2 = TMEM allocator, 3 = idle, 4.. = row-owning workers (epilogue / operand generators); worker warp w touches TMEM
@@ -36,11 +41,10 @@ namespace rae {
 
 namespace {
 
-// optional in-kernel timeline (build with -DRAE_TRACE): SM cycle counter of CTA-local milestones, [CTA][64] slots
+// optional in-kernel timeline (build with -DRAE_TRACE, never part of the shipped library): SM cycle counter of CTA-local
+// milestones, [CTA][64] slots; forward kernel slots 0.., dq 16.., dC 32.. (see profiles/trace_tc.py)
 #ifdef RAE_TRACE
 __device__ unsigned long long* g_tc_trace = nullptr;
-// TC_TRACE_INIT() once per thread (reads the buffer pointer into a register: a timestamp then costs one clock read and
-// one asynchronous store, not a dependent global load)
 #define TC_TRACE_INIT() unsigned long long* const tc_trace_ptr_ = g_tc_trace
 #define TC_TRACE(slot)                                                                                         \
     do {                                                                                                       \
@@ -51,13 +55,13 @@ __device__ unsigned long long* g_tc_trace = nullptr;
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
-__device__ int g_tc_bwd_dbg = 0;   // measurement knobs of the backward kernels (RAE_TC_DEBUG bits 8: no MMAs, 16: generators do not store)
-
-constexpr int TC_M = 128;          // rows per CTA (TMEM lanes)
-constexpr int TC_N = 64;           // forward: B-operand rows per chunk (TMEM columns per accumulator stage)
-constexpr int TC_TSTAGES = 4;      // forward: accumulator stages in TMEM
-constexpr int TC_BSTAGES = 4;      // B-operand smem stages
-constexpr int TC_NC = 32;          // backward: reduction rows per chunk (4 k-steps of 8)
+constexpr int TC_M = 128;          // rows per CTA tile (TMEM lanes)
+constexpr int TC_N = 128;          // forward: B-operand rows per chunk = accumulator columns per MMA
+constexpr int TC_H = 64;           // forward: half chunk, the unit one epilogue group consumes
+constexpr int TC_TSTAGES = 2;      // forward: accumulator stages in TMEM (2 x 128 columns)
+constexpr int TC_NC = 32;          // backward: reduction rows per operand chunk in HBM ([c32][hi/lo][8][NK])
+constexpr int TC_SR = 64;          // backward: reduction rows per pipeline stage (two chunks)
+constexpr int TC_BSTAGES = 3;      // backward: B-operand shared-memory stages
 constexpr int TC_FWD_THREADS = 384;    // 4 control + 8 epilogue warps
 constexpr int TC_BWD_THREADS = 640;    // 4 control + 16 generator warps
 constexpr uint32_t TC_FWD_ACOL = 256;  // forward: first TMEM column of the resident P operand (hi, then lo)
@@ -96,42 +100,6 @@ __device__ __forceinline__ void bulk_g2s_pieces(uint8_t* dst_smem, const uint8_t
     constexpr uint32_t PIECE = 1u << 16;    // one instruction per stage: each bulk copy costs ~85 cycles + bytes / 130 B per cycle (profiles/microbench)
     for (uint32_t off = 0; off < bytes; off += PIECE) bulk_g2s(dst_smem + off, src_gmem + off, min(PIECE, bytes - off), bar);
 }
-// ---- thread-block clusters: the B operand of a chunk is fetched ONCE per cluster (each CTA loads 1/cs of it and multicasts
-// the slice into every CTA's stage) instead of once per CTA: the contractions are bound by L2 -> SM operand traffic
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-        : "memory");
-}
-// slice `crank` of a chunk -> the same stage offset of every CTA of the cluster (cs == 1: plain copy of the whole chunk)
-__device__ __forceinline__ void bulk_g2s_chunk(uint8_t* stage, const uint8_t* chunk, uint32_t bytes, uint64_t* bar, uint32_t cs,
-                                               uint32_t crank) {
-    constexpr uint32_t PIECE = 1u << 16;    // one instruction per stage: each bulk copy costs ~85 cycles + bytes / 130 B per cycle (profiles/microbench)
-    const uint32_t slice = bytes / cs, base = slice * crank;
-    const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-    for (uint32_t off = 0; off < slice; off += PIECE) {
-        const uint32_t nb = min(PIECE, slice - off);
-        if (cs == 1) bulk_g2s(stage + base + off, chunk + base + off, nb, bar);
-        else bulk_g2s_mc(stage + base + off, chunk + base + off, nb, bar, mask);
-    }
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
-
 // one lane of a converged warp (the loops around it stay warp-uniform, so descriptor math lives in uniform registers)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -228,9 +196,37 @@ __device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& 
     lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
 }
 
+// 16 bytes x 4 of one row -> 16 floats
+__device__ __forceinline__ void load16(const float* p, bool ok0, bool ok1, bool ok2, bool ok3, float (&x)[16]) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = ok0 ? *reinterpret_cast<const float4*>(p) : z;
+    const float4 b = ok1 ? *reinterpret_cast<const float4*>(p + 4) : z;
+    const float4 c = ok2 ? *reinterpret_cast<const float4*>(p + 8) : z;
+    const float4 d = ok3 ? *reinterpret_cast<const float4*>(p + 12) : z;
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w; x[12] = d.x; x[13] = d.y; x[14] = d.z; x[15] = d.w;
+}
+
+// segments of a CTA's range under the balanced schedule (rae_internal.h)
+struct TcSeg { int tile, u0, u1, slot; };
+struct TcSegIter {
+    TcSched s; long long cur, end; int x;
+    __device__ __forceinline__ TcSegIter(TcSched s_, int x_) : s(s_), cur(tcs_start(s_, x_)), end(tcs_start(s_, x_ + 1)), x(x_) {}
+    __device__ __forceinline__ bool next(TcSeg& g) {
+        if (cur >= end) return false;
+        g.tile = (int)(cur / s.upt);
+        g.u0 = (int)(cur - (long long)g.tile * s.upt);
+        const long long len = min((long long)(s.upt - g.u0), end - cur);
+        g.u1 = g.u0 + (int)len;
+        g.slot = x - tcs_first(s, g.tile);
+        cur += len;
+        return true;
+    }
+};
+
 // row n of the dense operand Cf -> source [K]-vector (nullptr = zero padding row)
 //   n <  n_bil_rows : C[i, j, :] with i = n / DP, j = n % DP
-//   then DP rows of C1[j,:] and DP rows of C2[j,:]
+//   then DP rows of C1[j,:] and DP rows of C2[j,:]; anything beyond is padding
 __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, const float* C2, int d, int K, int DP,
                                                int n_bil_rows, int n) {
     if (n < n_bil_rows) {
@@ -239,7 +235,7 @@ __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, 
     }
     const int m = n - n_bil_rows;
     const int which = m / DP, j = m - which * DP;
-    if (j >= d) return nullptr;
+    if (j >= d || which > 1) return nullptr;
     const float* src = which == 0 ? C1 : C2;
     return src != nullptr ? src + (size_t)j * K : nullptr;
 }
@@ -247,14 +243,14 @@ __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, 
 // ------------------------------------------------------------------------------------------------------------
 // operand preparation (per step; the dense parameters change every step)
 // ------------------------------------------------------------------------------------------------------------
-// forward B operand: [chunk of 64 rows n][hi/lo][kq][row] float4, 4 consecutive relations per float4
+// blockIdx.y == 0: forward B operand [chunk of 128 rows n][hi/lo][kq][row] float4, 4 consecutive relations per float4
+// blockIdx.y == 1: dq B operand, Cf transposed: [chunk of 32 rows n][hi/lo][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
 __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, const float* __restrict__ C1,
                                                    const float* __restrict__ C2, int d, int K, int KQ, int DP, int n_bil_rows,
-                                                   int n_rows_total, float4* __restrict__ out, int NK, float4* __restrict__ out2) {
+                                                   int n_rows_fwd, float4* __restrict__ out, int NK, int n_rows_bwd,
+                                                   float4* __restrict__ out2) {
     if (blockIdx.y == 1) {
-        // second half of the grid: the transposed operand of the dq contraction
-        // out2[c32][hi/lo][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
-        const size_t total2 = (size_t)(n_rows_total / 4) * NK;
+        const size_t total2 = (size_t)(n_rows_bwd / 4) * NK;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (size_t)gridDim.x * blockDim.x) {
             const int krow = (int)(idx % NK);
             const int nq_g = (int)(idx / NK);
@@ -273,7 +269,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
         }
         return;
     }
-    const size_t total = (size_t)n_rows_total * KQ;
+    const size_t total = (size_t)n_rows_fwd * KQ;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int kq = (int)(idx % KQ);
         const int n = (int)(idx / KQ);
@@ -293,35 +289,13 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
     }
 }
 
-// dq B operand: Cf transposed, [chunk of 32 rows n][hi/lo][nq 0..7][krow 0..NK-1] float4 = (Cf[32c+4nq+0..3][krow])
-__global__ void __launch_bounds__(256) k_tc_prep_ct(const float* __restrict__ C, const float* __restrict__ C1,
-                                                    const float* __restrict__ C2, int d, int K, int NK, int DP, int n_bil_rows,
-                                                    int n_rows_total, float4* __restrict__ out) {
-    const size_t total = (size_t)(n_rows_total / 4) * NK;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int krow = (int)(idx % NK);
-        const int nq_g = (int)(idx / NK);
-        float x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 4 * nq_g + u);
-            x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
-        }
-        float4 hi, lo;
-        split4(x, hi, lo);
-        const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
-        float4* base = out + (size_t)c32 * 2 * 8 * NK;
-        base[(size_t)nq * NK + krow] = hi;
-        base[(size_t)(8 + nq) * NK + krow] = lo;
-    }
-}
-
-// dC B operand: q transposed, [chunk of 32 examples][hi/lo][bq 0..7][krow 0..NK-1] float4 = (q[32c+4bq+0..3][krow])
-__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, float4* __restrict__ out,
+// blockIdx.y == 0: dC B operand, q transposed: [chunk of 32 examples][hi/lo][bq 0..7][krow 0..NK-1] = (q[32c+4bq+0..3][krow]),
+//                  nbc chunks (an even number: the kernels consume two per stage; examples >= B are zero)
+// blockIdx.y == 1: L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev, one warp per example
+__global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, int nbc, float4* __restrict__ out,
                                                     const float* __restrict__ A, const int32_t* __restrict__ a1,
                                                     const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev) {
     if (blockIdx.y == 1) {
-        // second half of the grid: L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev, one warp per example
         const int lane = threadIdx.x & 31;
         for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
             const int r1 = a1[b], r2 = quirk ? r1 : a2[b];
@@ -333,7 +307,6 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
         }
         return;
     }
-    const int nbc = (B + TC_NC - 1) / TC_NC;
     const size_t total = (size_t)nbc * 8 * NK;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int krow = (int)(idx % NK);
@@ -355,23 +328,23 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
 
 // ------------------------------------------------------------------------------------------------------------
 // forward contraction (also used for the backward recompute with L := a, R := c)
-// TMEM map: accumulator stages [0,256) (4 x 64 columns), P operand hi at [256, 256+Kp), lo at [256+Kp, 256+2Kp)
+// TMEM map: accumulator stages [0,256) (2 x 128 columns), P operand hi at [256, 256+Kp), lo at [256+Kp, 256+2Kp)
+// Work unit = one 128-row chunk of Cf = two 64-row half chunks; epilogue group g (4 warps) consumes half g of EVERY chunk
+// (accumulator columns [64 g, 64 g + 64)), so for DP = 128 group g always holds the column half j in [64 g, 64 g + 64).
 // ------------------------------------------------------------------------------------------------------------
 struct TcArgs {
     const float* q;         // [B,K]
     const float4* bop;      // B operand chunks
     const float* ev;        // per-example vectors (L at slotL, R at slotR), row stride E_NV*dp
-    float* ev_out;          // SP chunks write c1 / c2 here (E_C1 / E_C2)
+    float* ev_out;          // SP half chunks write c1 / c2 here (E_C1 / E_C2)
     float* vg;              // [2][B][dp]   v partial per epilogue group
-    float* wp;              // [NS][2][B][dp] w partial per (split, group)
+    float* wp;              // [slot][2][B][dp] w partial per (segment slot, group)
     int B, K, d, dp, KQ;
     int slotL, slotR;
-    int n_bil_chunks;       // chunks holding bilinear rows
-    int n_sp_chunks;        // chunks holding C1/C2 rows (forward only)
-    int NS;                 // splits of the bilinear chunk range per tile
-    int cs;                 // cluster size (1, 2 or 4): CTAs of a cluster = consecutive tiles of the SAME split
-    int ntile;
-    int dbg;                // measurement knobs (RAE_TC_DEBUG): 1 no operand copies after the first fills, 2 no MMAs, 4 no epilogue math
+    int n_bil_half;         // half chunks holding bilinear rows
+    int n_sp_half;          // half chunks holding C1/C2 rows (forward only; 0 for the recompute pass)
+    int nbs;                // B-operand shared-memory stages
+    TcSched sch;            // units = 128-row chunks, tiles = example tiles
 };
 
 template <int DP>
@@ -379,36 +352,23 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
-    const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;     // a cluster = cs consecutive tiles
-    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint32_t B_BYTES = 2u * p.KQ * TC_N * 16u;
     const uint32_t Kp = 4u * p.KQ;                          // relations padded to a multiple of 8
+    const int nbs = p.nbs;
     uint8_t* smB = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * B_BYTES);
-    uint64_t* a_full = bars;                                // 8 epilogue-warp arrivals: P operand is in TMEM
-    uint64_t* b_full = bars + 1;
-    uint64_t* b_empty = b_full + TC_BSTAGES;
-    uint64_t* t_full = b_empty + TC_BSTAGES;
-    uint64_t* t_empty = t_full + TC_TSTAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nbs * B_BYTES);
+    uint64_t* a_full = bars;                                // 8 epilogue-warp arrivals per segment: P operand is in TMEM
+    uint64_t* b_full = bars + 1;                            // [4]
+    uint64_t* b_empty = b_full + 4;                         // [4]
+    uint64_t* t_full = b_empty + 4;                         // [TC_TSTAGES]
+    uint64_t* t_empty = t_full + TC_TSTAGES;                // [TC_TSTAGES] 8 epilogue-warp arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TC_TSTAGES);
-
-    // chunk range of this CTA: the bilinear chunks are split NS ways at even boundaries, the last split also takes SP
-    int c_begin, c_end;
-    {
-        const int pairs = (p.n_bil_chunks + 1) / 2;
-        const int per = (pairs + p.NS - 1) / p.NS;
-        c_begin = min(2 * per * split, p.n_bil_chunks);
-        c_end = min(2 * per * (split + 1), p.n_bil_chunks);
-        if (split == p.NS - 1) c_end = p.n_bil_chunks + p.n_sp_chunks;
-    }
-    const int nit = c_end - c_begin;
     if (threadIdx.x == 0) TC_TRACE(0);
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 8);
-        // a stage is free once EVERY CTA of the cluster has consumed it (its next fill is multicast into all of them)
-        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], cs); }
-        for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < nbs; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -417,7 +377,6 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (cs > 1) cluster_sync_all();       // every CTA's barriers exist before a peer multicasts into them / arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TRACE(1);
@@ -426,288 +385,231 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     }
     if (warp == 0) {
-        // ===== producer =====
+        // ===== producer: the chunk sequence of all segments, one bulk copy per chunk =====
         if (lane == 0) {
-            for (int it = 0; it < nit; ++it) {
-                const int s = it % TC_BSTAGES;
-                const uint32_t ph = (it / TC_BSTAGES) & 1;
-                mbar_wait(&b_empty[s], ph ^ 1);
-                if ((p.dbg & 1) && it >= TC_BSTAGES) {      // measurement only: stage keeps its old contents
-                    mbar_arrive(&b_full[s]);
-                    continue;
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0;
+            while (si.next(sg)) {
+                for (int c = sg.u0; c < sg.u1; ++c, ++it) {
+                    const int s = it % nbs;
+                    const uint32_t ph = (it / nbs) & 1;
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    mbar_expect_tx(&b_full[s], B_BYTES);
+                    bulk_g2s_pieces(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)c * B_BYTES, B_BYTES,
+                                    &b_full[s]);
                 }
-                mbar_expect_tx(&b_full[s], B_BYTES);
-                bulk_g2s_chunk(smB + (size_t)s * B_BYTES, reinterpret_cast<const uint8_t*>(p.bop) + (size_t)(c_begin + it) * B_BYTES,
-                               B_BYTES, &b_full[s], cs, crank);
-                if (it == 0) TC_TRACE(2);
             }
-            TC_TRACE(3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
-        if (nit > 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
-            const uint32_t a_hi = tmem_base + TC_FWD_ACOL, a_lo = a_hi + Kp;
-            uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
-#pragma unroll
-            for (int s = 0; s < TC_BSTAGES; ++s) {
-                const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
-                dbh0[s] = make_desc(b_hi, TC_N * 16u, 128u);
-                dbl0[s] = make_desc(b_hi + p.KQ * TC_N * 16u, TC_N * 16u, 128u);
-            }
-            const int ksteps = p.KQ / 2;
-            mbar_wait(a_full, 0);
+        const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
+        const uint32_t a_hi = tmem_base + TC_FWD_ACOL, a_lo = a_hi + Kp;
+        const int ksteps = p.KQ / 2;
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0;
+        while (si.next(sg)) {
+            mbar_wait(a_full, seg & 1);             // this segment's P rows are in TMEM
             tc_fence_after();
-            if (lane == 0) TC_TRACE(4);
-            // Two chunks are issued INTERLEAVED (different accumulator stages): consecutive MMAs into one accumulator are
-            // a dependent chain whose latency (~60 cycles, measured) exceeds the 32-cycle issue slot of a 128x64x8 MMA.
-            for (int it = 0; it < nit; it += 2) {
-                const bool two = it + 1 < nit;
-                const int s0 = it % TC_BSTAGES, ts0 = it % TC_TSTAGES;
-                const int s1 = (it + 1) % TC_BSTAGES, ts1 = (it + 1) % TC_TSTAGES;
-                mbar_wait(&t_empty[ts0], ((it / TC_TSTAGES) & 1) ^ 1);
-                if (lane == 0 && it < 4) TC_TRACE(8 + 2 * it);
-                mbar_wait(&b_full[s0], (it / TC_BSTAGES) & 1);
-                if (two) {
-                    mbar_wait(&t_empty[ts1], (((it + 1) / TC_TSTAGES) & 1) ^ 1);
-                    mbar_wait(&b_full[s1], ((it + 1) / TC_BSTAGES) & 1);
-                }
-                if (lane == 0 && it < 4) TC_TRACE(9 + 2 * it);
+            for (int c = sg.u0; c < sg.u1; ++c, ++it) {
+                const int s = it % nbs, ts = it % TC_TSTAGES;
+                mbar_wait(&t_empty[ts], ((it / TC_TSTAGES) & 1) ^ 1);
+                mbar_wait(&b_full[s], (it / nbs) & 1);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(ts0 * TC_N), d1 = tmem_base + (uint32_t)(ts1 * TC_N);
+                if (lane == 0 && it == 4) TC_TRACE(6);
                 if (elect_one()) {
-                    uint64_t h0 = dbh0[s0], l0 = dbl0[s0], h1 = dbh0[s1], l1 = dbl0[s1];
-                    for (int ks = 0; ks < ((p.dbg & 2) ? 0 : ksteps); ++ks) {
-                        const uint32_t acc = ks > 0 ? 1u : 0u;
-                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, h0, idesc, acc);                   // hi * hi
-                        if (two) tc_mma_tf32_ts(d1, a_hi + 8u * ks, h1, idesc, acc);
+                    const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
+                    uint64_t h0 = make_desc(b_hi, TC_N * 16u, 128u);
+                    uint64_t l0 = make_desc(b_hi + p.KQ * TC_N * 16u, TC_N * 16u, 128u);
+                    const uint32_t d0 = tmem_base + (uint32_t)(ts * TC_N);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, h0, idesc, ks > 0 ? 1u : 0u);      // hi * hi
                         tc_mma_tf32_ts(d0, a_hi + 8u * ks, l0, idesc, 1u);                    // hi * lo
-                        if (two) tc_mma_tf32_ts(d1, a_hi + 8u * ks, l1, idesc, 1u);
                         tc_mma_tf32_ts(d0, a_lo + 8u * ks, h0, idesc, 1u);                    // lo * hi
-                        if (two) tc_mma_tf32_ts(d1, a_lo + 8u * ks, h1, idesc, 1u);
                         h0 = desc_advance(h0, 2u * TC_N * 16u);
                         l0 = desc_advance(l0, 2u * TC_N * 16u);
-                        h1 = desc_advance(h1, 2u * TC_N * 16u);
-                        l1 = desc_advance(l1, 2u * TC_N * 16u);
                     }
-                    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
-                    // smem stages reusable once these MMAs have read them (signalled to every CTA of the cluster)
-                    if (cs > 1) tc_commit_mc(&b_empty[s0], cmask); else tc_commit(&b_empty[s0]);
-                    tc_commit(&t_full[ts0]);     // accumulators complete
-                    if (two) {
-                        if (cs > 1) tc_commit_mc(&b_empty[s1], cmask); else tc_commit(&b_empty[s1]);
-                        tc_commit(&t_full[ts1]);
-                    }
+                    tc_commit(&b_empty[s]);      // the stage is reusable once these MMAs have read it
+                    tc_commit(&t_full[ts]);      // accumulators complete
                 }
                 __syncwarp();
+                if (lane == 0 && it == 4) TC_TRACE(7);
             }
+            ++seg;
         }
+        if (lane == 0) TC_TRACE(3);
     } else if (warp >= 4) {
         // ===== row-owning warps: P operand -> TMEM, then epilogue =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
         const int ew = warp - 4, g = ew >> 2, q4 = ew & 3;
         const int row = q4 * 32 + lane;
-        const int b = tile * TC_M + row;
-        const bool ok = b < p.B;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        {
-            // q row -> TF32 hi / lo planes of the A operand in TMEM.  Group g converts relations [56 g, 56 g + 56): all of a
-            // thread's loads are issued before the first conversion (one memory latency) and the code stays small
-            // (straight-line code that runs once is paid in instruction-cache misses).
-            const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
-            const int kb = 56 * g;
-            float qh[56];
-            if ((p.K & 3) == 0) {
-                const float4* q4 = reinterpret_cast<const float4*>(qr + kb);
-#pragma unroll
-                for (int i = 0; i < 14; ++i) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && kb + 4 * i < p.K) v = q4[i];
-                    qh[4 * i] = v.x; qh[4 * i + 1] = v.y; qh[4 * i + 2] = v.z; qh[4 * i + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 56; ++i) qh[i] = (ok && kb + i < p.K) ? qr[kb + i] : 0.f;
-            }
-            const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)kb, a_lo_col = a_hi_col + Kp;
-#pragma unroll
-            for (int c8 = 0; c8 < 7; ++c8) {
-                if ((uint32_t)(kb + 8 * c8) < Kp) {
-                    float x[8], hi[8], lo[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) x[u] = qh[8 * c8 + u];
-                    split8(x, hi, lo);
-                    tc_st8(a_hi_col + 8u * c8, hi);
-                    tc_st8(a_lo_col + 8u * c8, lo);
-                }
-            }
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
-            if (warp == 4 && lane == 0) TC_TRACE(5);
-        }
-        const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
         constexpr int RW = (DP >= 64) ? 64 : 32;      // columns of R / w held per thread
         const int jbase = (DP == 128) ? 64 * g : 0;
-        float Rr[RW], Wr[RW];
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0;
+        while (si.next(sg)) {
+            const int b = sg.tile * TC_M + row;
+            const bool ok = b < p.B;
+            {
+                // q row -> TF32 hi / lo planes of the A operand in TMEM.  Group g converts relations [56 g, 56 g + 56): all of
+                // a thread's loads are issued before the first conversion (one memory latency).  Segments after the first:
+                // this warp has seen t_full of the previous segment's last chunk, so every MMA that read the old rows is done.
+                const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
+                const int kb = 56 * g;
+                float qh[56];
+                if ((p.K & 3) == 0) {
+                    const float4* qv = reinterpret_cast<const float4*>(qr + kb);
 #pragma unroll
-        for (int c = 0; c < RW; ++c) {
-            const int j = jbase + c;
-            Rr[c] = (ok && j < p.d) ? evb[p.slotR * p.dp + j] : 0.f;
-            Wr[c] = 0.f;
-        }
-        for (int it = g; it < nit; it += 2) {
-            const int ts = it % TC_TSTAGES;
-            const uint32_t tph = (it / TC_TSTAGES) & 1;
-            const int c = c_begin + it;
-            // L values this chunk needs (issued before the wait so the loads overlap it)
-            float L0 = 0.f, L1 = 0.f;
-            int i0 = 0;
-            if (c < p.n_bil_chunks) {
-                i0 = (DP == 128) ? (c >> 1) : (DP == 64 ? c : 2 * c);
-                if (ok && i0 < p.d) L0 = evb[p.slotL * p.dp + i0];
-                if (DP == 32 && ok && i0 + 1 < p.d) L1 = evb[p.slotL * p.dp + i0 + 1];
+                    for (int i = 0; i < 14; ++i) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && kb + 4 * i < p.K) v = qv[i];
+                        qh[4 * i] = v.x; qh[4 * i + 1] = v.y; qh[4 * i + 2] = v.z; qh[4 * i + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 56; ++i) qh[i] = (ok && kb + i < p.K) ? qr[kb + i] : 0.f;
+                }
+                const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)kb, a_lo_col = a_hi_col + Kp;
+#pragma unroll
+                for (int c8 = 0; c8 < 7; ++c8) {
+                    if ((uint32_t)(kb + 8 * c8) < Kp) {
+                        float x[8], hi[8], lo[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) x[u] = qh[8 * c8 + u];
+                        split8(x, hi, lo);
+                        tc_st8(a_hi_col + 8u * c8, hi);
+                        tc_st8(a_lo_col + 8u * c8, lo);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
             }
-            if (ew == 0 && lane == 0 && it < 8) TC_TRACE(24 + it);
-            mbar_wait(&t_full[ts], tph);
-            if (ew == 0 && lane == 0 && it < 8) TC_TRACE(25 + it);
-            tc_fence_after();
-            const bool bil = c < p.n_bil_chunks;
-            const int sc = c - p.n_bil_chunks;
+            const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
             float* o = p.ev_out + (size_t)(ok ? b : 0) * E_NV * p.dp;
-            float vsum = 0.f;
-            // the 64 accumulator columns are consumed in two halves of 32 to bound register pressure
+            float Rr[RW], Wr[RW];
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                float t[32];
-                tc_ld32(lane_base + (uint32_t)(ts * TC_N + 32 * hf), t);
-                if (ew == 0 && lane == 0 && (it == 4 || it == 6)) TC_TRACE(16 + 2 * (it - 4) + hf);
-                if (hf == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[ts]);     // accumulator stage free for the next MMA
-                }
-                if (p.dbg & 4) continue;
-                if (bil) {
-                    if (DP >= 64) {
-                        float v4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            v4[x & 3] = fmaf(t[x], Rr[(32 * hf + x) % RW], v4[x & 3]);
-                            Wr[(32 * hf + x) % RW] = fmaf(t[x], L0, Wr[(32 * hf + x) % RW]);
-                        }
-                        vsum += (v4[0] + v4[1]) + (v4[2] + v4[3]);
-                    } else {
-                        const float Lh = hf == 0 ? L0 : L1;
-                        float v4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            v4[x & 3] = fmaf(t[x], Rr[x % RW], v4[x & 3]);
-                            Wr[x % RW] = fmaf(t[x], Lh, Wr[x % RW]);
-                        }
-                        if (ok && i0 + hf < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0 + hf] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
-                    }
-                } else if (ok) {
-                    // selectional-preference rows: the accumulator row IS c1 / c2
-                    if (DP == 128) {
-                        const int slot = (sc < 2) ? E_C1 : E_C2, jb = 64 * (sc & 1) + 32 * hf;
-#pragma unroll
-                        for (int x = 0; x < 32; ++x)
-                            if (jb + x < p.d) o[slot * p.dp + jb + x] = t[x];
-                    } else if (DP == 64) {
-                        const int slot = (sc == 0) ? E_C1 : E_C2;
-#pragma unroll
-                        for (int x = 0; x < 32; ++x)
-                            if (32 * hf + x < p.d) o[slot * p.dp + 32 * hf + x] = t[x];
-                    } else {
-                        const int slot = hf == 0 ? E_C1 : E_C2;
-#pragma unroll
-                        for (int x = 0; x < 32; ++x)
-                            if (x < p.d) o[slot * p.dp + x] = t[x];
-                    }
-                }
-            }
-            if (DP >= 64 && bil && ok && i0 < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0] = vsum;
-            if (ew == 0 && lane == 0 && (it == 4 || it == 6)) TC_TRACE(18 + 2 * (it - 4));
-        }
-        if (ew == 0 && lane == 0) TC_TRACE(6);
-        if (ok) {
-            float* o = p.wp + (((size_t)split * 2 + g) * p.B + b) * p.dp;      // dp % 4 == 0: 16-byte stores
-#pragma unroll
-            for (int c = 0; c < RW; c += 4) {
+            for (int c = 0; c < RW; ++c) {
                 const int j = jbase + c;
-                if (j < p.dp) *reinterpret_cast<float4*>(o + j) = make_float4(Wr[c], Wr[c + 1], Wr[c + 2], Wr[c + 3]);
+                Rr[c] = (ok && j < p.d) ? evb[p.slotR * p.dp + j] : 0.f;
+                Wr[c] = 0.f;
+            }
+            for (int c = sg.u0; c < sg.u1; ++c, ++it) {
+                const int ts = it % TC_TSTAGES;
+                const uint32_t tph = (it / TC_TSTAGES) & 1;
+                const int hc = 2 * c + g;                      // this group's half chunk
+                const bool bil = hc < p.n_bil_half;
+                const bool sp = !bil && hc < p.n_bil_half + p.n_sp_half;
+                // L values this half chunk needs (issued before the wait so the loads overlap it)
+                float L0 = 0.f, L1 = 0.f;
+                int i0 = 0;
+                if (bil) {
+                    i0 = (DP == 128) ? (hc >> 1) : (DP == 64 ? hc : 2 * hc);
+                    if (ok && i0 < p.d) L0 = evb[p.slotL * p.dp + i0];
+                    if (DP == 32 && ok && i0 + 1 < p.d) L1 = evb[p.slotL * p.dp + i0 + 1];
+                }
+                mbar_wait(&t_full[ts], tph);
+                tc_fence_after();
+                if (!bil && !sp) {                             // padding half chunk: nothing to read
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[ts]);
+                    continue;
+                }
+                const int sc = hc - p.n_bil_half;
+                float vsum = 0.f;
+                // the 64 accumulator columns are consumed in two halves of 32 to bound register pressure
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float t[32];
+                    tc_ld32(lane_base + (uint32_t)(ts * TC_N + TC_H * g + 32 * hf), t);
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&t_empty[ts]);     // this group is done with the accumulator stage
+                    }
+                    if (bil) {
+                        if (DP >= 64) {
+                            float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int x = 0; x < 32; ++x) {
+                                v4[x & 3] = fmaf(t[x], Rr[(32 * hf + x) % RW], v4[x & 3]);
+                                Wr[(32 * hf + x) % RW] = fmaf(t[x], L0, Wr[(32 * hf + x) % RW]);
+                            }
+                            vsum += (v4[0] + v4[1]) + (v4[2] + v4[3]);
+                        } else {
+                            const float Lh = hf == 0 ? L0 : L1;
+                            float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int x = 0; x < 32; ++x) {
+                                v4[x & 3] = fmaf(t[x], Rr[x % RW], v4[x & 3]);
+                                Wr[x % RW] = fmaf(t[x], Lh, Wr[x % RW]);
+                            }
+                            if (ok && i0 + hf < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0 + hf] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
+                        }
+                    } else if (ok) {
+                        // selectional-preference rows: the accumulator row IS c1 / c2
+                        if (DP == 128) {
+                            const int slot = (sc < 2) ? E_C1 : E_C2, jb = 64 * (sc & 1) + 32 * hf;
+#pragma unroll
+                            for (int x = 0; x < 32; ++x)
+                                if (jb + x < p.d) o[slot * p.dp + jb + x] = t[x];
+                        } else if (DP == 64) {
+                            const int slot = (sc == 0) ? E_C1 : E_C2;
+#pragma unroll
+                            for (int x = 0; x < 32; ++x)
+                                if (32 * hf + x < p.d) o[slot * p.dp + 32 * hf + x] = t[x];
+                        } else {
+                            const int slot = hf == 0 ? E_C1 : E_C2;
+#pragma unroll
+                            for (int x = 0; x < 32; ++x)
+                                if (x < p.d) o[slot * p.dp + x] = t[x];
+                        }
+                    }
+                }
+                if (DP >= 64 && bil && ok && i0 < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0] = vsum;
+            }
+            if (ok) {
+                float* wo = p.wp + (((size_t)sg.slot * 2 + g) * p.B + b) * p.dp;      // dp % 4 == 0: 16-byte stores
+#pragma unroll
+                for (int c = 0; c < RW; c += 4) {
+                    const int j = jbase + c;
+                    if (j < p.dp) *reinterpret_cast<float4*>(wo + j) = make_float4(Wr[c], Wr[c + 1], Wr[c + 2], Wr[c + 3]);
+                }
             }
         }
-        if (ew == 0 && lane == 0) TC_TRACE(7);
+        if (ew == 0 && lane == 0) TC_TRACE(4);
     }
     tc_fence_before();
     __syncthreads();
-    if (cs > 1) cluster_sync_all();       // nobody leaves while a peer may still write into its stages / barriers
-    if (threadIdx.x == 0) TC_TRACE(62);
+    if (threadIdx.x == 0) TC_TRACE(5);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-        if (lane == 0) TC_TRACE(63);
-    }
-}
-
-// v[b,i]: DP=128 both epilogue groups hold a half-row partial; DP=64 group i%2 produced it; DP=32 group (i/2)%2.
-// w[b,j]: sum over splits of the group partials (DP=128: only group j/64 holds column j).  Nothing needs pre-zeroing.
-__global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vg, const float* __restrict__ wp, float* __restrict__ ev,
-                                                    int B, int d, int dp, int DP, int NS, int slotV, int slotW) {
-    const size_t total = (size_t)B * dp;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx % dp);
-        const size_t b = idx / dp;
-        if (j >= d) continue;
-        float v;
-        if (DP == 128) v = vg[idx] + vg[total + idx];
-        else if (DP == 64) v = vg[(size_t)(j & 1) * total + idx];
-        else v = vg[(size_t)((j >> 1) & 1) * total + idx];
-        float w = 0.f;
-        if (DP == 128) {
-            const int g = j >> 6;
-            for (int s = 0; s < NS; ++s) w += wp[(size_t)(2 * s + g) * total + idx];
-        } else {
-            for (int s = 0; s < 2 * NS; ++s) w += wp[(size_t)s * total + idx];
-        }
-        ev[(b * E_NV + slotV) * dp + j] = v;
-        ev[(b * E_NV + slotW) * dp + j] = w;
-    }
-}
-
-// L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev
-__global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ A, const int32_t* __restrict__ a1,
-                                                      const int32_t* __restrict__ a2, int B, int d, int dp, int quirk,
-                                                      float* __restrict__ ev) {
-    const int lane = threadIdx.x & 31;
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= B) return;
-    const int r1 = a1[b], r2 = quirk ? r1 : a2[b];
-    float* o = ev + (size_t)b * E_NV * dp;
-    for (int j = lane; j < d; j += 32) {
-        o[E_L * dp + j] = ld_nc(A + (size_t)r1 * d + j);
-        o[E_R * dp + j] = ld_nc(A + (size_t)r2 * d + j);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward kernels: generated A operand in TMEM.
-// TMEM map: accumulator [0,128) (NK <= 128 columns used); A stage s: hi at [128 + 64 s, +32), lo at [128 + 64 s + 32, +32)
+// backward kernels: generated A operand in TMEM, 64 reduction rows per pipeline stage.
+// TMEM map: accumulator [0,128) (NK <= 128 columns used); A stage s: hi at [128 + 128 s, +64), lo at [128 + 128 s + 64, +64);
+//           dq: 3 A stages ([128, 512)); dC: 2 A stages ([128, 384)) and a second accumulator at [384, 512)
 // generated operand  G[b,n]:  bilinear row n=(i,j): a_bi R_bj + L_bi Y2_bj ;  C1 row j: a_bj + G2_b L_bj ;  C2 row j: c_bj + G1_b R_bj
+// Each of the 16 generator warps publishes 16 columns of a stage per hand-off (one mbarrier arrival per warp and stage).
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t TC_BWD_ACOL = 128;
-constexpr int TC_ASTAGES = 4;          // generated-operand stages in TMEM (64 columns each: hi 32 + lo 32); 128 + 4*64 = 384 <= 512
+constexpr int TC_DQ_ASTAGES = 3;
+constexpr int TC_DC_ASTAGES = 2;
 // Second accumulator of the dC contraction at [384, 512).  tcgen05.mma adds into the fp32 accumulator with truncation, so
 // a long chain of MMAs into ONE accumulator drifts towards zero by ~2e-8 of the sum per MMA (measured at the target shape,
 // profiles/r01_accum_chain.md: 1536 MMAs -> 3.4e-5 of ||dC||_inf, 180 MMAs -> 3.2e-6).  The reduction over examples is
-// therefore dealt over two accumulators (even / odd chunks, summed with a rounded fp32 add in the epilogue) and over
-// enough batch splits (tc_init) that no accumulator takes more than TC_DC_MAX_CHAIN chunks of 12 MMAs.
+// therefore dealt over two accumulators (even / odd stages, summed with a rounded fp32 add in the epilogue) and the
+// schedule (tc_init) gives no segment more than TC_DC_MAX_STAGES stages of 24 MMAs per accumulator.
 constexpr uint32_t TC_BWD_ACC2 = 384;
-constexpr int TC_DC_MAX_CHAIN = 32;    // chunks (of 32 examples, 12 MMAs each) per accumulator
-constexpr int TC_DQ_MAX_CHAIN = 130;   // dq: chunks (of 32 reduction rows, 12 MMAs each) per CTA; random-sign terms drift less
+constexpr int TC_DC_MAX_STAGES = 16;   // stages (of 64 examples, 24 MMAs each) per accumulator: 384 MMAs
+constexpr int TC_DQ_MAX_STAGES = 64;   // dq: stages (of 64 reduction rows) per segment: 1536 MMAs; random-sign terms drift less
 
 // transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
 __global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
@@ -731,34 +633,26 @@ __global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict
     }
 }
 
-struct TcDqArgs {
-    const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
-    const float* ev; const float* sc; const float* aT; const float* LT;
-    float* dqp;             // [NS][B][NK]
-    int B, d, dp, K, NK;
-    int n_bil_rows, n_chunks32, NS;
-    int cs, ntile;          // cluster size; CTAs of a cluster = consecutive example tiles of the SAME split (same streamed chunks)
-};
-
 // shared skeleton pieces of the two backward kernels ------------------------------------------------------------
 struct BwdBars {
-    uint64_t* a_full; uint64_t* a_empty; uint64_t* b_full; uint64_t* b_empty; uint64_t* acc_full; uint32_t* tmem_slot;
+    uint64_t* a_full; uint64_t* a_empty; uint64_t* b_full; uint64_t* b_empty; uint64_t* acc_full; uint64_t* acc_empty; uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t B_BYTES, int warp, uint32_t& tmem_base, uint32_t cs) {
+__device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t ST_BYTES, int warp, uint32_t& tmem_base) {
     BwdBars br;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * B_BYTES);
-    br.a_full = bars;                         // [TC_ASTAGES] 16 generator-warp arrivals
-    br.a_empty = bars + TC_ASTAGES;           // [TC_ASTAGES] tcgen05.commit
-    br.b_full = bars + 2 * TC_ASTAGES;        // [TC_BSTAGES] bulk-copy tx
-    br.b_empty = br.b_full + TC_BSTAGES;      // [TC_BSTAGES] tcgen05.commit
-    br.acc_full = br.b_empty + TC_BSTAGES;
-    br.tmem_slot = reinterpret_cast<uint32_t*>(br.acc_full + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_BSTAGES * ST_BYTES);
+    br.a_full = bars;                 // [4] 16 generator-warp arrivals
+    br.a_empty = bars + 4;            // [4] tcgen05.commit
+    br.b_full = bars + 8;             // [4] bulk-copy tx
+    br.b_empty = bars + 12;           // [4] tcgen05.commit
+    br.acc_full = bars + 16;          // tcgen05.commit behind a segment's last MMA
+    br.acc_empty = bars + 17;         // 4 drain-warp arrivals: the accumulators may be overwritten by the next segment
+    br.tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_ASTAGES; ++s) { mbar_init(&br.a_full[s], 16); mbar_init(&br.a_empty[s], 1); }
-        // a stage is free once EVERY CTA of the cluster has consumed it (its next fill is multicast into all of them)
-        for (int s = 0; s < TC_BSTAGES; ++s) { mbar_init(&br.b_full[s], 1); mbar_init(&br.b_empty[s], cs); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&br.a_full[s], 16); mbar_init(&br.a_empty[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&br.b_full[s], 1); mbar_init(&br.b_empty[s], 1); }
         mbar_init(br.acc_full, 1);
+        mbar_init(br.acc_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -767,368 +661,440 @@ __device__ __forceinline__ BwdBars bwd_setup(uint8_t* smem_raw, uint32_t B_BYTES
     }
     tc_fence_before();
     __syncthreads();
-    if (cs > 1) cluster_sync_all();
     tc_fence_after();
     tmem_base = *br.tmem_slot;
     return br;
 }
 
-__device__ __forceinline__ void bwd_producer(const BwdBars& br, uint8_t* smB, const uint8_t* src, uint32_t B_BYTES, int c_begin, int nit,
-                                             uint32_t cs, uint32_t crank) {
-    for (int it = 0; it < nit; ++it) {
-        const int s = it % TC_BSTAGES;
-        const uint32_t ph = (it / TC_BSTAGES) & 1;
-        mbar_wait(&br.b_empty[s], ph ^ 1);
-        mbar_expect_tx(&br.b_full[s], B_BYTES);
-        bulk_g2s_chunk(smB + (size_t)s * B_BYTES, src + (size_t)(c_begin + it) * B_BYTES, B_BYTES, &br.b_full[s], cs, crank);
+// producer of one segment: stage `st0 + lt` of the operand = two consecutive 32-row chunks, one bulk copy
+__device__ __forceinline__ void bwd_produce(const BwdBars& br, uint8_t* smB, const uint8_t* src, uint32_t ST_BYTES, int st0, int nst, int it0) {
+    for (int lt = 0; lt < nst; ++lt) {
+        const int git = it0 + lt, s = git % TC_BSTAGES;
+        mbar_wait(&br.b_empty[s], ((git / TC_BSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&br.b_full[s], ST_BYTES);
+        bulk_g2s_pieces(smB + (size_t)s * ST_BYTES, src + (size_t)(st0 + lt) * ST_BYTES, ST_BYTES, &br.b_full[s]);
     }
 }
 
-__device__ __forceinline__ void bwd_mma(const BwdBars& br, uint8_t* smB, uint32_t B_BYTES, int NK, uint32_t tmem_base, int nit, int trace_base,
-                                        uint32_t cs, int nacc = 1) {
+// MMAs of one segment: 24 per stage (2 chunks x 4 k-steps x {hi.hi, hi.lo, lo.hi}); stage lt accumulates into accumulator
+// lt % nacc, whose first MMA overwrites; the commit behind the last stage signals acc_full
+template <int NAS>
+__device__ __forceinline__ void bwd_mma_segment(const BwdBars& br, uint8_t* smB, uint32_t ST_BYTES, int NK, uint32_t tmem_base, int nst,
+                                                int it0, int nacc, int trace_base) {
     TC_TRACE_INIT();
     const uint32_t idesc = make_idesc_tf32(TC_M, NK);
-    uint64_t dbh0[TC_BSTAGES], dbl0[TC_BSTAGES];
-#pragma unroll
-    for (int s = 0; s < TC_BSTAGES; ++s) {
-        const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
-        dbh0[s] = make_desc(b_hi, (uint32_t)NK * 16u, 128u);
-        dbl0[s] = make_desc(b_hi + 8u * (uint32_t)NK * 16u, (uint32_t)NK * 16u, 128u);
-    }
-    for (int it = 0; it < nit; ++it) {
-        const int s = it % TC_BSTAGES, as = it % TC_ASTAGES;
-        const uint32_t ph = (it / TC_BSTAGES) & 1, aph = (it / TC_ASTAGES) & 1;
-        mbar_wait(&br.a_full[as], aph);
-        if ((threadIdx.x & 31) == 0 && it >= 40 && it < 43) TC_TRACE(trace_base + 2 * (it - 40));
-        mbar_wait(&br.b_full[s], ph);
-        if ((threadIdx.x & 31) == 0 && it >= 40 && it < 43) TC_TRACE(trace_base + 2 * (it - 40) + 1);
+    const uint32_t CH_BYTES = ST_BYTES / 2;
+    for (int lt = 0; lt < nst; ++lt) {
+        const int git = it0 + lt, s = git % TC_BSTAGES, as = git % NAS;
+        mbar_wait(&br.a_full[as], (git / NAS) & 1);
+        mbar_wait(&br.b_full[s], (git / TC_BSTAGES) & 1);
         tc_fence_after();
+        if ((threadIdx.x & 31) == 0 && git == 8) TC_TRACE(trace_base + 6);
         if (elect_one()) {
-            const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 64u * as, a_lo = a_hi + 32u;
-            // chunk `it` accumulates into accumulator it % nacc; the first chunk of each accumulator overwrites it
-            const uint32_t acc = tmem_base + ((nacc == 2 && (it & 1)) ? TC_BWD_ACC2 : 0u);
-            uint64_t dbh = dbh0[s], dbl = dbl0[s];
+            const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 128u * as, a_lo = a_hi + 64u;
+            const uint32_t acc = tmem_base + ((nacc == 2 && (lt & 1)) ? TC_BWD_ACC2 : 0u);
+            const uint32_t b_base = smem_u32(smB + (size_t)s * ST_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < ((g_tc_bwd_dbg & 8) ? 0 : 4); ++ks) {
-                tc_mma_tf32_ts(acc, a_hi + 8u * ks, dbh, idesc, (it >= nacc || ks > 0) ? 1u : 0u);
-                tc_mma_tf32_ts(acc, a_hi + 8u * ks, dbl, idesc, 1u);
-                tc_mma_tf32_ts(acc, a_lo + 8u * ks, dbh, idesc, 1u);
-                dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
-                dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
+            for (int h = 0; h < 2; ++h) {
+                uint64_t dbh = make_desc(b_base + h * CH_BYTES, (uint32_t)NK * 16u, 128u);
+                uint64_t dbl = make_desc(b_base + h * CH_BYTES + 8u * (uint32_t)NK * 16u, (uint32_t)NK * 16u, 128u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t col = 32u * h + 8u * ks;
+                    tc_mma_tf32_ts(acc, a_hi + col, dbh, idesc, (lt >= nacc || h > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_tf32_ts(acc, a_hi + col, dbl, idesc, 1u);
+                    tc_mma_tf32_ts(acc, a_lo + col, dbh, idesc, 1u);
+                    dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
+                    dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
+                }
             }
-            if (it >= 40 && it < 43) TC_TRACE(trace_base + 6 + (it - 40));     // MMAs of chunk `it` issued
             tc_commit(&br.a_empty[as]);
-            if (cs > 1) tc_commit_mc(&br.b_empty[s], (uint16_t)((1u << cs) - 1u)); else tc_commit(&br.b_empty[s]);
-            if (it == nit - 1) tc_commit(br.acc_full);
+            tc_commit(&br.b_empty[s]);
+            if (lt == nst - 1) tc_commit(br.acc_full);
         }
         __syncwarp();
+        if ((threadIdx.x & 31) == 0 && git == 8) TC_TRACE(trace_base + 7);
     }
 }
 
-// generator warp publishes its 8 columns of A stage `as`
-__device__ __forceinline__ void bwd_publish(const BwdBars& br, uint32_t lane_base, int as, int cg, const float (&g)[8], int lane) {
+// 8 generated values -> hi / lo planes of A stage `as`, columns col8 .. col8 + 7 (the caller waits for the stores)
+__device__ __forceinline__ void bwd_store8(uint32_t lane_base, int as, int col8, const float (&g)[8]) {
     float hi[8], lo[8];
     split8(g, hi, lo);
-    const uint32_t col = lane_base + TC_BWD_ACOL + 64u * as + 8u * cg;
-    if (!(g_tc_bwd_dbg & 16)) {
-        tc_st8(col, hi);
-        tc_st8(col + 32u, lo);
-        tc_wait_st();
-    }
+    const uint32_t col = lane_base + TC_BWD_ACOL + 128u * as + (uint32_t)col8;
+    tc_st8(col, hi);
+    tc_st8(col + 64u, lo);
+}
+// the warp's columns of stage `as` are in TMEM: one arrival
+__device__ __forceinline__ void bwd_publish(const BwdBars& br, int as, int lane) {
+    tc_wait_st();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&br.a_full[as]);
 }
 
-// dq: rows = examples.  Generator thread = (row b, octet cg of the chunk's 32 reduction rows); the R / Y2 values it needs
-// for every bilinear chunk are cached in registers (X, Y), a_bi / L_bi come coalesced from the transposed copies.
+struct TcDqArgs {
+    const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
+    const float* ev; const float* sc; const float* aT; const float* LT;
+    float* dqp;             // [slot][B][NK]
+    int B, d, dp, K, NK;
+    int n_bil_rows;         // reduction rows holding bilinear rows (a multiple of 64)
+    TcSched sch;            // units = SPR stages (one bilinear row for DP >= 64), tiles = example tiles
+};
+
+// dq: rows = examples.  Generator thread = (row b, column group cg of the stage's 64 reduction rows: columns 16 cg .. +15);
+// the R / Y2 values it needs for every bilinear stage are cached in registers (X, Y), a_bi / L_bi come coalesced from
+// the transposed copies, one row ahead of their use.
 template <int DP>
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
-    const int split = blockIdx.x / p.ntile, tile = blockIdx.x - split * p.ntile;
-    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
-    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
+    constexpr int NAS = TC_DQ_ASTAGES;
+    constexpr int SPR = DP >= 64 ? DP / 64 : 1;             // stages per schedule unit (= per bilinear row for DP >= 64)
+    const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     uint32_t tmem_base;
-    if (threadIdx.x == 0) TC_TRACE(32);
-    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base, cs);
-    if (threadIdx.x == 0) TC_TRACE(33);
-    constexpr int JQ = DP / 32;                 // chunks per bilinear row i
-    // split the chunk range at row-i boundaries
-    const int per = ((p.n_chunks32 + p.NS - 1) / p.NS + JQ - 1) / JQ * JQ;
-    const int c_begin = min(per * split, p.n_chunks32), c_end = min(per * (split + 1), p.n_chunks32);
-    const int nit = c_end - c_begin;
+    if (threadIdx.x == 0) TC_TRACE(16);
+    const BwdBars br = bwd_setup(smem_raw, ST_BYTES, warp, tmem_base);
+    if (threadIdx.x == 0) TC_TRACE(17);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     }
     if (warp == 0) {
-        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), B_BYTES, c_begin, nit, cs, crank);
+        if (lane == 0) {
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0;
+            while (si.next(sg)) {
+                const int st0 = sg.u0 * SPR, nst = (sg.u1 - sg.u0) * SPR;
+                bwd_produce(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), ST_BYTES, st0, nst, it);
+                it += nst;
+            }
+        }
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 8, cs);
-    } else if (warp >= 4) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
-        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column octet
-        const int row = q4 * 32 + lane;
-        const int b = tile * TC_M + row;
-        const bool ok = b < p.B;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
-        const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
-        // register cache: for chunk jq of a row i this thread needs j = 32 jq + 8 cg + 0..7 (two 16-byte loads each)
-        float X[JQ][8], Y[JQ][8];
-#pragma unroll
-        for (int jq = 0; jq < JQ; ++jq) {
-            const int j = 32 * jq + 8 * cg;
-            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, y0 = x0, y1 = x0;
-            if (ok && j < p.dp) {              // dp is a multiple of 4 and rows of ev are 16-byte aligned
-                x0 = *reinterpret_cast<const float4*>(evb + E_R * p.dp + j);
-                y0 = *reinterpret_cast<const float4*>(evb + E_Y2 * p.dp + j);
-            }
-            if (ok && j + 4 < p.dp) {
-                x1 = *reinterpret_cast<const float4*>(evb + E_R * p.dp + j + 4);
-                y1 = *reinterpret_cast<const float4*>(evb + E_Y2 * p.dp + j + 4);
-            }
-            X[jq][0] = x0.x; X[jq][1] = x0.y; X[jq][2] = x0.z; X[jq][3] = x0.w; X[jq][4] = x1.x; X[jq][5] = x1.y; X[jq][6] = x1.z; X[jq][7] = x1.w;
-            Y[jq][0] = y0.x; Y[jq][1] = y0.y; Y[jq][2] = y0.z; Y[jq][3] = y0.w; Y[jq][4] = y1.x; Y[jq][5] = y1.y; Y[jq][6] = y1.z; Y[jq][7] = y1.w;
-        }
-        const int n_bil_chunks = p.n_bil_rows / TC_NC;
-        auto emit = [&](const float (&g)[8], int it) {
-            const int as = it % TC_ASTAGES;
-            const uint32_t aph = (it / TC_ASTAGES) & 1;
-            const bool tr = gw == 0 && lane == 0 && it >= 40 && it < 44;      // steady state (not the first fills)
-            if (tr) TC_TRACE(36 + 3 * (it - 40));
-            mbar_wait(&br.a_empty[as], aph ^ 1);
-            if (tr) TC_TRACE(37 + 3 * (it - 40));
-            tc_fence_after();
-            bwd_publish(br, lane_base, as, cg, g, lane);
-            if (tr) TC_TRACE(38 + 3 * (it - 40));
-        };
-        // bilinear rows: the CTA's range starts and ends at row boundaries, so every row i contributes its JQ chunks in
-        // order (static indexing of the register cache).  a_bi / L_bi are loaded one row AHEAD of their use.
-        const int nbil = max(0, min(c_end, n_bil_chunks) - c_begin);
-        int it = 0;
-        float ai_n = 0.f, li_n = 0.f;
-        if (nbil > 0 && ok && c_begin / JQ < p.dp) {
-            ai_n = p.aT[(size_t)(c_begin / JQ) * p.B + b];
-            li_n = p.LT[(size_t)(c_begin / JQ) * p.B + b];
-        }
-        for (int i = c_begin / JQ; it < nbil; ++i) {
-            const float ai = ai_n, li = li_n;
-            const bool more = ok && i + 1 < p.dp && it + JQ < nbil;
-            ai_n = more ? p.aT[(size_t)(i + 1) * p.B + b] : 0.f;
-            li_n = more ? p.LT[(size_t)(i + 1) * p.B + b] : 0.f;
-#pragma unroll
-            for (int jq = 0; jq < JQ; ++jq, ++it) {
-                float g[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) g[u] = fmaf(ai, X[jq][u], li * Y[jq][u]);
-                emit(g, it);
-            }
-        }
-        // selectional-preference rows (a few chunks per tile): direct loads
-        for (; it < nit; ++it) {
-            const int c = c_begin + it;
-            const int m = c * TC_NC - p.n_bil_rows;
-            const int which = m / DP, j0 = m - which * DP + 8 * cg;
-            const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
-            const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
-            float g[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = j0 + u;
-                g[u] = (ok && j < p.dp) ? fmaf(s2, evb[sy * p.dp + j], evb[sx * p.dp + j]) : 0.f;
-            }
-            emit(g, it);
-        }
-        if (gw == 0 && lane == 0) TC_TRACE(34);
-        if (gw < 4) {
-            // ===== epilogue: accumulator row -> dq partial =====
-            if (nit > 0) {
-                mbar_wait(br.acc_full, 0);
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0;
+        while (si.next(sg)) {
+            const int nst = (sg.u1 - sg.u0) * SPR;
+            if (seg > 0) {                                   // the previous segment's accumulator has been drained
+                mbar_wait(br.acc_empty, (seg - 1) & 1);
                 tc_fence_after();
             }
-            float* o = p.dqp + ((size_t)split * p.B + (ok ? b : 0)) * p.NK;
-            for (int c0 = 0; c0 < p.NK; c0 += 32) {
-                float t[32];
-                if (nit > 0) {
-                    tc_ld32(lane_base + (uint32_t)c0, t);
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) t[x] = 0.f;
-                }
-                if (ok) store_row32(o + c0, t, p.NK - c0, true);       // NK is a multiple of 16
-            }
+            bwd_mma_segment<NAS>(br, smB, ST_BYTES, p.NK, tmem_base, nst, it, 1, 16);
+            it += nst;
+            ++seg;
         }
+        if (lane == 0) TC_TRACE(19);
+    } else if (warp >= 4) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column group
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int rsel = (DP == 32) ? (cg >> 1) : 0;                 // DP = 32: a stage holds two rows i
+        const int n_bil_st = p.n_bil_rows / TC_SR;
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0;
+        while (si.next(sg)) {
+            const int b = sg.tile * TC_M + row;
+            const bool ok = b < p.B;
+            const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
+            const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
+            // register cache: stage h of a row needs j = jc(h) + 0..15 (four 16-byte loads each; dp is a multiple of 4)
+            float X[SPR][16], Y[SPR][16];
+#pragma unroll
+            for (int h = 0; h < SPR; ++h) {
+                const int j = (DP == 32) ? 16 * (cg & 1) : 64 * h + 16 * cg;
+                const bool o0 = ok && j < p.dp, o1 = ok && j + 4 < p.dp, o2 = ok && j + 8 < p.dp, o3 = ok && j + 12 < p.dp;
+                load16(evb + E_R * p.dp + j, o0, o1, o2, o3, X[h]);
+                load16(evb + E_Y2 * p.dp + j, o0, o1, o2, o3, Y[h]);
+            }
+            const int st0 = sg.u0 * SPR, st1 = sg.u1 * SPR, nst = st1 - st0;
+            // bilinear rows: segments start and end at row boundaries, so every row contributes its SPR stages in order
+            // (static indexing of the register cache).  a_bi / L_bi are loaded one row AHEAD of their use.
+            const int nbil = max(0, min(st1, n_bil_st) - st0);
+            int lt = 0;
+            float ai_n = 0.f, li_n = 0.f;
+            {
+                const int i = (DP == 32) ? 2 * st0 + rsel : st0 / SPR;
+                if (nbil > 0 && ok && i < p.dp) {
+                    ai_n = p.aT[(size_t)i * p.B + b];
+                    li_n = p.LT[(size_t)i * p.B + b];
+                }
+            }
+            for (int cs = st0; lt < nbil; cs += SPR) {
+                const float ai = ai_n, li = li_n;
+                const int i_next = (DP == 32) ? 2 * (cs + 1) + rsel : cs / SPR + 1;
+                const bool more = ok && i_next < p.dp && lt + SPR < nbil;
+                ai_n = more ? p.aT[(size_t)i_next * p.B + b] : 0.f;
+                li_n = more ? p.LT[(size_t)i_next * p.B + b] : 0.f;
+#pragma unroll
+                for (int h = 0; h < SPR; ++h, ++lt) {
+                    const int git = it + lt, as = git % NAS;
+                    float g0[8], g1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        g0[u] = fmaf(ai, X[h][u], li * Y[h][u]);
+                        g1[u] = fmaf(ai, X[h][8 + u], li * Y[h][8 + u]);
+                    }
+                    const bool tr = gw == 0 && lane == 0 && git == 8;
+                    if (tr) TC_TRACE(24);
+                    mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
+                    tc_fence_after();
+                    if (tr) TC_TRACE(25);
+                    bwd_store8(lane_base, as, 16 * cg, g0);
+                    bwd_store8(lane_base, as, 16 * cg + 8, g1);
+                    bwd_publish(br, as, lane);
+                    if (tr) TC_TRACE(26);
+                }
+            }
+            // selectional-preference rows (a few stages per tile): direct loads
+            for (; lt < nst; ++lt) {
+                const int git = it + lt, as = git % NAS;
+                const int m = (st0 + lt) * TC_SR - p.n_bil_rows + 16 * cg;
+                const int which = m / DP, j0 = m - which * DP;
+                const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
+                const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
+                float xs[16], ys[16];
+                const bool o0 = ok && which < 2 && j0 < p.dp, o1 = ok && which < 2 && j0 + 4 < p.dp, o2 = ok && which < 2 && j0 + 8 < p.dp,
+                           o3 = ok && which < 2 && j0 + 12 < p.dp;
+                load16(evb + sx * p.dp + j0, o0, o1, o2, o3, xs);
+                load16(evb + sy * p.dp + j0, o0, o1, o2, o3, ys);
+                float g0[8], g1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    g0[u] = fmaf(s2, ys[u], xs[u]);
+                    g1[u] = fmaf(s2, ys[8 + u], xs[8 + u]);
+                }
+                mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
+                tc_fence_after();
+                bwd_store8(lane_base, as, 16 * cg, g0);
+                bwd_store8(lane_base, as, 16 * cg + 8, g1);
+                bwd_publish(br, as, lane);
+            }
+            it += nst;
+            if (gw < 4) {
+                // ===== epilogue: accumulator row -> dq partial of this segment's slot =====
+                mbar_wait(br.acc_full, seg & 1);
+                tc_fence_after();
+                float* o = p.dqp + ((size_t)sg.slot * p.B + (ok ? b : 0)) * p.NK;
+                for (int c0 = 0; c0 < p.NK; c0 += 32) {
+                    float t[32];
+                    tc_ld32(lane_base + (uint32_t)c0, t);
+                    if (ok) store_row32(o + c0, t, p.NK - c0, true);       // NK is a multiple of 16
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(br.acc_empty);
+            }
+            ++seg;
+        }
+        if (gw == 0 && lane == 0) TC_TRACE(20);
     }
     tc_fence_before();
     __syncthreads();
-    if (cs > 1) cluster_sync_all();
-    if (threadIdx.x == 0) TC_TRACE(35);
+    if (threadIdx.x == 0) TC_TRACE(21);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-// dC: rows = operand rows n (one CTA per 128-row tile, batch range split NSb ways), reduction over examples.
+// dC: rows = operand rows n (128-row tiles), reduction over examples in stages of 64.
 struct TcDcArgs {
     const float4* pop3;     // q^T chunks [bc][hi/lo][8][NK]
     const float* ev; const float* sc; const float* aT; const float* LT;
-    float* out;             // gC_part [NSb][units*d*K]
+    float* out;             // gC_part [slot][units*d*K]
     int B, d, dp, K, NK, DP;
-    int n_bil_rows, n_rows_total, n_bchunks, NSb, hasM;
-    int nacc;               // TMEM accumulators the example chunks are dealt over (1 or 2)
+    int n_bil_rows, n_rows_total, hasM;
+    int nacc;               // TMEM accumulators the example stages are dealt over (1 or 2)
+    int share;              // most stages one CTA handles (sizes the per-example scalar staging)
     size_t split_stride;    // units*d*K
-    int cs, n_ntiles_pad;   // cluster size; CTAs of a cluster = consecutive ROW tiles of the same batch split; the row-tile count
-                            // is padded to a multiple of cs (tiles past n_rows_total hold padding rows only)
+    TcSched sch;            // units = stages of 64 examples, tiles = 128-row tiles of the operand rows
 };
 
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
-    const int split = blockIdx.x / p.n_ntiles_pad, ntile = blockIdx.x - split * p.n_ntiles_pad;
-    const uint32_t cs = (uint32_t)p.cs, crank = cs > 1 ? cluster_ctarank() : 0u;
-    const uint32_t B_BYTES = 2u * 8u * (uint32_t)p.NK * 16u;
+    constexpr int NAS = TC_DC_ASTAGES;
+    const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
-    const int per = (p.n_bchunks + p.NSb - 1) / p.NSb;
-    const int c_begin = min(per * split, p.n_bchunks), c_end = min(per * (split + 1), p.n_bchunks);
-    const int nit = c_end - c_begin;
-    // Per-example scalars of the generated operand, staged once in shared memory.  A 32-row quarter of the tile is one
-    // bilinear row i (P1 = a_bi, P2 = L_bi) or one selectional-preference table (P1 = 1, P2 = G2_b | G1_b); the tile
-    // holds TC_M / DP such sources.  Coalesced reads of the transposed copies aT / LT.
+    if (threadIdx.x == 0) TC_TRACE(32);
+    // Per-example scalars of the generated operand, staged once in shared memory for every segment of the CTA.  A 32-row
+    // quarter of a tile is one bilinear row i (P1 = a_bi, P2 = L_bi) or one selectional-preference table (P1 = 1,
+    // P2 = G2_b | G1_b); a tile holds TC_M / DP such sources.  Coalesced reads of the transposed copies aT / LT.
     const int nsrc = TC_M / p.DP;
-    const int nbc = per * TC_NC;
-    float* sP1 = reinterpret_cast<float*>(smem_raw + TC_BSTAGES * B_BYTES + 256);
+    const int nbc = p.share * TC_SR;
+    float* sP1 = reinterpret_cast<float*>(smem_raw + TC_BSTAGES * ST_BYTES + 256);
     float* sP2 = sP1 + (size_t)nsrc * nbc;
-    for (int idx = threadIdx.x; idx < nsrc * nbc; idx += blockDim.x) {
-        const int src = idx / nbc, bl = idx - src * nbc;
-        const int b = c_begin * TC_NC + bl;
-        const int n0 = ntile * TC_M + src * p.DP;
-        float v1 = 0.f, v2 = 0.f;
-        if (b < p.B && bl < nit * TC_NC) {
-            if (n0 < p.n_bil_rows) {
-                const int i = n0 / p.DP;
-                if (i < p.d) { v1 = p.aT[(size_t)i * p.B + b]; v2 = p.LT[(size_t)i * p.B + b]; }
-            } else if (n0 < p.n_rows_total) {
-                v1 = 1.f;
-                v2 = p.sc[(size_t)b * SC_N + ((n0 - p.n_bil_rows) / p.DP == 0 ? SC_G2 : SC_G1)];
+    {
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int off = 0;                                        // example offset of the segment inside the staging area
+        while (si.next(sg)) {
+            const int ne = (sg.u1 - sg.u0) * TC_SR;
+            for (int idx = threadIdx.x; idx < nsrc * ne; idx += blockDim.x) {
+                const int src = idx / ne, bl = idx - src * ne;
+                const int b = sg.u0 * TC_SR + bl;
+                const int n0 = sg.tile * TC_M + src * p.DP;
+                float v1 = 0.f, v2 = 0.f;
+                if (b < p.B) {
+                    if (n0 < p.n_bil_rows) {
+                        const int i = n0 / p.DP;
+                        if (i < p.d) { v1 = p.aT[(size_t)i * p.B + b]; v2 = p.LT[(size_t)i * p.B + b]; }
+                    } else if (n0 < p.n_rows_total) {
+                        v1 = 1.f;
+                        v2 = p.sc[(size_t)b * SC_N + ((n0 - p.n_bil_rows) / p.DP == 0 ? SC_G2 : SC_G1)];
+                    }
+                }
+                sP1[(size_t)src * nbc + off + bl] = v1;
+                sP2[(size_t)src * nbc + off + bl] = v2;
             }
+            off += ne;
         }
-        sP1[idx] = v1;
-        sP2[idx] = v2;
     }
-    if (threadIdx.x == 0) TC_TRACE(52);
     uint32_t tmem_base;
-    const BwdBars br = bwd_setup(smem_raw, B_BYTES, warp, tmem_base, cs);  // __syncthreads inside: staging visible
-    if (threadIdx.x == 0) TC_TRACE(53);
+    const BwdBars br = bwd_setup(smem_raw, ST_BYTES, warp, tmem_base);  // __syncthreads inside: staging visible
+    if (threadIdx.x == 0) TC_TRACE(33);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     }
     if (warp == 0) {
-        if (lane == 0) bwd_producer(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), B_BYTES, c_begin, nit, cs, crank);
+        if (lane == 0) {
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0;
+            while (si.next(sg)) {
+                bwd_produce(br, smB, reinterpret_cast<const uint8_t*>(p.pop3), ST_BYTES, sg.u0, sg.u1 - sg.u0, it);
+                it += sg.u1 - sg.u0;
+            }
+        }
     } else if (warp == 1) {
-        if (nit > 0) bwd_mma(br, smB, B_BYTES, p.NK, tmem_base, nit, 100, cs, p.nacc);
-    } else if (warp >= 4) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
-        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;
-        const int row = q4 * 32 + lane;
-        const int n = ntile * TC_M + row;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        // decode the row once: g(b) = P1(b) * X(b) + P2(b) * Y(b)
-        int type = -1, i = 0, j = 0;          // -1: padding row (zero)
-        if (n < p.n_bil_rows) {
-            i = n / p.DP; j = n - i * p.DP;
-            if (i < p.d && j < p.d) type = 0;
-        } else if (n < p.n_rows_total) {
-            const int m = n - p.n_bil_rows;
-            const int which = m / p.DP;
-            j = m - which * p.DP;
-            if (j < p.d) type = 1 + which;
-        }
-        const size_t estride = (size_t)E_NV * p.dp;
-        int oX = 0, oY = 0;
-        if (type == 0) { oX = E_R * p.dp + j; oY = E_Y2 * p.dp + j; }
-        else if (type == 1) { oX = E_A * p.dp + j; oY = E_L * p.dp + j; }
-        else if (type == 2) { oX = E_CV * p.dp + j; oY = E_R * p.dp + j; }
-        const int src = q4 / (p.DP >> 5);
-        const float* s1 = sP1 + (size_t)src * nbc + 8 * cg;
-        const float* s2 = sP2 + (size_t)src * nbc + 8 * cg;
-        // the 16 per-lane loads of chunk it+1 are issued before chunk it is generated and published (register double
-        // buffer): the generator loop no longer pays a global-memory latency per chunk
-        auto load = [&](int it, float (&x)[8], float (&y)[8]) {
-            const int b0 = (c_begin + it) * TC_NC + 8 * cg;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float* evb = p.ev + (size_t)min(b0 + u, p.B - 1) * estride;
-                x[u] = evb[oX];
-                y[u] = evb[oY];
-            }
-        };
-        auto process = [&](int it, const float (&x)[8], const float (&y)[8]) {
-            const int as = it % TC_ASTAGES;
-            const uint32_t aph = (it / TC_ASTAGES) & 1;
-            const int b0 = (c_begin + it) * TC_NC + 8 * cg;
-            const float4 pa = *reinterpret_cast<const float4*>(s1 + it * TC_NC), pb = *reinterpret_cast<const float4*>(s1 + it * TC_NC + 4);
-            const float4 qa = *reinterpret_cast<const float4*>(s2 + it * TC_NC), qb = *reinterpret_cast<const float4*>(s2 + it * TC_NC + 4);
-            const float p1[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-            const float p2[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            float g[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], x[u], p2[u] * y[u]) : 0.f;
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(100 + 2 * it);      // (slots >= 64 are dropped: dq owns 36..47 now)
-            mbar_wait(&br.a_empty[as], aph ^ 1);
-            tc_fence_after();
-            bwd_publish(br, lane_base, as, cg, g, lane);
-            if (gw == 0 && lane == 0 && it < 4) TC_TRACE(101 + 2 * it);
-        };
-        float xa[8], ya[8], xb[8], yb[8];
-        if (nit > 0) load(0, xa, ya);
-        for (int it = 0; it < nit; it += 2) {
-            if (it + 1 < nit) load(it + 1, xb, yb);
-            process(it, xa, ya);
-            if (it + 1 < nit) {
-                if (it + 2 < nit) load(it + 2, xa, ya);
-                process(it + 1, xb, yb);
-            }
-        }
-        if (gw == 0 && lane == 0) TC_TRACE(55);
-        if (gw < 4) {
-            if (nit > 0) {
-                mbar_wait(br.acc_full, 0);
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0;
+        while (si.next(sg)) {
+            if (seg > 0) {                                   // the previous segment's accumulators have been drained
+                mbar_wait(br.acc_empty, (seg - 1) & 1);
                 tc_fence_after();
             }
-            // destination inside the split's block: units are [bilinear rows i][C1][C2], each [d][K]
-            size_t off = 0;
-            if (type == 0) off = ((size_t)i * p.d + j) * p.K;
-            else if (type > 0) off = ((size_t)((p.hasM ? p.d : 0) + (type - 1)) * p.d + j) * p.K;
-            float* o = p.out + (size_t)split * p.split_stride + off;
-            for (int c0 = 0; c0 < p.NK; c0 += 32) {
-                float t[32];
-                if (nit > 0) {
+            bwd_mma_segment<NAS>(br, smB, ST_BYTES, p.NK, tmem_base, sg.u1 - sg.u0, it, p.nacc, 32);
+            it += sg.u1 - sg.u0;
+            ++seg;
+        }
+        if (lane == 0) TC_TRACE(35);
+    } else if (warp >= 4) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;     // lane quarter; examples 16 cg .. 16 cg + 15 of a stage
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const size_t estride = (size_t)E_NV * p.dp;
+        const int src = q4 / (p.DP >> 5);
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0, off = 0;
+        while (si.next(sg)) {
+            const int n = sg.tile * TC_M + row;
+            // decode the row once: g(b) = P1(b) * X(b) + P2(b) * Y(b)
+            int type = -1, i = 0, j = 0;          // -1: padding row (zero)
+            if (n < p.n_bil_rows) {
+                i = n / p.DP; j = n - i * p.DP;
+                if (i < p.d && j < p.d) type = 0;
+            } else if (n < p.n_rows_total) {
+                const int m = n - p.n_bil_rows;
+                const int which = m / p.DP;
+                j = m - which * p.DP;
+                if (j < p.d) type = 1 + which;
+            }
+            int oX = 0, oY = 0;
+            if (type == 0) { oX = E_R * p.dp + j; oY = E_Y2 * p.dp + j; }
+            else if (type == 1) { oX = E_A * p.dp + j; oY = E_L * p.dp + j; }
+            else if (type == 2) { oX = E_CV * p.dp + j; oY = E_R * p.dp + j; }
+            const float* s1 = sP1 + (size_t)src * nbc + off + 16 * cg;
+            const float* s2 = sP2 + (size_t)src * nbc + off + 16 * cg;
+            const int nst = sg.u1 - sg.u0, nh = 2 * nst;
+            const int e0 = sg.u0 * TC_SR + 16 * cg;              // first example of this thread in the segment's first stage
+            // Half-stage software pipeline: the 16 per-lane loads of half hh+1 are issued before half hh is generated
+            // (register double buffer), so the generator loop does not pay a memory latency per hand-off.
+            auto load = [&](int hh, float (&x)[8], float (&y)[8]) {
+                const int b0 = e0 + (hh >> 1) * TC_SR + 8 * (hh & 1);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float* evb = p.ev + (size_t)min(b0 + u, p.B - 1) * estride;
+                    x[u] = evb[oX];
+                    y[u] = evb[oY];
+                }
+            };
+            auto process = [&](int hh, const float (&x)[8], const float (&y)[8]) {
+                const int lt = hh >> 1, git = it + lt, as = git % NAS, half = hh & 1;
+                const int b0 = e0 + lt * TC_SR + 8 * half;
+                const float* q1 = s1 + lt * TC_SR + 8 * half;
+                const float* q2 = s2 + lt * TC_SR + 8 * half;
+                const float4 pa = *reinterpret_cast<const float4*>(q1), pb = *reinterpret_cast<const float4*>(q1 + 4);
+                const float4 qa = *reinterpret_cast<const float4*>(q2), qb = *reinterpret_cast<const float4*>(q2 + 4);
+                const float p1[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                const float p2[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                float g[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) g[u] = (type >= 0 && b0 + u < p.B) ? fmaf(p1[u], x[u], p2[u] * y[u]) : 0.f;
+                const bool tr = gw == 0 && lane == 0 && git == 8;
+                if (half == 0) {
+                    if (tr) TC_TRACE(40);
+                    mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
+                    tc_fence_after();
+                    if (tr) TC_TRACE(41);
+                }
+                bwd_store8(lane_base, as, 16 * cg + 8 * half, g);
+                if (half == 1) {
+                    bwd_publish(br, as, lane);
+                    if (tr) TC_TRACE(42);
+                }
+            };
+            float xa[8], ya[8], xb[8], yb[8];
+            load(0, xa, ya);
+            for (int hh = 0; hh < nh; hh += 2) {          // nh is even
+                load(hh + 1, xb, yb);
+                process(hh, xa, ya);
+                if (hh + 2 < nh) load(hh + 2, xa, ya);
+                process(hh + 1, xb, yb);
+            }
+            it += nst;
+            off += nst * TC_SR;
+            if (gw < 4) {
+                mbar_wait(br.acc_full, seg & 1);
+                tc_fence_after();
+                // destination inside the slot's block: units are [bilinear rows i][C1][C2], each [d][K]
+                size_t o_off = 0;
+                if (type == 0) o_off = ((size_t)i * p.d + j) * p.K;
+                else if (type > 0) o_off = ((size_t)((p.hasM ? p.d : 0) + (type - 1)) * p.d + j) * p.K;
+                float* o = p.out + (size_t)sg.slot * p.split_stride + o_off;
+                for (int c0 = 0; c0 < p.NK; c0 += 32) {
+                    float t[32];
                     tc_ld32(lane_base + (uint32_t)c0, t);
-                    if (p.nacc == 2 && nit > 1) {            // odd chunks went to the second accumulator
+                    if (p.nacc == 2 && nst > 1) {            // odd stages went to the second accumulator
                         float t2[32];
                         tc_ld32(lane_base + TC_BWD_ACC2 + (uint32_t)c0, t2);
 #pragma unroll
                         for (int x = 0; x < 32; ++x) t[x] += t2[x];
                     }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) t[x] = 0.f;
+                    if (type >= 0) store_row32(o + c0, t, p.K - c0, (p.K & 3) == 0);
                 }
-                if (type >= 0) store_row32(o + c0, t, p.K - c0, (p.K & 3) == 0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(br.acc_empty);
             }
+            ++seg;
         }
+        if (gw == 0 && lane == 0) TC_TRACE(36);
     }
     tc_fence_before();
     __syncthreads();
-    if (cs > 1) cluster_sync_all();
-    if (threadIdx.x == 0) TC_TRACE(54);
+    if (threadIdx.x == 0) TC_TRACE(37);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1138,21 +1104,22 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
 // per-example finishing of the backward (one warp per example): SP terms of dL/dR, dq += entropy term, softmax backward
 __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
                                                        const float* __restrict__ logq, const float* __restrict__ dqp, float* __restrict__ dz,
-                                                       float* __restrict__ dzsum_part, int B, int K, int NK, int NS, int d, int dp,
+                                                       float* __restrict__ dzsum_part, int B, int K, int NK, TcSched sch_dq, int d, int dp,
                                                        int hasSP, float ent_coef, const float* __restrict__ vg, const float* __restrict__ wp,
-                                                       int tcDP, int tcNS) {
+                                                       int tcDP, TcSched sch_rec) {
     extern __shared__ float dzs[];     // [8][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * 8 + warp;
     if (b < B) {
         float* evb = ev + (size_t)b * E_NV * dp;
+        const int ns_vw = tcs_nslots(sch_rec, b >> 7), ns_dq = tcs_nslots(sch_dq, b >> 7);   // partial slots of this example's tile
         {
             // d cost / d L = M c (+ SP term), d cost / d R = M^T a (+ SP term): the recompute pass left M c and M^T a in
             // the contraction's partial buffers
             const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
             for (int j = lane; j < d; j += 32) {
                 float ga1, ga2;
-                tc_combined_vw(vg, wp, B, dp, tcDP, tcNS, b, j, ga1, ga2);
+                tc_combined_vw(vg, wp, B, dp, tcDP, ns_vw, b, j, ga1, ga2);
                 if (hasSP) {
                     ga1 = fmaf(gp + g2, evb[E_C1 * dp + j], ga1);
                     ga2 = fmaf(gp + g1, evb[E_C2 * dp + j], ga2);
@@ -1164,7 +1131,7 @@ __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, c
         float dot = 0.f;
         for (int k = lane; k < K; k += 32) {
             float v = 0.f;
-            for (int s = 0; s < NS; ++s) v += dqp[((size_t)s * B + b) * NK + k];
+            for (int s = 0; s < ns_dq; ++s) v += dqp[((size_t)s * B + b) * NK + k];
             v = fmaf(ent_coef, logq[(size_t)b * K + k] + 1.f, v);
             dzs[warp * K + k] = v;
             dot = fmaf(q[(size_t)b * K + k], v, dot);
@@ -1197,6 +1164,47 @@ extern "C" int rae_debug_set_trace(unsigned long long* dev_buf) {
 namespace {
 #endif
 
+// balanced schedule of T = ntile * upt units: one CTA per SM, or whole waves of CTAs when a CTA's share would exceed
+// `max_share` units (accuracy bound on the MMA chain of one accumulator / capacity of a staging area)
+TcSched make_sched(int ntile, int upt, int num_sms, int max_share) {
+    TcSched s;
+    s.ntile = ntile; s.upt = upt;
+    const long long T = (long long)ntile * upt;
+    long long G = std::min<long long>(T, num_sms);
+    if (max_share > 0 && (T + G - 1) / G > max_share) {
+        const long long waves = (T + (long long)num_sms * max_share - 1) / ((long long)num_sms * max_share);
+        G = std::min<long long>(T, waves * num_sms);
+    }
+    s.G = (int)std::max<long long>(G, 1);
+    return s;
+}
+int sched_max_slots(TcSched s) {
+    int m = 1;
+    for (int t = 0; t < s.ntile; ++t) m = std::max(m, tcs_nslots(s, t));
+    return m;
+}
+int sched_max_share(TcSched s) {
+    const long long T = (long long)s.ntile * s.upt;
+    return (int)((T + s.G - 1) / s.G);
+}
+
+}  // namespace
+
+// L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev
+namespace {
+__global__ void __launch_bounds__(256) k_tc_gather_lr(const float* __restrict__ A, const int32_t* __restrict__ a1,
+                                                      const int32_t* __restrict__ a2, int B, int d, int dp, int quirk,
+                                                      float* __restrict__ ev) {
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const int r1 = a1[b], r2 = quirk ? r1 : a2[b];
+    float* o = ev + (size_t)b * E_NV * dp;
+    for (int j = lane; j < d; j += 32) {
+        o[E_L * dp + j] = ld_nc(A + (size_t)r1 * d + j);
+        o[E_R * dp + j] = ld_nc(A + (size_t)r2 * d + j);
+    }
+}
 }  // namespace
 
 // shapes the tensor path handles: 16 < d <= 128 (padded to 32/64/128 columns per row) and K <= 104 (P operand resident
@@ -1215,56 +1223,49 @@ int tc_init(rae_engine* h) {
     t.KQ = 2 * ((h->K + 7) / 8);
     const int di = (DP == 32) ? ((h->d + 1) & ~1) : h->d;
     t.n_bil_rows = di * DP;
-    t.n_bil_chunks = t.n_bil_rows / TC_N;
-    t.n_sp_chunks = h->hasSP ? (2 * DP) / TC_N : 0;
-    t.n_rows_total = (t.n_bil_chunks + t.n_sp_chunks) * TC_N;
+    t.n_bil_half = t.n_bil_rows / TC_H;
+    t.n_sp_half = h->hasSP ? (2 * DP) / TC_H : 0;
+    t.n_rows_total = (t.n_bil_half + t.n_sp_half) * TC_H;
+    t.n_chunks_fwd = (t.n_bil_half + t.n_sp_half + 1) / 2;
+    t.n_chunks_rec = (t.n_bil_half + 1) / 2;
     t.ntile = (h->B + TC_M - 1) / TC_M;
-    int ns = h->num_sms / t.ntile;
-    const int pairs = (t.n_bil_chunks + 1) / 2;
-    if (ns > pairs) ns = pairs;
-    if (ns < 1) ns = 1;
-    t.NS = ns;
-    // cluster of consecutive example tiles sharing the streamed operand (multicast): 4, 2 or none
-    t.cs = (t.ntile % 4 == 0) ? 4 : (t.ntile % 2 == 0 ? 2 : 1);
-    if (!(h->cfg.flags & RAE_FLAG_CLUSTER_MULTICAST)) t.cs = 1;
-    if ((2 * t.KQ * TC_N * 16) % (16 * t.cs) != 0) t.cs = 1;
-    t.smem = (size_t)TC_BSTAGES * 2 * t.KQ * TC_N * 16 + 256;
-    // backward operands: NK = relations padded to a multiple of 16, reduction chunks of 32 rows
+    // forward: as many 128-row operand stages as fit (2 at K = 100: 106 KB each)
+    const size_t b_bytes = (size_t)2 * t.KQ * TC_N * 16;
+    t.fwd_stages = (int)std::min<size_t>(4, ((size_t)h->max_smem_optin - 256) / b_bytes);
+    if (t.fwd_stages < 2) return fail(h, RAE_EINVAL, "tensor path: K=%d needs %zu bytes per operand stage, two do not fit", h->K, b_bytes);
+    t.smem = (size_t)t.fwd_stages * b_bytes + 256;
+    t.sch_fwd = make_sched(t.ntile, t.n_chunks_fwd, h->num_sms, 0);
+    t.sch_rec = make_sched(t.ntile, t.n_chunks_rec, h->num_sms, 0);
+    t.slots_vw = std::max(sched_max_slots(t.sch_fwd), sched_max_slots(t.sch_rec));
+    // backward operands: NK = relations padded to a multiple of 16, reduction stages of 64 rows (two 32-row chunks)
     t.NK = (h->K + 15) & ~15;
-    t.n_chunks32 = t.n_rows_total / TC_NC;
-    t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), h->num_sms / t.ntile));
-    // accuracy bound for large batches (many example tiles leave few splits per tile): the measured-safe chain of the dq
-    // reduction is 130 chunks = 1560 MMAs into one accumulator (4.5e-6 of ||dW||_inf at the target shape)
-    t.NS2 = std::max(t.NS2, std::min(t.n_chunks32 / (DP / 32), (t.n_chunks32 + TC_DQ_MAX_CHAIN - 1) / TC_DQ_MAX_CHAIN));
-    if (const char* e = getenv("RAE_TC_DQ_SPLITS")) {          // A/B knob: reduction splits of the dq contraction
-        const int v = atoi(e);
-        if (v > 0) t.NS2 = std::max(1, std::min(t.n_chunks32 / (DP / 32), v));
-    }
-    t.smem_dq = (size_t)TC_BSTAGES * (2 * 8 * t.NK * 16) + 256;
+    const int SPR = DP >= 64 ? DP / 64 : 1;
+    const int n_st = t.n_rows_total / TC_SR;
+    // accuracy bound of the dq reduction: the measured-safe chain is 1560 MMAs into one accumulator (4.5e-6 of
+    // ||dW||_inf at the target shape); a segment never exceeds TC_DQ_MAX_STAGES stages = 1536 MMAs
+    t.sch_dq = make_sched(t.ntile, n_st / SPR, h->num_sms, std::max(1, TC_DQ_MAX_STAGES / SPR));
+    t.slots_dq = sched_max_slots(t.sch_dq);
+    const size_t st_bytes = (size_t)2 * 2 * 8 * t.NK * 16;
+    t.smem_dq = (size_t)TC_BSTAGES * st_bytes + 256;
+    if (t.smem_dq > (size_t)h->max_smem_optin) return fail(h, RAE_EINVAL, "tensor path: backward operand stages do not fit in shared memory");
     t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
-    t.n_bchunks = (h->B + TC_NC - 1) / TC_NC;
-    t.NSb = std::max(1, std::min(t.n_bchunks, h->num_sms / t.n_ntiles));
-    // accuracy bound (see TC_DC_MAX_CHAIN): at most TC_DC_MAX_CHAIN chunks per TMEM accumulator
+    t.n_bst = (h->B + TC_SR - 1) / TC_SR;
+    // dC: accuracy bound (see TC_DC_MAX_STAGES) and the capacity of the per-example scalar staging area
     t.dc_nacc = 2;
-    if (const char* e = getenv("RAE_TC_DC_ACCS")) t.dc_nacc = atoi(e) == 1 ? 1 : 2;     // A/B knob
-    t.NSb = std::max(t.NSb, (t.n_bchunks + t.dc_nacc * TC_DC_MAX_CHAIN - 1) / (t.dc_nacc * TC_DC_MAX_CHAIN));
-    if (const char* e = getenv("RAE_TC_DC_SPLITS")) {          // A/B knob: batch splits of the dC contraction
-        const int v = atoi(e);
-        if (v > 0) t.NSb = std::max(1, std::min(t.n_bchunks, v));
-    }
-    for (;;) {
-        const int per = (t.n_bchunks + t.NSb - 1) / t.NSb;       // batch chunks per CTA of the dC kernel
-        t.smem_dc = t.smem_dq + (size_t)(TC_M / DP) * 2 * per * TC_NC * sizeof(float);
-        if (t.smem_dc <= (size_t)h->max_smem_optin || t.NSb >= t.n_bchunks) break;
-        t.NSb = std::min(t.n_bchunks, t.NSb * 2);               // large batches: more batch splits, smaller staging area
-    }
+    const size_t per_stage = (size_t)(TC_M / DP) * 2 * TC_SR * sizeof(float);
+    const int cap = (int)(((size_t)h->max_smem_optin - t.smem_dq) / per_stage);
+    if (cap < 1) return fail(h, RAE_EINVAL, "tensor path: no shared memory left for the dC staging area");
+    t.sch_dc = make_sched(t.n_ntiles, t.n_bst, h->num_sms, std::min(t.dc_nacc * TC_DC_MAX_STAGES, cap));
+    t.dc_share = sched_max_share(t.sch_dc);
+    t.slots_dc = sched_max_slots(t.sch_dc);
+    t.smem_dc = t.smem_dq + (size_t)t.dc_share * per_stage;
     cudaError_t e;
-    if ((e = cudaMalloc((void**)&t.bop, (size_t)(t.n_bil_chunks + t.n_sp_chunks) * 2 * t.KQ * TC_N * 16)) != cudaSuccess ||
+    if ((e = cudaMalloc((void**)&t.bop, (size_t)t.n_chunks_fwd * b_bytes)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.vg, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.wp, (size_t)2 * t.NS * h->B * h->dp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.bop2, (size_t)t.n_chunks32 * 2 * 8 * t.NK * 16)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.dqp, (size_t)t.NS2 * h->B * t.NK * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bchunks * 2 * 8 * t.NK * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.wp, (size_t)2 * t.slots_vw * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.bop2, (size_t)n_st * st_bytes)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.dqp, (size_t)t.slots_dq * h->B * t.NK * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bst * st_bytes)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.aT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.LT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess)
         return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
@@ -1289,21 +1290,22 @@ void tc_free(rae_engine* h) {
 // pre-split / pre-arrange the dense operands (call whenever C, C1, C2 changed, i.e. once per step)
 int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    const size_t total = (size_t)t.n_rows_total * t.KQ;
+    const size_t total = (size_t)t.n_chunks_fwd * TC_N * t.KQ;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
-                                                 t.n_rows_total, t.bop, t.NK, t.bop2);
+                                                 t.n_chunks_fwd * TC_N, t.bop, t.NK, t.n_rows_total, t.bop2);
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-// q-dependent operand of the dC contraction (after the encoder)
+// q-dependent operand of the dC contraction (after the encoder) + L / R gather
 int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st) {
     TcState& t = h->tc;
-    const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
+    const int nbc = 2 * t.n_bst;
+    const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<dim3(blocks3, 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
+    k_tc_prep_qt<<<dim3(blocks3, 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
                                                    h->quirk ? 1 : 0, h->ev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
@@ -1313,62 +1315,37 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
 // the q-dependent operand alone (only the dC contraction at the end of the step needs it: prepared off the critical path)
 int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    const size_t total3 = (size_t)t.n_bchunks * 8 * t.NK;
+    const int nbc = 2 * t.n_bst;
+    const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
+    k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
                                                    h->quirk ? 1 : 0, h->ev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-// one contraction pass: (slotL, slotR) in -> (slotV = M R [+SP rows to E_C1/E_C2 when with_sp], slotW = M^T L) out
-int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st) {
+// one contraction pass: (slotL, slotR) in -> v = M R (per-group partials in vg) [+ SP rows to E_C1/E_C2 when with_sp],
+// w = M^T L (per-slot partials in wp); k_score (forward) and k_tc_bwd_finish (backward) read the partial buffers directly
+int tc_contract(rae_engine* h, int slotL, int slotR, bool with_sp, cudaStream_t st) {
     TcState& t = h->tc;
     TcArgs p{};
     p.q = h->q; p.bop = t.bop; p.ev = h->ev; p.ev_out = h->ev; p.vg = t.vg; p.wp = t.wp;
     p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
-    p.n_bil_chunks = t.n_bil_chunks; p.n_sp_chunks = with_sp ? t.n_sp_chunks : 0; p.NS = t.NS;
-    const int grid = t.ntile * t.NS;
-    p.ntile = t.ntile;
-    p.cs = t.cs;
-    {
-        static int dbg = -1;
-        if (dbg < 0) {
-            const char* e = getenv("RAE_TC_DEBUG");
-            dbg = e ? atoi(e) : 0;
-            cudaMemcpyToSymbol(g_tc_bwd_dbg, &dbg, sizeof(int));
-        }
-        p.dbg = dbg;
-    }
-    {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TC_FWD_THREADS);
-        cfg.dynamicSmemBytes = t.smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)t.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = t.cs > 1 ? 1 : 0;
-        cudaError_t e;
-        if (t.DP == 32) e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<32>, p);
-        else if (t.DP == 64) e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<64>, p);
-        else e = cudaLaunchKernelEx(&cfg, k_tc_bilinear<128>, p);
-        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_bilinear launch (cluster %d): %s", t.cs, cudaGetErrorString(e));
-    }
-    // no combine pass: k_score (forward) and k_tc_bwd_finish (backward) read the partial buffers directly
-    (void)slotV; (void)slotW;
+    p.n_bil_half = t.n_bil_half; p.n_sp_half = with_sp ? t.n_sp_half : 0;
+    p.nbs = t.fwd_stages;
+    p.sch = with_sp ? t.sch_fwd : t.sch_rec;
+    if (t.DP == 32) k_tc_bilinear<32><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
+    else if (t.DP == 64) k_tc_bilinear<64><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
+    else k_tc_bilinear<128><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-// backward on the tensor path: dL, dR (through the forward kernel with L := a, R := c), dq, softmax backward -> dz
 // backward on the tensor path, three parts (separately timed phases): (1) M c and M^T a through the forward kernel with
 // L := a, R := c; (2) dq contraction; (3) per-example finish: dL, dR, entropy term, softmax backward -> dz
-int tc_backward_recompute(rae_engine* h, cudaStream_t st) { return tc_contract(h, E_A, E_CV, E_GA1, E_GA2, false, st); }
+int tc_backward_recompute(rae_engine* h, cudaStream_t st) { return tc_contract(h, E_A, E_CV, false, st); }
 
 int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
@@ -1376,27 +1353,11 @@ int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     TcDqArgs p{};
     p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.dqp = t.dqp;
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
-    p.n_bil_rows = t.n_bil_rows; p.n_chunks32 = t.n_chunks32; p.NS = t.NS2;
-    const int grid = t.ntile * t.NS2;
-    p.cs = ((2 * 8 * t.NK * 16) % (16 * t.cs) == 0) ? t.cs : 1;
-    p.ntile = t.ntile;
-    {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TC_BWD_THREADS);
-        cfg.dynamicSmemBytes = t.smem_dq;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = p.cs > 1 ? 1 : 0;
-        cudaError_t e;
-        if (t.DP == 32) e = cudaLaunchKernelEx(&cfg, k_tc_dq<32>, p);
-        else if (t.DP == 64) e = cudaLaunchKernelEx(&cfg, k_tc_dq<64>, p);
-        else e = cudaLaunchKernelEx(&cfg, k_tc_dq<128>, p);
-        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_dq launch (cluster %d): %s", p.cs, cudaGetErrorString(e));
-    }
+    p.n_bil_rows = t.n_bil_rows;
+    p.sch = t.sch_dq;
+    if (t.DP == 32) k_tc_dq<32><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    else if (t.DP == 64) k_tc_dq<64><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    else k_tc_dq<128><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1408,40 +1369,25 @@ int tc_backward_finish(rae_engine* h, cudaStream_t st) {
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
     k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
-                                                                  t.NK, t.NS2, h->d, h->dp, h->hasSP ? 1 : 0,
-                                                                  (float)(2.0 * h->cfg.alpha / h->Z), t.vg, t.wp, t.DP, t.NS);
+                                                                  t.NK, t.sch_dq, h->d, h->dp, h->hasSP ? 1 : 0,
+                                                                  (float)(2.0 * h->cfg.alpha / h->Z), t.vg, t.wp, t.DP, t.sch_rec);
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-// dC, dC1, dC2 partials on the tensor path (k_dense_finalize sums the NSb batch splits)
+// dC, dC1, dC2 partials on the tensor path (k_dense_finalize sums the slots of every row tile)
 int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     TcDcArgs p{};
     p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
-    p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.n_bchunks = t.n_bchunks; p.NSb = t.NSb; p.hasM = h->hasM ? 1 : 0;
+    p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.hasM = h->hasM ? 1 : 0;
     p.nacc = t.dc_nacc;
+    p.share = t.dc_share;
     p.split_stride = (size_t)h->off_gWb;
-    {
-        int cs = (h->cfg.flags & RAE_FLAG_CLUSTER_MULTICAST) ? 4 : 1;
-        while (cs > 1 && (2 * 8 * t.NK * 16) % (16 * cs) != 0) cs >>= 1;
-        p.cs = cs;
-        p.n_ntiles_pad = (t.n_ntiles + cs - 1) / cs * cs;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(p.n_ntiles_pad * t.NSb);
-        cfg.blockDim = dim3(TC_BWD_THREADS);
-        cfg.dynamicSmemBytes = t.smem_dc;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = cs > 1 ? 1 : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_tc_dc, p);
-        if (e != cudaSuccess) return fail(h, RAE_ECUDA, "k_tc_dc launch (cluster %d): %s", cs, cudaGetErrorString(e));
-    }
+    p.sch = t.sch_dc;
+    k_tc_dc<<<p.sch.G, TC_BWD_THREADS, t.smem_dc, st>>>(p);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

@@ -102,14 +102,9 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     // while the caller's stream carries encoder -> decoder -> dense gradients -> cost -> dense update.
     // Disabled when gradients are emitted densely (debug / regulariser) or per-phase profiling is on.
     const bool overlap = !h->dense_w && !h->debug_dense && !h->profiling && h->s1 != nullptr;
-    // RAE_SIDE_PREP=1 moves the q^T operand + L/R gather to the side stream.  Measured on B200: 13 us SLOWER per step at
-    // both bench shapes (the two extra cross-stream event edges cost more than the 6 us kernel they hide) -> off by default.
-    static int side_prep = -1;
-    if (side_prep < 0) { const char* e = getenv("RAE_SIDE_PREP"); side_prep = e ? atoi(e) : 0; }
-    const bool sprep = overlap && h->use_tc && side_prep != 0;
-    static int prepc_main = -1;      // RAE_PREPC_MAIN=1: dense-operand prep on the main stream (A/B measurement)
-    if (prepc_main < 0) { const char* e = getenv("RAE_PREPC_MAIN"); prepc_main = e ? atoi(e) : 0; }
-    const bool prepc_side = overlap && h->use_tc && prepc_main == 0;
+    // The dense-operand preparation depends only on the parameters: it runs beside the encoder on side stream 2.  (Moving
+    // the q^T operand / L, R gather there as well was measured 13 us SLOWER per step: two more cross-stream edges.)
+    const bool prepc_side = overlap && h->use_tc;
     cudaStream_t se = overlap ? h->s1 : st, sw = overlap ? h->s2 : st;
     const int64_t n_occ = (int64_t)(2 + 2 * h->S) * h->B;
     if (overlap) {
@@ -119,23 +114,13 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
             // the pre-split dense operands depend only on the parameters: prepared beside the encoder
             RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork0, 0));
             if ((rc = tc_prepare_c(h, h->s2))) return rc;
-            // L = A[a1], R = A[a2] depend on the ids only (multi-GPU: the compact A is still being fetched -> later, main stream)
-            if (sprep && !h->pending_wait && (rc = tc_gather_lr(h, a1, a2, h->s2))) return rc;
             RAE_CUDA(h, cudaEventRecord(h->ev_prepc, h->s2));
         }
         if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
         if ((rc = sort_pairs(h, h->ent, n_occ, se, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
     }
     RAE_PHASE();   // 0 encoder forward: q, log q, entropy
-    const bool lr_on_main = sprep && h->pending_wait != nullptr;
     if ((rc = launch_encoder_forward(h, indptr, indices, h->B, h->q, h->logq, h->sc + SC_ENT, nullptr, st))) return rc;
-    if (sprep) {
-        // the q^T operand of the dC contraction: prepared beside the forward pass, needed at the end of the step
-        RAE_CUDA(h, cudaEventRecord(h->ev_q, st));
-        RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_q, 0));
-        if ((rc = tc_prepare_qt(h, h->s2))) return rc;
-        RAE_CUDA(h, cudaEventRecord(h->ev_qt, h->s2));
-    }
     RAE_PHASE();   // 1 entity occurrence keys -> stable sort -> segments (depends on the indices only)
     if (!overlap) {
         if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
@@ -157,15 +142,11 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     if (h->use_tc) {
         if (prepc_side) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
         else if ((rc = tc_prepare_c(h, st))) return rc;
-        if (sprep) {
-            if (lr_on_main && (rc = tc_gather_lr(h, a1, a2, st))) return rc;
-        } else if ((rc = tc_prepare_p(h, a1, a2, st))) {
-            return rc;
-        }
+        if ((rc = tc_prepare_p(h, a1, a2, st))) return rc;
     }
     RAE_PHASE();   // 4 forward contraction: v = M R, w = M^T L, c1, c2
     if (h->use_tc) {
-        if ((rc = tc_contract(h, E_L, E_R, E_V1, E_V2, true, st))) return rc;
+        if ((rc = tc_contract(h, E_L, E_R, true, st))) return rc;
     } else {
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
     }
@@ -211,7 +192,6 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 11 dense-parameter gradients: dC contraction
     if (h->use_tc) {
-        if (sprep) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_qt, 0));
         if ((rc = tc_grad_dense(h, st))) return rc;
     } else {
         if ((rc = launch_grad_dense_simt(h, st))) return rc;
@@ -472,7 +452,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
         const int max_by_batch = (h->B + 63) / 64;
         if (ns > max_by_batch) ns = max_by_batch;
         if (ns < 1) ns = 1;
-        if (h->use_tc) ns = h->tc.NSb;      // the tensor path splits the batch its own way
+        if (h->use_tc) ns = h->tc.slots_dc;  // the tensor path deals the batch over slots its own way
         h->gC_nsplit = ns;
         RAE_CREATE_RC(dev_alloc(h, &h->gC_part, (size_t)ns * (size_t)(dd + 2 * dk)));
     }

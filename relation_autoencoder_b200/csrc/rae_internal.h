@@ -60,22 +60,47 @@ struct FeatureCache {
     bool valid = false;
 };
 
+// Balanced schedule of the tensor-core contractions (rae_decoder_tc.cu).  The work of a contraction is `ntile` tiles of
+// `upt` units each (a unit = one streamed operand chunk / pipeline stage); the T = ntile * upt units are dealt over G
+// CTAs in contiguous ranges [start(x), start(x+1)), start(x) = floor(x T / G), so every SM gets the same number of
+// MMAs whatever the tile count.  A range is cut at tile boundaries into segments; the segment of CTA x inside tile t
+// writes its partial result into slot x - first_cta(t).  G <= T, so every CTA owns at least one unit and the CTAs that
+// overlap a tile are consecutive.  G == 0 marks the rectangular layout of the SIMT path (`upt` = uniform slot count).
+struct TcSched { int G, upt, ntile; };
+__host__ __device__ __forceinline__ long long tcs_start(TcSched s, int x) { return (long long)x * s.upt * s.ntile / s.G; }
+// the CTA whose range holds unit u: the largest x with floor(x T / G) <= u
+__host__ __device__ __forceinline__ int tcs_cta_of(TcSched s, long long u) {
+    const long long T = (long long)s.upt * s.ntile;
+    return (int)(((u + 1) * s.G + T - 1) / T) - 1;
+}
+__host__ __device__ __forceinline__ int tcs_first(TcSched s, int tile) { return tcs_cta_of(s, (long long)tile * s.upt); }
+__host__ __device__ __forceinline__ int tcs_nslots(TcSched s, int tile) {
+    if (s.G == 0) return s.upt;
+    return tcs_cta_of(s, (long long)(tile + 1) * s.upt - 1) - tcs_first(s, tile) + 1;
+}
+
 // tensor-core (tcgen05) contraction path state (rae_decoder_tc.cu)
 struct TcState {
     bool ready = false;
     int DP = 0;            // columns per row of M, padded: 32 / 64 / 128
     int KQ = 0;            // float4 planes along the relation axis (K padded to a multiple of 8, / 4)
-    int n_bil_rows = 0, n_bil_chunks = 0, n_sp_chunks = 0, n_rows_total = 0;
-    int ntile = 0, NS = 0, cs = 1;
+    // operand rows n of Cf = [C rows (i, j) | C1 rows | C2 rows] in half chunks of 64 rows
+    int n_bil_rows = 0, n_bil_half = 0, n_sp_half = 0;
+    int n_rows_total = 0;  // (n_bil_half + n_sp_half) * 64: reduction length of dq, operand rows of dC
+    int n_chunks_fwd = 0;  // 128-row chunks of the forward pass (bilinear + C1/C2 rows, padded to a whole chunk)
+    int n_chunks_rec = 0;  // 128-row chunks of the backward recompute pass (bilinear rows only)
+    int ntile = 0;         // example tiles of 128
+    int fwd_stages = 2;    // B-operand shared-memory stages of the forward kernel
     size_t smem = 0;
-    float4* pop = nullptr; // P operand tiles  [tile][hi/lo][KQ][128]
-    float4* bop = nullptr; // B operand chunks [chunk][hi/lo][KQ][64]
+    TcSched sch_fwd{}, sch_rec{}, sch_dq{}, sch_dc{};
+    int slots_vw = 0, slots_dq = 0, slots_dc = 0;   // partial-result slots per tile (maximum over tiles)
+    float4* bop = nullptr; // forward B operand chunks [chunk][hi/lo][KQ][128]
     float* vg = nullptr;   // [2][B][dp]
-    float* wp = nullptr;   // [NS][2][B][dp]
-    int NK = 0, n_chunks32 = 0, NS2 = 0; size_t smem_dq = 0, smem_dc = 0;
+    float* wp = nullptr;   // [slots_vw][2][B][dp]
+    int NK = 0; size_t smem_dq = 0, smem_dc = 0;
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
-    float* dqp = nullptr;   // [NS2][B][NK]
-    int n_ntiles = 0, n_bchunks = 0, NSb = 0, dc_nacc = 2;
+    float* dqp = nullptr;   // [slots_dq][B][NK]
+    int n_ntiles = 0, n_bst = 0, dc_nacc = 2, dc_share = 0;   // dC: 128-row tiles, 64-example stages, accumulators, stages per CTA
     float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
     float* aT = nullptr; float* LT = nullptr;   // transposed a, L: [dp][B]
 };
@@ -181,7 +206,7 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st);
 int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // q^T operand + gather L, R
 int tc_prepare_qt(rae_engine* h, cudaStream_t st);                                      // q^T operand only
 int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // L, R only
-int tc_contract(rae_engine* h, int slotL, int slotR, int slotV, int slotW, bool with_sp, cudaStream_t st);
+int tc_contract(rae_engine* h, int slotL, int slotR, bool with_sp, cudaStream_t st);
 int tc_backward_recompute(rae_engine* h, cudaStream_t st);
 int tc_backward_dq(rae_engine* h, cudaStream_t st);
 int tc_backward_finish(rae_engine* h, cudaStream_t st);

@@ -557,13 +557,27 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
 // blocks [0, n_elem_blocks): 4 consecutive elements per thread (float4 when aligned), the splits summed in split order;
 // blocks [n_elem_blocks, +K): one CTA per column k of dWb - thread t sums partial rows t, t+256, ... and a fixed-shape
 // shared-memory tree combines the 256 values (deterministic).
-__global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, int nsplit, size_t n_units_elems,
+// slots of the partial buffer that hold element i0 of [C | C1 | C2]: uniform (SIMT path, sch.G == 0) or, on the tensor
+// path, the slot count of the 128-row operand tile the element's row n = (i, j) | C1 row | C2 row falls in
+struct DenseSlots { TcSched sch; int d, K, DP, n_bil_rows, hasM; };
+__device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
+    if (ds.sch.G == 0) return ds.sch.upt;
+    const int r = (int)(i0 / (size_t)ds.K);                    // row of the [units*d, K] layout
+    const int nb = ds.hasM ? ds.d * ds.d : 0;
+    int n;
+    if (r < nb) { const int i = r / ds.d; n = i * ds.DP + (r - i * ds.d); }
+    else { const int m = r - nb, which = m / ds.d; n = ds.n_bil_rows + which * ds.DP + (m - which * ds.d); }
+    return tcs_nslots(ds.sch, n >> 7);
+}
+
+__global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, DenseSlots ds, size_t n_units_elems,
                                                         const float* __restrict__ dzsum_part, int n_dz_part, int K,
                                                         float* __restrict__ out, size_t off_wb, int n_elem_blocks) {
     if ((int)blockIdx.x < n_elem_blocks) {
         const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
         if (i0 >= n_units_elems) return;
-        if ((n_units_elems & 3) == 0) {
+        if ((n_units_elems & 3) == 0 && (K & 3) == 0) {        // the 4 elements share a row
+            const int nsplit = dense_slots_of(ds, i0);
             float4 s = *reinterpret_cast<const float4*>(part + i0);
             for (int sp = 1; sp < nsplit; ++sp) {
                 const float4 x = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
@@ -572,6 +586,7 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
             *reinterpret_cast<float4*>(out + i0) = s;
         } else {
             for (size_t i = i0; i < min(i0 + 4, n_units_elems); ++i) {
+                const int nsplit = dense_slots_of(ds, i);
                 float s = 0.f;
                 for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * n_units_elems + i];
                 out[i] = s;
@@ -848,7 +863,11 @@ int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const 
 int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
     const size_t n_units = (size_t)h->off_gWb;   // elements of [C | C1 | C2]
     const int n_elem_blocks = (int)((n_units + 1023) / 1024);
-    k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, h->gC_nsplit, n_units, h->dzsum_part, h->dz_part_used, h->K,
+    DenseSlots ds{};
+    ds.sch = TcSched{0, h->gC_nsplit, 1};
+    ds.d = h->d; ds.K = h->K; ds.hasM = h->hasM ? 1 : 0;
+    if (h->use_tc) { ds.sch = h->tc.sch_dc; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows; }
+    k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, ds, n_units, h->dzsum_part, h->dz_part_used, h->K,
                                                           h->dense_grad, (size_t)h->off_gWb, n_elem_blocks);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());

@@ -7,6 +7,21 @@ import numpy as np
 from oracle import rae_oracle as O
 
 
+def tc_eligible(model, K, d):
+    """Shapes the tcgen05 contraction path takes (rae_decoder_tc.cu: tc_supported): a bilinear model, 16 < d <= 128, K <= 104."""
+    return O.MODEL_ALIASES.get(model, model) != "sp" and 16 < d <= 128 and K <= 104
+
+
+def record_err(test, name, value):
+    """Measured parity errors, appended to $RAE_PARITY_LOG (one JSON line each) so a GPU run leaves the margins behind."""
+    import json
+    import os
+    path = os.environ.get("RAE_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": test, "what": name, "err": float(value)}) + "\n")
+
+
 def make_problem(model, B=12, K=5, d=6, S=3, F=40, N=25, fbar=4, seed=0, dup_heavy=False, empty_rows=False):
     """Random tiny instance: params in reference init order + one batch with injected negatives."""
     rng = np.random.RandomState(seed)
