@@ -68,5 +68,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_trace() -> str:
+    """librae_trace.so at the repository root: the same sources with -DRAE_TRACE (in-kernel timeline of the tcgen05
+    kernels, profiles/trace_tc.py).  A measurement build: never loaded by the package."""
+    nvcc = _nvcc()
+    out = os.path.join(os.path.dirname(HERE), "librae_trace.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + ARCH + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + ["-DRAE_TRACE", "-shared", "-o", out] + srcs + ["-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("trace build failed")
+    return out
+
+
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_trace())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

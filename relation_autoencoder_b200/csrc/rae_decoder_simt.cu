@@ -790,7 +790,6 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
     p.loss_part = h->loss_part;
     p.B = h->B; p.S = h->S; p.d = h->d; p.dp = h->dp; p.hasM = h->hasM; p.hasSP = h->hasSP;
     p.invZ = (float)(1.0 / h->Z);
-    if (h->use_tc) { p.vg = h->tc.vg; p.wp = h->tc.wp; p.tcDP = h->tc.DP; p.tcSch = h->tc.sch_fwd; }
     const int blocks = (h->B + 3) / 4;
     if (blocks > h->n_loss_part) return fail(h, RAE_EINVAL, "internal: loss_part too small");
     const int dt = (h->d + 31) / 32;

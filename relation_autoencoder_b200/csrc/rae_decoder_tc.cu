@@ -50,7 +50,17 @@ __device__ unsigned long long* g_tc_trace = nullptr;
     do {                                                                                                       \
         if (tc_trace_ptr_ != nullptr && (slot) < 64) tc_trace_ptr_[(size_t)blockIdx.x * 64 + (slot)] = clock64(); \
     } while (0)
+// wall-clock stamp (ns, synchronised across SMs): kernel duration and the SM clock actually held under tensor load
+#define TC_TRACE_NS(slot)                                                                                      \
+    do {                                                                                                       \
+        if (tc_trace_ptr_ != nullptr) {                                                                        \
+            unsigned long long ns_;                                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_));                                            \
+            tc_trace_ptr_[(size_t)blockIdx.x * 64 + (slot)] = ns_;                                             \
+        }                                                                                                      \
+    } while (0)
 #else
+#define TC_TRACE_NS(slot) do { } while (0)
 #define TC_TRACE_INIT() do { } while (0)
 #define TC_TRACE(slot) do { } while (0)
 #endif
@@ -332,15 +342,19 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
 // Work unit = one 128-row chunk of Cf = two 64-row half chunks; epilogue group g (4 warps) consumes half g of EVERY chunk
 // (accumulator columns [64 g, 64 g + 64)), so for DP = 128 group g always holds the column half j in [64 g, 64 g + 64).
 // ------------------------------------------------------------------------------------------------------------
+// Every per-thread global access of the row-owning warps is COALESCED: a thread owns example row b, so the inputs come
+// from transposed copies [column][example] (lane = example -> consecutive addresses) and the outputs are written the same
+// way; k_tc_combine transposes / sums them back into the row-major per-example vectors.  (Reading ev[b][...] directly
+// costs one L1 wavefront per lane, ~66 cycles per warp instruction: measured as 2/3 of the kernel's time.)
 struct TcArgs {
-    const float* q;         // [B,K]
+    const float* qT;        // [Kp][B]  q transposed (rows >= K zero)
     const float4* bop;      // B operand chunks
-    const float* ev;        // per-example vectors (L at slotL, R at slotR), row stride E_NV*dp
-    float* ev_out;          // SP half chunks write c1 / c2 here (E_C1 / E_C2)
-    float* vg;              // [2][B][dp]   v partial per epilogue group
-    float* wp;              // [slot][2][B][dp] w partial per (segment slot, group)
+    const float* LT;        // [dp][B]  left vectors transposed  (L forward, a for the recompute pass)
+    const float* RT;        // [dp][B]  right vectors transposed (R forward, c for the recompute pass)
+    float* ev_out;          // SP half chunks write c1 / c2 here (E_C1 / E_C2), row stride E_NV*dp
+    float* vT;              // [2][dp][B]        v partial per epilogue group
+    float* wT;              // [slot][2][dp][B]  w partial per (segment slot, group)
     int B, K, d, dp, KQ;
-    int slotL, slotR;
     int n_bil_half;         // half chunks holding bilinear rows
     int n_sp_half;          // half chunks holding C1/C2 rows (forward only; 0 for the recompute pass)
     int nbs;                // B-operand shared-memory stages
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     uint64_t* t_full = b_empty + 4;                         // [TC_TSTAGES]
     uint64_t* t_empty = t_full + TC_TSTAGES;                // [TC_TSTAGES] 8 epilogue-warp arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TC_TSTAGES);
-    if (threadIdx.x == 0) TC_TRACE(0);
+    if (threadIdx.x == 0) { TC_TRACE(0); TC_TRACE_NS(14); }
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 8);
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 mbar_wait(&b_full[s], (it / nbs) & 1);
                 tc_fence_after();
                 if (lane == 0 && it == 4) TC_TRACE(6);
+                if (lane == 0 && it == 12) TC_TRACE(10);
                 if (elect_one()) {
                     const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
                     uint64_t h0 = make_desc(b_hi, TC_N * 16u, 128u);
@@ -435,6 +450,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 }
                 __syncwarp();
                 if (lane == 0 && it == 4) TC_TRACE(7);
+                if (lane == 0 && it == 12) TC_TRACE(11);
             }
             ++seg;
         }
@@ -457,21 +473,10 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 // q row -> TF32 hi / lo planes of the A operand in TMEM.  Group g converts relations [56 g, 56 g + 56): all of
                 // a thread's loads are issued before the first conversion (one memory latency).  Segments after the first:
                 // this warp has seen t_full of the previous segment's last chunk, so every MMA that read the old rows is done.
-                const float* qr = p.q + (size_t)(ok ? b : 0) * p.K;
                 const int kb = 56 * g;
                 float qh[56];
-                if ((p.K & 3) == 0) {
-                    const float4* qv = reinterpret_cast<const float4*>(qr + kb);
 #pragma unroll
-                    for (int i = 0; i < 14; ++i) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok && kb + 4 * i < p.K) v = qv[i];
-                        qh[4 * i] = v.x; qh[4 * i + 1] = v.y; qh[4 * i + 2] = v.z; qh[4 * i + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 56; ++i) qh[i] = (ok && kb + i < p.K) ? qr[kb + i] : 0.f;
-                }
+                for (int i = 0; i < 56; ++i) qh[i] = (ok && (uint32_t)(kb + i) < Kp) ? p.qT[(size_t)(kb + i) * p.B + b] : 0.f;
                 const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)kb, a_lo_col = a_hi_col + Kp;
 #pragma unroll
                 for (int c8 = 0; c8 < 7; ++c8) {
@@ -488,14 +493,14 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full);
+                if (ew == 0 && lane == 0 && it == 0) TC_TRACE(2);
             }
-            const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
             float* o = p.ev_out + (size_t)(ok ? b : 0) * E_NV * p.dp;
             float Rr[RW], Wr[RW];
 #pragma unroll
             for (int c = 0; c < RW; ++c) {
                 const int j = jbase + c;
-                Rr[c] = (ok && j < p.d) ? evb[p.slotR * p.dp + j] : 0.f;
+                Rr[c] = (ok && j < p.dp) ? p.RT[(size_t)j * p.B + b] : 0.f;
                 Wr[c] = 0.f;
             }
             for (int c = sg.u0; c < sg.u1; ++c, ++it) {
@@ -509,8 +514,8 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 int i0 = 0;
                 if (bil) {
                     i0 = (DP == 128) ? (hc >> 1) : (DP == 64 ? hc : 2 * hc);
-                    if (ok && i0 < p.d) L0 = evb[p.slotL * p.dp + i0];
-                    if (DP == 32 && ok && i0 + 1 < p.d) L1 = evb[p.slotL * p.dp + i0 + 1];
+                    if (ok && i0 < p.d) L0 = p.LT[(size_t)i0 * p.B + b];
+                    if (DP == 32 && ok && i0 + 1 < p.d) L1 = p.LT[(size_t)(i0 + 1) * p.B + b];
                 }
                 mbar_wait(&t_full[ts], tph);
                 tc_fence_after();
@@ -548,7 +553,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                                 v4[x & 3] = fmaf(t[x], Rr[x % RW], v4[x & 3]);
                                 Wr[x % RW] = fmaf(t[x], Lh, Wr[x % RW]);
                             }
-                            if (ok && i0 + hf < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0 + hf] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
+                            if (ok && i0 + hf < p.d) p.vT[((size_t)g * p.dp + i0 + hf) * p.B + b] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
                         }
                     } else if (ok) {
                         // selectional-preference rows: the accumulator row IS c1 / c2
@@ -570,22 +575,23 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                         }
                     }
                 }
-                if (DP >= 64 && bil && ok && i0 < p.d) p.vg[((size_t)g * p.B + b) * p.dp + i0] = vsum;
+                if (DP >= 64 && bil && ok && i0 < p.d) p.vT[((size_t)g * p.dp + i0) * p.B + b] = vsum;
             }
             if (ok) {
-                float* wo = p.wp + (((size_t)sg.slot * 2 + g) * p.B + b) * p.dp;      // dp % 4 == 0: 16-byte stores
+                float* wo = p.wT + ((size_t)sg.slot * 2 + g) * p.dp * p.B + b;
 #pragma unroll
-                for (int c = 0; c < RW; c += 4) {
+                for (int c = 0; c < RW; ++c) {
                     const int j = jbase + c;
-                    if (j < p.dp) *reinterpret_cast<float4*>(wo + j) = make_float4(Wr[c], Wr[c + 1], Wr[c + 2], Wr[c + 3]);
+                    if (j < p.dp) wo[(size_t)j * p.B] = Wr[c];
                 }
             }
+            if (ew == 0 && lane == 0 && it <= (sg.u1 - sg.u0)) TC_TRACE(9);     // first segment done
         }
         if (ew == 0 && lane == 0) TC_TRACE(4);
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) TC_TRACE(5);
+    if (threadIdx.x == 0) { TC_TRACE(5); TC_TRACE_NS(15); }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -611,24 +617,61 @@ constexpr uint32_t TC_BWD_ACC2 = 384;
 constexpr int TC_DC_MAX_STAGES = 16;   // stages (of 64 examples, 24 MMAs each) per accumulator: 384 MMAs
 constexpr int TC_DQ_MAX_STAGES = 64;   // dq: stages (of 64 reduction rows) per segment: 1536 MMAs; random-sign terms drift less
 
-// transposed copies aT[i][b], LT[i][b] so that lane = example reads of a_bi / L_bi are coalesced
-__global__ void __launch_bounds__(256) k_tc_transpose_al(const float* __restrict__ ev, int B, int d, int dp, float* __restrict__ aT,
-                                                         float* __restrict__ LT) {
-    __shared__ float ta[32][33], tl[32][33];
-    const int b0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+// tiled transposes: job z copies src[b * stride + c] (b < B, c < cols) to dst[c * B + b], zero rows for cols <= c < cols_out.
+// They give the contraction kernels their [column][example] views (lane = example reads are coalesced).
+struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; };
+struct TrJobs { TrJob j[4]; int B; };
+__global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
+    __shared__ float tile[32][33];
+    const TrJob jb = jobs.j[blockIdx.z];
+    const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if (c0 >= jb.cols_out) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of 32
     for (int r = ty; r < 32; r += 8) {
-        const int b = b0 + r, i = i0 + tx;
-        const bool in = b < B && i < d;
-        ta[r][tx] = in ? ev[((size_t)b * E_NV + E_A) * dp + i] : 0.f;
-        tl[r][tx] = in ? ev[((size_t)b * E_NV + E_L) * dp + i] : 0.f;
+        const int b = b0 + r, c = c0 + tx;
+        tile[r][tx] = (b < jobs.B && c < jb.cols) ? jb.src[(size_t)b * jb.stride + c] : 0.f;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
-        const int i = i0 + r, b = b0 + tx;
-        if (i < dp && b < B) {
-            aT[(size_t)i * B + b] = ta[tx][r];
-            LT[(size_t)i * B + b] = tl[tx][r];
+        const int c = c0 + r, b = b0 + tx;
+        if (c < jb.cols_out && b < jobs.B) jb.dst[(size_t)c * jobs.B + b] = tile[tx][r];
+    }
+}
+
+// v, w of a contraction pass: transposed partial buffers -> row-major per-example vectors ev[b][slotV | slotW][j]
+//   vT [2][dp][B]        DP=128: both epilogue groups hold a half-row partial; DP=64: group j%2; DP=32: group (j/2)%2
+//   wT [slot][2][dp][B]  sum over the slots of the example's tile (DP=128: only group j/64 holds column j; else both groups)
+__global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT, const float* __restrict__ wT, float* __restrict__ ev,
+                                                    int B, int d, int dp, int DP, TcSched sch, int slotV, int slotW) {
+    __shared__ float tv[32][33], tw[32][33];
+    const int b0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int ns = tcs_nslots(sch, b0 >> 7);                    // the 32 examples of a block share a 128-example tile
+    const size_t plane = (size_t)dp * B;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, b = b0 + tx;
+        float v = 0.f, w = 0.f;
+        if (j < d && b < B) {
+            const size_t idx = (size_t)j * B + b;
+            if (DP == 128) v = vT[idx] + vT[plane + idx];
+            else if (DP == 64) v = vT[(size_t)(j & 1) * plane + idx];
+            else v = vT[(size_t)((j >> 1) & 1) * plane + idx];
+            if (DP == 128) {
+                const int g = j >> 6;
+                for (int s = 0; s < ns; ++s) w += wT[(size_t)(2 * s + g) * plane + idx];
+            } else {
+                for (int s = 0; s < 2 * ns; ++s) w += wT[(size_t)s * plane + idx];
+            }
+        }
+        tv[r][tx] = v;
+        tw[r][tx] = w;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int b = b0 + r, j = j0 + tx;
+        if (b < B && j < d) {
+            ev[((size_t)b * E_NV + slotV) * dp + j] = tv[tx][r];
+            ev[((size_t)b * E_NV + slotW) * dp + j] = tw[tx][r];
         }
     }
 }
@@ -690,6 +733,7 @@ __device__ __forceinline__ void bwd_mma_segment(const BwdBars& br, uint8_t* smB,
         mbar_wait(&br.b_full[s], (git / TC_BSTAGES) & 1);
         tc_fence_after();
         if ((threadIdx.x & 31) == 0 && git == 8) TC_TRACE(trace_base + 6);
+        if ((threadIdx.x & 31) == 0 && git == 24) TC_TRACE(trace_base + 11);
         if (elect_one()) {
             const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 128u * as, a_lo = a_hi + 64u;
             const uint32_t acc = tmem_base + ((nacc == 2 && (lt & 1)) ? TC_BWD_ACC2 : 0u);
@@ -714,6 +758,7 @@ __device__ __forceinline__ void bwd_mma_segment(const BwdBars& br, uint8_t* smB,
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0 && git == 8) TC_TRACE(trace_base + 7);
+        if ((threadIdx.x & 31) == 0 && git == 24) TC_TRACE(trace_base + 12);
     }
 }
 
@@ -735,8 +780,9 @@ __device__ __forceinline__ void bwd_publish(const BwdBars& br, int as, int lane)
 
 struct TcDqArgs {
     const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
-    const float* ev; const float* sc; const float* aT; const float* LT;
-    float* dqp;             // [slot][B][NK]
+    const float* sc;
+    const float* aT; const float* LT; const float* RT; const float* cT; const float* Y2T;   // [dp][B] transposed a, L, R, c, Y2
+    float* dqT;             // [slot][NK][B]  dq partial per segment slot, transposed (coalesced stores)
     int B, d, dp, K, NK;
     int n_bil_rows;         // reduction rows holding bilinear rows (a multiple of 64)
     TcSched sch;            // units = SPR stages (one bilinear row for DP >= 64), tiles = example tiles
@@ -755,7 +801,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     uint32_t tmem_base;
-    if (threadIdx.x == 0) TC_TRACE(16);
+    if (threadIdx.x == 0) { TC_TRACE(16); TC_TRACE_NS(30); }
     const BwdBars br = bwd_setup(smem_raw, ST_BYTES, warp, tmem_base);
     if (threadIdx.x == 0) TC_TRACE(17);
 
@@ -801,16 +847,18 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
         while (si.next(sg)) {
             const int b = sg.tile * TC_M + row;
             const bool ok = b < p.B;
-            const float* evb = p.ev + (size_t)(ok ? b : 0) * E_NV * p.dp;
             const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
-            // register cache: stage h of a row needs j = jc(h) + 0..15 (four 16-byte loads each; dp is a multiple of 4)
+            // register cache: stage h of a row needs j = jc(h) + 0..15 (coalesced loads from the transposed copies)
             float X[SPR][16], Y[SPR][16];
 #pragma unroll
             for (int h = 0; h < SPR; ++h) {
                 const int j = (DP == 32) ? 16 * (cg & 1) : 64 * h + 16 * cg;
-                const bool o0 = ok && j < p.dp, o1 = ok && j + 4 < p.dp, o2 = ok && j + 8 < p.dp, o3 = ok && j + 12 < p.dp;
-                load16(evb + E_R * p.dp + j, o0, o1, o2, o3, X[h]);
-                load16(evb + E_Y2 * p.dp + j, o0, o1, o2, o3, Y[h]);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const bool in = ok && j + u < p.dp;
+                    X[h][u] = in ? p.RT[(size_t)(j + u) * p.B + b] : 0.f;
+                    Y[h][u] = in ? p.Y2T[(size_t)(j + u) * p.B + b] : 0.f;
+                }
             }
             const int st0 = sg.u0 * SPR, st1 = sg.u1 * SPR, nst = st1 - st0;
             // bilinear rows: segments start and end at row boundaries, so every row contributes its SPR stages in order
@@ -856,18 +904,15 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
                 const int git = it + lt, as = git % NAS;
                 const int m = (st0 + lt) * TC_SR - p.n_bil_rows + 16 * cg;
                 const int which = m / DP, j0 = m - which * DP;
-                const int sx = which == 0 ? E_A : E_CV, sy = which == 0 ? E_L : E_R;
+                const float* sx = which == 0 ? p.aT : p.cT;
+                const float* sy = which == 0 ? p.LT : p.RT;
                 const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
-                float xs[16], ys[16];
-                const bool o0 = ok && which < 2 && j0 < p.dp, o1 = ok && which < 2 && j0 + 4 < p.dp, o2 = ok && which < 2 && j0 + 8 < p.dp,
-                           o3 = ok && which < 2 && j0 + 12 < p.dp;
-                load16(evb + sx * p.dp + j0, o0, o1, o2, o3, xs);
-                load16(evb + sy * p.dp + j0, o0, o1, o2, o3, ys);
                 float g0[8], g1[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    g0[u] = fmaf(s2, ys[u], xs[u]);
-                    g1[u] = fmaf(s2, ys[8 + u], xs[8 + u]);
+                    const bool in0 = ok && which < 2 && j0 + u < p.dp, in1 = ok && which < 2 && j0 + 8 + u < p.dp;
+                    g0[u] = in0 ? fmaf(s2, sy[(size_t)(j0 + u) * p.B + b], sx[(size_t)(j0 + u) * p.B + b]) : 0.f;
+                    g1[u] = in1 ? fmaf(s2, sy[(size_t)(j0 + 8 + u) * p.B + b], sx[(size_t)(j0 + 8 + u) * p.B + b]) : 0.f;
                 }
                 mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
                 tc_fence_after();
@@ -880,11 +925,15 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
                 // ===== epilogue: accumulator row -> dq partial of this segment's slot =====
                 mbar_wait(br.acc_full, seg & 1);
                 tc_fence_after();
-                float* o = p.dqp + ((size_t)sg.slot * p.B + (ok ? b : 0)) * p.NK;
+                float* o = p.dqT + (size_t)sg.slot * p.NK * p.B + (ok ? b : 0);
                 for (int c0 = 0; c0 < p.NK; c0 += 32) {
                     float t[32];
                     tc_ld32(lane_base + (uint32_t)c0, t);
-                    if (ok) store_row32(o + c0, t, p.NK - c0, true);       // NK is a multiple of 16
+                    if (ok) {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x)
+                            if (c0 + x < p.NK) o[(size_t)(c0 + x) * p.B] = t[x];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -896,7 +945,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) TC_TRACE(21);
+    if (threadIdx.x == 0) { TC_TRACE(21); TC_TRACE_NS(31); }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -923,7 +972,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     constexpr int NAS = TC_DC_ASTAGES;
     const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
-    if (threadIdx.x == 0) TC_TRACE(32);
+    if (threadIdx.x == 0) { TC_TRACE(32); TC_TRACE_NS(46); }
     // Per-example scalars of the generated operand, staged once in shared memory for every segment of the CTA.  A 32-row
     // quarter of a tile is one bilinear row i (P1 = a_bi, P2 = L_bi) or one selectional-preference table (P1 = 1,
     // P2 = G2_b | G1_b); a tile holds TC_M / DP such sources.  Coalesced reads of the transposed copies aT / LT.
@@ -1094,63 +1143,71 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) TC_TRACE(37);
+    if (threadIdx.x == 0) { TC_TRACE(37); TC_TRACE_NS(47); }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-// per-example finishing of the backward (one warp per example): SP terms of dL/dR, dq += entropy term, softmax backward
+// per-example finishing of the backward: SP terms of dL/dR, dq (sum of the tile's slot partials) += entropy term, softmax
+// backward.  One CTA per 32 examples: the transposed dq partials dqT[slot][k][b] are read coalesced (lane = example) into a
+// shared tile, then one warp per example works on its row (4 examples per warp).
 __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
-                                                       const float* __restrict__ logq, const float* __restrict__ dqp, float* __restrict__ dz,
+                                                       const float* __restrict__ logq, const float* __restrict__ dqT, float* __restrict__ dz,
                                                        float* __restrict__ dzsum_part, int B, int K, int NK, TcSched sch_dq, int d, int dp,
-                                                       int hasSP, float ent_coef, const float* __restrict__ vg, const float* __restrict__ wp,
-                                                       int tcDP, TcSched sch_rec) {
-    extern __shared__ float dzs[];     // [8][K]
+                                                       int hasSP, float ent_coef) {
+    extern __shared__ float fin_smem[];
+    const int KS = K | 1;                  // odd row stride: conflict-free transposed writes
+    float* sdq = fin_smem;                 // [32][KS]
+    float* dzs = fin_smem + 32 * KS;       // [32][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * 8 + warp;
-    if (b < B) {
-        float* evb = ev + (size_t)b * E_NV * dp;
-        const int ns_vw = tcs_nslots(sch_rec, b >> 7), ns_dq = tcs_nslots(sch_dq, b >> 7);   // partial slots of this example's tile
-        {
-            // d cost / d L = M c (+ SP term), d cost / d R = M^T a (+ SP term): the recompute pass left M c and M^T a in
-            // the contraction's partial buffers
-            const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
-            for (int j = lane; j < d; j += 32) {
-                float ga1, ga2;
-                tc_combined_vw(vg, wp, B, dp, tcDP, ns_vw, b, j, ga1, ga2);
-                if (hasSP) {
-                    ga1 = fmaf(gp + g2, evb[E_C1 * dp + j], ga1);
-                    ga2 = fmaf(gp + g1, evb[E_C2 * dp + j], ga2);
-                }
-                evb[E_GA1 * dp + j] = ga1;
-                evb[E_GA2 * dp + j] = ga2;
-            }
-        }
-        float dot = 0.f;
-        for (int k = lane; k < K; k += 32) {
+    const int b0 = blockIdx.x * 32;
+    {
+        const int ns = tcs_nslots(sch_dq, b0 >> 7);
+        const int b = b0 + lane;
+        for (int k = warp; k < K; k += 8) {
             float v = 0.f;
-            for (int s = 0; s < ns_dq; ++s) v += dqp[((size_t)s * B + b) * NK + k];
-            v = fmaf(ent_coef, logq[(size_t)b * K + k] + 1.f, v);
-            dzs[warp * K + k] = v;
-            dot = fmaf(q[(size_t)b * K + k], v, dot);
+            if (b < B)
+                for (int s = 0; s < ns; ++s) v += dqT[((size_t)s * NK + k) * B + b];
+            sdq[lane * KS + k] = v;
         }
-        dot = warp_sum(dot);
-        for (int k = lane; k < K; k += 32) {
-            const float v = q[(size_t)b * K + k] * (dzs[warp * K + k] - dot);
-            dzs[warp * K + k] = v;
-            dz[(size_t)b * K + k] = v;
+    }
+    __syncthreads();
+    for (int e = warp * 4; e < warp * 4 + 4; ++e) {
+        const int b = b0 + e;
+        if (b < B) {
+            float* evb = ev + (size_t)b * E_NV * dp;
+            if (hasSP) {
+                // d cost / d L = M c + SP term, d cost / d R = M^T a + SP term: k_tc_combine left M c and M^T a in E_GA1 / E_GA2
+                const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
+                for (int j = lane; j < d; j += 32) {
+                    evb[E_GA1 * dp + j] = fmaf(gp + g2, evb[E_C1 * dp + j], evb[E_GA1 * dp + j]);
+                    evb[E_GA2 * dp + j] = fmaf(gp + g1, evb[E_C2 * dp + j], evb[E_GA2 * dp + j]);
+                }
+            }
+            float dot = 0.f;
+            for (int k = lane; k < K; k += 32) {
+                const float v = fmaf(ent_coef, logq[(size_t)b * K + k] + 1.f, sdq[e * KS + k]);
+                dzs[e * K + k] = v;
+                dot = fmaf(q[(size_t)b * K + k], v, dot);
+            }
+            dot = warp_sum(dot);
+            for (int k = lane; k < K; k += 32) {
+                const float v = q[(size_t)b * K + k] * (dzs[e * K + k] - dot);
+                dzs[e * K + k] = v;
+                dz[(size_t)b * K + k] = v;
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) dzs[e * K + k] = 0.f;
         }
-    } else {
-        for (int k = lane; k < K; k += 32) dzs[warp * K + k] = 0.f;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += dzs[w * K + k];
-        dzsum_part[(size_t)blockIdx.x * K + k] = s;
+        double s = 0.0;            // cancelling sum: see k_dense_finalize
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) s += (double)dzs[w * K + k];
+        dzsum_part[(size_t)blockIdx.x * K + k] = (float)s;
     }
 }
 
@@ -1261,13 +1318,17 @@ int tc_init(rae_engine* h) {
     t.smem_dc = t.smem_dq + (size_t)t.dc_share * per_stage;
     cudaError_t e;
     if ((e = cudaMalloc((void**)&t.bop, (size_t)t.n_chunks_fwd * b_bytes)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.vg, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.wp, (size_t)2 * t.slots_vw * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.vT, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.wT, (size_t)2 * t.slots_vw * h->B * h->dp * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.bop2, (size_t)n_st * st_bytes)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.dqp, (size_t)t.slots_dq * h->B * t.NK * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.dqT, (size_t)t.slots_dq * h->B * t.NK * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bst * st_bytes)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.qT, (size_t)4 * t.KQ * h->B * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.aT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.LT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess)
+        (e = cudaMalloc((void**)&t.LT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.RT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.cT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.Y2T, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess)
         return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
 #define RAE_TC_ATTR(KERN, BYTES)                                                                                     \
     if ((e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) \
@@ -1282,8 +1343,8 @@ int tc_init(rae_engine* h) {
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.bop); cudaFree(t.vg); cudaFree(t.wp); cudaFree(t.bop2); cudaFree(t.dqp); cudaFree(t.pop3);
-    cudaFree(t.aT); cudaFree(t.LT);
+    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3);
+    cudaFree(t.qT); cudaFree(t.aT); cudaFree(t.LT); cudaFree(t.RT); cudaFree(t.cT); cudaFree(t.Y2T);
     t = TcState{};
 }
 
@@ -1299,7 +1360,28 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     return RAE_OK;
 }
 
-// q-dependent operand of the dC contraction (after the encoder) + L / R gather
+namespace {
+int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst, bool with_q, cudaStream_t st) {
+    TcState& t = h->tc;
+    TrJobs jobs{};
+    jobs.B = h->B;
+    int nj = 0, maxc = 0;
+    for (int i = 0; i < n; ++i) {
+        jobs.j[nj++] = TrJob{h->ev + (size_t)slots[i] * h->dp, (size_t)E_NV * h->dp, h->d, h->dp, dst[i]};
+        maxc = std::max(maxc, h->dp);
+    }
+    if (with_q) {
+        jobs.j[nj++] = TrJob{h->q, (size_t)h->K, h->K, 4 * t.KQ, t.qT};
+        maxc = std::max(maxc, 4 * t.KQ);
+    }
+    k_tc_transpose<<<dim3((h->B + 31) / 32, (maxc + 31) / 32, nj), 256, 0, st>>>(jobs);
+    h->launches++;
+    RAE_CUDA(h, cudaGetLastError());
+    return RAE_OK;
+}
+}  // namespace
+
+// q-dependent operand of the dC contraction (after the encoder) + L / R gather, then the transposed views qT, LT, RT
 int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st) {
     TcState& t = h->tc;
     const int nbc = 2 * t.n_bst;
@@ -1309,7 +1391,9 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
                                                    h->quirk ? 1 : 0, h->ev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
-    return RAE_OK;
+    const int slots[2] = {E_L, E_R};
+    float* const dst[2] = {t.LT, t.RT};
+    return tc_transpose_slots(h, 2, slots, dst, true, st);
 }
 
 // the q-dependent operand alone (only the dC contraction at the end of the step needs it: prepared off the critical path)
@@ -1325,52 +1409,63 @@ int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
     return RAE_OK;
 }
 
-// one contraction pass: (slotL, slotR) in -> v = M R (per-group partials in vg) [+ SP rows to E_C1/E_C2 when with_sp],
-// w = M^T L (per-slot partials in wp); k_score (forward) and k_tc_bwd_finish (backward) read the partial buffers directly
-int tc_contract(rae_engine* h, int slotL, int slotR, bool with_sp, cudaStream_t st) {
+// one contraction pass over the transposed views (LT_in, RT_in): v = M R [+ SP rows to E_C1/E_C2 when with_sp], w = M^T L,
+// combined into ev[b][slotV | slotW]
+int tc_contract(rae_engine* h, const float* LT_in, const float* RT_in, int slotV, int slotW, bool with_sp, cudaStream_t st) {
     TcState& t = h->tc;
     TcArgs p{};
-    p.q = h->q; p.bop = t.bop; p.ev = h->ev; p.ev_out = h->ev; p.vg = t.vg; p.wp = t.wp;
-    p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ; p.slotL = slotL; p.slotR = slotR;
+    p.qT = t.qT; p.bop = t.bop; p.LT = LT_in; p.RT = RT_in; p.ev_out = h->ev; p.vT = t.vT; p.wT = t.wT;
+    p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ;
     p.n_bil_half = t.n_bil_half; p.n_sp_half = with_sp ? t.n_sp_half : 0;
     p.nbs = t.fwd_stages;
     p.sch = with_sp ? t.sch_fwd : t.sch_rec;
     if (t.DP == 32) k_tc_bilinear<32><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
     else if (t.DP == 64) k_tc_bilinear<64><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
     else k_tc_bilinear<128><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
-    h->launches += 1;
+    RAE_CUDA(h, cudaGetLastError());
+    k_tc_combine<<<dim3((h->B + 31) / 32, (h->d + 31) / 32), 256, 0, st>>>(t.vT, t.wT, h->ev, h->B, h->d, h->dp, t.DP, p.sch, slotV, slotW);
+    h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-// backward on the tensor path, three parts (separately timed phases): (1) M c and M^T a through the forward kernel with
-// L := a, R := c; (2) dq contraction; (3) per-example finish: dL, dR, entropy term, softmax backward -> dz
-int tc_backward_recompute(rae_engine* h, cudaStream_t st) { return tc_contract(h, E_A, E_CV, false, st); }
+int tc_forward(rae_engine* h, cudaStream_t st) { return tc_contract(h, h->tc.LT, h->tc.RT, E_V1, E_V2, true, st); }
+
+// backward on the tensor path, three parts (separately timed phases): (1) the transposed views of a, c, Y2 and M c, M^T a
+// through the forward kernel with L := a, R := c; (2) dq contraction; (3) per-example finish: dL, dR, entropy term,
+// softmax backward -> dz
+int tc_backward_recompute(rae_engine* h, cudaStream_t st) {
+    TcState& t = h->tc;
+    const int slots[3] = {E_A, E_CV, E_Y2};
+    float* const dst[3] = {t.aT, t.cT, t.Y2T};
+    int rc = tc_transpose_slots(h, 3, slots, dst, false, st);
+    if (rc) return rc;
+    return tc_contract(h, t.aT, t.cT, E_GA1, E_GA2, false, st);
+}
 
 int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    k_tc_transpose_al<<<dim3((h->B + 31) / 32, (h->dp + 31) / 32), 256, 0, st>>>(h->ev, h->B, h->d, h->dp, t.aT, t.LT);
     TcDqArgs p{};
-    p.bop2 = t.bop2; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.dqp = t.dqp;
+    p.bop2 = t.bop2; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.RT = t.RT; p.cT = t.cT; p.Y2T = t.Y2T; p.dqT = t.dqT;
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
     p.n_bil_rows = t.n_bil_rows;
     p.sch = t.sch_dq;
     if (t.DP == 32) k_tc_dq<32><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     else if (t.DP == 64) k_tc_dq<64><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
     else k_tc_dq<128><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
-    h->launches += 2;
+    h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
 int tc_backward_finish(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    const int blocks = (h->B + 7) / 8;
+    const int blocks = (h->B + 31) / 32;
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
-    k_tc_bwd_finish<<<blocks, 256, sizeof(float) * 8 * h->K, st>>>(h->ev, h->sc, h->q, h->logq, t.dqp, h->dz, h->dzsum_part, h->B, h->K,
-                                                                  t.NK, t.sch_dq, h->d, h->dp, h->hasSP ? 1 : 0,
-                                                                  (float)(2.0 * h->cfg.alpha / h->Z), t.vg, t.wp, t.DP, t.sch_rec);
+    const size_t smem = sizeof(float) * 32 * ((size_t)(h->K | 1) + h->K);
+    k_tc_bwd_finish<<<blocks, 256, smem, st>>>(h->ev, h->sc, h->q, h->logq, t.dqT, h->dz, h->dzsum_part, h->B, h->K, t.NK, t.sch_dq,
+                                               h->d, h->dp, h->hasSP ? 1 : 0, (float)(2.0 * h->cfg.alpha / h->Z));
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;

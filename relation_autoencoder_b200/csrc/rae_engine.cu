@@ -146,7 +146,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 4 forward contraction: v = M R, w = M^T L, c1, c2
     if (h->use_tc) {
-        if ((rc = tc_contract(h, E_L, E_R, true, st))) return rc;
+        if ((rc = tc_forward(h, st))) return rc;
     } else {
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
     }

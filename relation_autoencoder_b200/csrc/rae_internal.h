@@ -95,14 +95,15 @@ struct TcState {
     TcSched sch_fwd{}, sch_rec{}, sch_dq{}, sch_dc{};
     int slots_vw = 0, slots_dq = 0, slots_dc = 0;   // partial-result slots per tile (maximum over tiles)
     float4* bop = nullptr; // forward B operand chunks [chunk][hi/lo][KQ][128]
-    float* vg = nullptr;   // [2][B][dp]
-    float* wp = nullptr;   // [slots_vw][2][B][dp]
+    float* vT = nullptr;   // [2][dp][B]            v partials, transposed (lane = example)
+    float* wT = nullptr;   // [slots_vw][2][dp][B]  w partials, transposed
     int NK = 0; size_t smem_dq = 0, smem_dc = 0;
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
-    float* dqp = nullptr;   // [slots_dq][B][NK]
+    float* dqT = nullptr;   // [slots_dq][NK][B]  dq partials, transposed
     int n_ntiles = 0, n_bst = 0, dc_nacc = 2, dc_share = 0;   // dC: 128-row tiles, 64-example stages, accumulators, stages per CTA
     float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
-    float* aT = nullptr; float* LT = nullptr;   // transposed a, L: [dp][B]
+    float* qT = nullptr;    // [4 KQ][B]  q transposed
+    float* aT = nullptr; float* LT = nullptr; float* RT = nullptr; float* cT = nullptr; float* Y2T = nullptr;   // [dp][B] views
 };
 
 }  // namespace rae
@@ -206,7 +207,7 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st);
 int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // q^T operand + gather L, R
 int tc_prepare_qt(rae_engine* h, cudaStream_t st);                                      // q^T operand only
 int tc_gather_lr(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream_t st);   // L, R only
-int tc_contract(rae_engine* h, int slotL, int slotR, bool with_sp, cudaStream_t st);
+int tc_forward(rae_engine* h, cudaStream_t st);                                         // v, w, c1, c2 -> ev
 int tc_backward_recompute(rae_engine* h, cudaStream_t st);
 int tc_backward_dq(rae_engine* h, cudaStream_t st);
 int tc_backward_finish(rae_engine* h, cudaStream_t st);

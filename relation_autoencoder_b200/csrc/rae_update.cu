@@ -594,17 +594,19 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
         }
         return;
     }
-    __shared__ float red[256];
+    // dWb[k] = sum over the examples of dz[b][k] is a heavily cancelling sum (every row of dz sums to zero): the partial rows
+    // are combined in double so that the reduction itself adds nothing to the fp32 error of the terms
+    __shared__ double red[256];
     const int k = (int)blockIdx.x - n_elem_blocks;
-    float s = 0.f;
-    for (int c = threadIdx.x; c < n_dz_part; c += 256) s += dzsum_part[(size_t)c * K + k];
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n_dz_part; c += 256) s += (double)dzsum_part[(size_t)c * K + k];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[off_wb + k] = red[0];
+    if (threadIdx.x == 0) out[off_wb + k] = (float)red[0];
 }
 
 // elementwise optimiser over up to 5 dense tensors in one launch (blockIdx.y = tensor):

@@ -120,6 +120,13 @@ def _feature_function(name):
     return _FeatureFunctionStub(name)
 
 
+_SAFE_GLOBALS = frozenset(
+    [(m, n) for m in ('builtins', '__builtin__') for n in ('set', 'frozenset', 'list', 'dict', 'tuple', 'object', 'int', 'long',
+                                                          'float', 'str', 'unicode', 'bytes', 'bool', 'complex')]
+    + [('copy_reg', '_reconstructor'), ('copyreg', '_reconstructor'), ('collections', 'OrderedDict'),
+       ('collections', 'defaultdict'), ('collections', 'Counter')])
+
+
 class _RefUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if name == 'FeatureLexicon' and module in ('__main__', REF_LEXICON_MODULE, 'OiePreprocessor', __name__):
@@ -128,7 +135,13 @@ class _RefUnpickler(pickle.Unpickler):
             return OieExample
         if module in (REF_FEATURES_MODULE, 'OieFeatures'):
             return _feature_function(name)
-        return super().find_class(module, name)
+        if module == __name__ and name == '_FeatureFunctionStub':
+            return _FeatureFunctionStub
+        # the format needs nothing else beyond a few harmless builtins (py2 names included): anything else - os.system
+        # through REDUCE, say - is refused instead of imported, so a dataset file from an untrusted source cannot run code
+        if (module, name) in _SAFE_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("dataset pickle refers to %s.%s, which the dataset format does not need" % (module, name))
 
 
 class _RefPickler(pickle._Pickler):
@@ -190,18 +203,20 @@ def unpickle_objects(a_file, verbose=False):
 
 
 def pickle_objects(feat_extrs, feat_lex, dataset_splits, goldstandard_splits, a_file):
-    """Writes the four pickles (protocol 2, reference module paths) - OiePreprocessor.py:290-320 incl. its checks."""
-    assert type(feat_extrs) == list, 'Expected a list of callables as the 1st object to be pickled'
-    for _ in feat_extrs:
-        assert callable(_) is True, 'Element {} of 1st object is not callable'.format(_)
-    assert isinstance(feat_lex, FeatureLexicon), \
-        "Expected an instance of FeatureLexicon as the 2nd object to be pickled. Got '{}' instead".format(type(feat_lex))
-    assert type(dataset_splits) == dict, 'Expected a dict as the 3rd object to be pickled'
-    for _ in dataset_splits:
-        assert _ in ['train', 'test', 'valid'], "The dict expected as the 3rd object to be pickled, has key '{}' not in ['train', 'test', 'valid']".format(_)
-    assert type(goldstandard_splits) == dict, 'Expected a dict as the 4th object to be pickled'
-    for _ in goldstandard_splits:
-        assert _ in ['train', 'test', 'valid'], "The dict expected as the 4th object to be pickled, has key '{}' not in ['train', 'test', 'valid']".format(_)
+    """Writes the four pickles (protocol 2, reference module paths) in the order OiePreprocessor.py:290-320 defines:
+    [feature functions], FeatureLexicon, {split: [OieExample]}, {split: {index: [label tokens]}}.  The arguments are
+    validated first (the reference does the same before it opens the file)."""
+    splits_allowed = ('train', 'test', 'valid')
+    if not isinstance(feat_extrs, list) or not all(callable(f) for f in feat_extrs):
+        raise AssertionError('object 1 of the dataset file must be a list of feature callables, got %r' % (feat_extrs,))
+    if not isinstance(feat_lex, FeatureLexicon):
+        raise AssertionError('object 2 of the dataset file must be a FeatureLexicon, got %s' % type(feat_lex).__name__)
+    for pos, obj in ((3, dataset_splits), (4, goldstandard_splits)):
+        if not isinstance(obj, dict):
+            raise AssertionError('object %d of the dataset file must be a dict keyed by split, got %s' % (pos, type(obj).__name__))
+        unknown = [k for k in obj if k not in splits_allowed]
+        if unknown:
+            raise AssertionError('object %d of the dataset file has split keys %r outside %r' % (pos, unknown, splits_allowed))
     with open(a_file, 'wb') as pkl_file:
         for obj in (feat_extrs, feat_lex, dataset_splits, goldstandard_splits):
             _RefPickler(pkl_file, protocol=2).dump(obj)

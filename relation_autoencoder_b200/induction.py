@@ -70,7 +70,7 @@ def cuda_backend(inducer: "ReconstructInducer") -> Dict[str, Callable]:
                  data.get_dimensionality(), data.get_arg_voc_size(), tr.get_size(), lr=inducer.learningRate,
                  l1=inducer.lambdaL1, l2=inducer.lambdaL2, alpha=inducer.alpha, optimizer=inducer.optimization,
                  ext_reg=inducer.extendedReg, device=inducer.device)
-    eng.set_params_numpy(inducer.initial_params)
+    eng.set_params_numpy(inducer.initial_params, inducer.initial_acc)     # initial_acc: AdaGrad state of a resumed run, else None
     func = {}
     for split in data.generate_split_keys():
         sp = data.split[split]
@@ -130,6 +130,7 @@ class ReconstructInducer(object):
                                               data.get_arg_voc_size(), embed_size)           # OieInduction.py:88
         self.func = dict(zip([SPLIT_LABELS[0]] + ['label_' + s for s in SPLIT_LABELS], [None] * (1 + len(SPLIT_LABELS))))
         self.cur_epoch = 0
+        self.initial_acc = None              # AdaGrad accumulators restored by load() before the functions are compiled
         self.evaluator = dict(zip(SPLIT_LABELS, [None] * len(SPLIT_LABELS)))
         for split in self.data.generate_split_keys():
             self.evaluator[split] = construct_split_evaluator(self.goldStandard[split], split)
@@ -180,7 +181,7 @@ class ReconstructInducer(object):
         ``func['train']`` call per batch on the [S, B] column slices, per-epoch labelling + B-cubed."""
         n_train = self.data.split['train'].get_size()
         self._print('Training model on {} examples'.format(n_train))
-        epoch = 0
+        epoch = self.cur_epoch               # 0 for a fresh run; load() restores the epochs a resumed run has already done
         while epoch < self.nb_epochs:
             t_epoch = time.perf_counter()
             err = 0
@@ -264,17 +265,33 @@ class ReconstructInducer(object):
                    train_error=self.train_error_series, metrics=self.metrics)
         arrays = {'param_' + k: v for k, v in params.items()}
         arrays.update({'acc_' + k: v for k, v in acc.items()})
+        # the run's generator feeds the negative sampler (OieInduction.py:183-184): its state is part of the run
+        kind, keys, pos, has_gauss, cached = self.rng.get_state()
+        arrays.update(rng_keys=np.asarray(keys, dtype=np.uint32), rng_pos=np.int64(pos), rng_has_gauss=np.int64(has_gauss),
+                      rng_cached_gaussian=np.float64(cached))
         np.savez(path, config=np.array(json.dumps(cfg)), **arrays)
         return path
 
     def load(self, path: str):
-        """Restores parameters and accumulators saved by :meth:`save` into the bound engine (resume)."""
+        """Resume from a checkpoint written by :meth:`save`: parameters, AdaGrad accumulators, the epoch counter, the
+        error / metric series and the generator state, so that training continues exactly where the saved run stopped
+        (works before or after the functions are compiled)."""
         ck = load_model(path)
-        if self.engine is None:
+        if self.engine is None and getattr(self, 'oracle_model', None) is None:
             self.initial_params = {k: v for k, v in ck['params'].items()}
-        else:
+            self.initial_acc = {k: v for k, v in ck['acc'].items()} if ck['acc'] else None
+        elif self.engine is not None:
             self.engine.set_params_numpy(ck['params'], ck['acc'])
-        self.cur_epoch = int(ck['config'].get('epochs_done', 0))
+        else:
+            self.oracle_model.params = {k: np.asarray(v, dtype=np.float64) for k, v in ck['params'].items()}
+            self.oracle_model.acc = {k: np.asarray(v, dtype=np.float64) for k, v in ck['acc'].items()}
+        cfg = ck['config']
+        self.cur_epoch = int(cfg.get('epochs_done', 0))
+        self.train_error_series = list(cfg.get('train_error', []))
+        for split, series in (cfg.get('metrics') or {}).items():
+            self.metrics[split] = [tuple(m) for m in series]
+        if ck.get('rng') is not None:
+            self.rng.set_state(ck['rng'])
         return ck
 
 
@@ -285,7 +302,10 @@ def load_model(path: str):
     z = np.load(path, allow_pickle=False)
     params = {k[len('param_'):]: z[k] for k in z.files if k.startswith('param_')}
     acc = {k[len('acc_'):]: z[k] for k in z.files if k.startswith('acc_')}
-    return {'config': json.loads(str(z['config'])), 'params': params, 'acc': acc}
+    rng = None
+    if 'rng_keys' in z.files:
+        rng = ('MT19937', z['rng_keys'], int(z['rng_pos']), int(z['rng_has_gauss']), float(z['rng_cached_gaussian']))
+    return {'config': json.loads(str(z['config'])), 'params': params, 'acc': acc, 'rng': rng}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

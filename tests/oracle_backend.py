@@ -11,9 +11,12 @@ from oracle import rae_oracle as O
 def oracle_backend(inducer):
     data = inducer.data
     p = {k: np.asarray(v, dtype=np.float64) for k, v in inducer.initial_params.items()}
+    acc0 = getattr(inducer, 'initial_acc', None)
     om = O.OracleModel(inducer.decoder_type, p, K=inducer.relationNum, d=inducer.embedSize, S=inducer.neg_sample_num,
                        B=inducer.batch_size, lr=inducer.learningRate, l1=inducer.lambdaL1, l2=inducer.lambdaL2,
                        alpha=inducer.alpha, optimizer=inducer.optimization, ext_reg=inducer.extendedReg)
+    if acc0 is not None:                       # a resumed run (ReconstructInducer.load before compile_function)
+        om.acc = {k: np.asarray(v, dtype=np.float64) for k, v in acc0.items()}
     func = {}
     for split in data.generate_split_keys():
         sp = data.split[split]

@@ -21,7 +21,7 @@ import pytest
 
 from oracle import rae_oracle as O
 from relation_autoencoder_b200 import synthetic as SY
-from tests.helpers import rel_err
+from tests.helpers import record_err, rel_err
 
 TOL_COST = 1e-5
 TOL_Q = 1e-5
@@ -81,6 +81,7 @@ def check_first_step(p0, p1, acc1, g_ref, touched, lr=LR):
         gmax = float(np.abs(g).max())
         g_abs = np.sqrt(a1.astype(np.float64))
         e = float(np.abs(g_abs - np.abs(g)).max())
+        record_err("fullsize", n, e / max(gmax, 1e-300))
         assert e <= TOL_GRAD * gmax, "%s: |g| from the accumulators off by %.3g of ||g||_inf" % (n, e / max(gmax, 1e-300))
         moved = q0.astype(np.float64) - q1.astype(np.float64)
         rule = lr * g_abs / (g_abs + 1e-6)
