@@ -11,8 +11,13 @@
 //   forward / backward-recompute  M_b = sum_k q_bk C[:,:,k]      D[b, n]  = sum_k P[b,k]  Cf[n,k]     -> v = M R, w = M^T L
 //   backward dq                   dq_bk = <dM_b, C[:,:,k]>        D[b, k]  = sum_n G[b,n]  Cf[n,k]     (G = a R^T + L Y2^T, rank 2)
 //   backward dC                   dC[n,k] = sum_b dM_b[n] q_bk    D[n, k]  = sum_b G[b,n]  q[b,k]
-// fp32 parity: every operand x is split x = hi + lo (both TF32-exact) and each k-step issues hi.hi + hi.lo + lo.hi
-// (3 tcgen05.mma kind::tf32, fp32 accumulation in TMEM; dropped lo.lo ~ 2^-22 relative).
+// fp32 parity: every operand x is split x = hi + lo and each k-step issues hi.hi + hi.lo + lo.hi with fp32 accumulation in
+// TMEM (dropped lo.lo ~ 2^-22 relative).  The forward / recompute and dq contractions split into FP16 pairs (kind::f16,
+// K = 16 per MMA: the same 64 cycles per instruction as a K = 8 kind::tf32 MMA, profiles/microbench/mma_power.cu, so half
+// the MMAs): an fp16 has the 11-bit significand of a TF32, and its narrow exponent is handled by scaling every operand
+// tensor by an exact power of two chosen from its measured |max| (so that |x| s < 2^12: no overflow; a value whose lo part
+// falls into the fp16 subnormals is still exact to 2^-37 of the tensor's maximum), undone in the epilogue.  The dC
+// contraction still splits into TF32 pairs (kind::tf32).
 //
 // The M-side (A) operand lives in TMEM (TS mode): the threads that own a TMEM lane (= an example row b, or an output row
 // n) write their row with tcgen05.st - q rows once per segment for the forward, the generated operand G stage by stage for
@@ -30,6 +35,7 @@
 // Warp roles (all kernels): warp 0 = bulk-copy producer, 1 = MMA issuer (warp-uniform loop, elect.sync lane issues),
 // 2 = TMEM allocator, 3 = idle, 4.. = row-owning workers (epilogue / operand generators); worker warp w touches TMEM
 // lanes 32*(w%4)..+31 as the hardware requires.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -206,6 +212,48 @@ __device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& 
     lo.x = tf32_hi(x[0] - hi.x); lo.y = tf32_hi(x[1] - hi.y); lo.z = tf32_hi(x[2] - hi.z); lo.w = tf32_hi(x[3] - hi.w);
 }
 
+// instruction descriptor: D = F32, A = B = F16, both K-major, dense, no negate (kind::f16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// FP16 pair split of two (already scaled) values: hi = rn_f16(x), lo = rn_f16(x - hi); element 0 in the low half-word
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const __half2 l = __floats2half2_rn(x0 - __low2float(h), x1 - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void tc_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+// power-of-two scale s with amax * s < 2^12 (amax given as the bits of a non-negative float; 1 for zero / denormal)
+__host__ __device__ __forceinline__ float pow2_scale(uint32_t amax_bits) {
+    const int e = (int)((amax_bits >> 23) & 255u) - 127;      // amax < 2^(e+1)
+    if (((amax_bits >> 23) & 255u) == 0u) return 1.f;
+    int se = 11 - e;
+    se = se < -100 ? -100 : (se > 100 ? 100 : se);
+    union { uint32_t u; float f; } cv;
+    cv.u = (uint32_t)(se + 127) << 23;
+    return cv.f;
+}
+constexpr float TC_QSCALE = 4096.f;        // q in [0, 1] -> [0, 2^12]
+// device scalars of the tensor path (TcState::scal, uint32 words)
+enum TcScal { TS_AMAX_C = 0, TS_AMAX_L = 1, TS_AMAX_R = 2, TS_AMAX_A = 3, TS_AMAX_CV = 4, TS_AMAX_Y2 = 5, TS_N = 8 };
+
 // 16 bytes x 4 of one row -> 16 floats
 __device__ __forceinline__ void load16(const float* p, bool ok0, bool ok1, bool ok2, bool ok3, float (&x)[16]) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,49 +301,73 @@ __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, 
 // ------------------------------------------------------------------------------------------------------------
 // operand preparation (per step; the dense parameters change every step)
 // ------------------------------------------------------------------------------------------------------------
-// blockIdx.y == 0: forward B operand [chunk of 128 rows n][hi/lo][kq][row] float4, 4 consecutive relations per float4
-// blockIdx.y == 1: dq B operand, Cf transposed: [chunk of 32 rows n][hi/lo][nq 0..7][krow 0..NK-1] = (Cf[32c+4nq+0..3][krow])
+// |max| over the dense decoder tensors -> scal[TS_AMAX_C] (bits of a non-negative float: integer max is order-free, so the
+// atomic is deterministic)
+__global__ void __launch_bounds__(256) k_tc_absmax(const float* __restrict__ C, size_t nC, const float* __restrict__ C1, size_t n1,
+                                                   const float* __restrict__ C2, size_t n2, uint32_t* __restrict__ out) {
+    __shared__ uint32_t red[8];
+    uint32_t m = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t0; i < nC; i += stride) m = max(m, __float_as_uint(fabsf(C[i])));
+    for (size_t i = t0; i < n1; i += stride) m = max(m, __float_as_uint(fabsf(C1[i])));
+    for (size_t i = t0; i < n2; i += stride) m = max(m, __float_as_uint(fabsf(C2[i])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+        atomicMax(out, m);
+    }
+}
+
+// FP16 pair operands of the dense tensors, scaled by s_C = pow2_scale(|max|):
+// blockIdx.y == 0: forward B operand [chunk of 128 rows n][hi/lo][kq 0..KQ8-1][row] x 16 B = relations 8 kq .. 8 kq + 7 of row n
+// blockIdx.y == 1: dq B operand, Cf transposed: [stage of 128 rows n][hi/lo][oct 0..15][krow 0..NK-1] x 16 B = rows
+//                  128 st + 8 oct + 0..7 at relation krow
 __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, const float* __restrict__ C1,
-                                                   const float* __restrict__ C2, int d, int K, int KQ, int DP, int n_bil_rows,
-                                                   int n_rows_fwd, float4* __restrict__ out, int NK, int n_rows_bwd,
-                                                   float4* __restrict__ out2) {
+                                                   const float* __restrict__ C2, int d, int K, int KQ8, int DP, int n_bil_rows,
+                                                   int n_rows_fwd, uint4* __restrict__ out, int NK, int n_rows_bwd,
+                                                   uint4* __restrict__ out2, const uint32_t* __restrict__ scal) {
+    const float sC = pow2_scale(scal[TS_AMAX_C]);
     if (blockIdx.y == 1) {
-        const size_t total2 = (size_t)(n_rows_bwd / 4) * NK;
+        const size_t total2 = (size_t)(n_rows_bwd / 8) * NK;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total2; idx += (size_t)gridDim.x * blockDim.x) {
             const int krow = (int)(idx % NK);
-            const int nq_g = (int)(idx / NK);
-            float x[4];
+            const int oct_g = (int)(idx / NK);
+            uint32_t hi[4], lo[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 4 * nq_g + u);
-                x[u] = (src != nullptr && krow < K) ? src[krow] : 0.f;
+                const float* s0 = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 8 * oct_g + 2 * u);
+                const float* s1 = cf_row(C, C1, C2, d, K, DP, n_bil_rows, 8 * oct_g + 2 * u + 1);
+                const float x0 = (s0 != nullptr && krow < K) ? s0[krow] * sC : 0.f;
+                const float x1 = (s1 != nullptr && krow < K) ? s1[krow] * sC : 0.f;
+                split_h2(x0, x1, hi[u], lo[u]);
             }
-            float4 hi, lo;
-            split4(x, hi, lo);
-            const int c32 = nq_g / 8, nq = nq_g - c32 * 8;
-            float4* base = out2 + (size_t)c32 * 2 * 8 * NK;
-            base[(size_t)nq * NK + krow] = hi;
-            base[(size_t)(8 + nq) * NK + krow] = lo;
+            const int st = oct_g / 16, oct = oct_g - st * 16;
+            uint4* base = out2 + (size_t)st * 2 * 16 * NK;
+            base[(size_t)oct * NK + krow] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            base[(size_t)(16 + oct) * NK + krow] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         return;
     }
-    const size_t total = (size_t)n_rows_fwd * KQ;
+    const size_t total = (size_t)n_rows_fwd * KQ8;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int kq = (int)(idx % KQ);
-        const int n = (int)(idx / KQ);
+        const int kq = (int)(idx % KQ8);
+        const int n = (int)(idx / KQ8);
         const float* src = cf_row(C, C1, C2, d, K, DP, n_bil_rows, n);
-        float x[4];
+        uint32_t hi[4], lo[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int k = 4 * kq + u;
-            x[u] = (src != nullptr && k < K) ? src[k] : 0.f;
+            const int k = 8 * kq + 2 * u;
+            const float x0 = (src != nullptr && k < K) ? src[k] * sC : 0.f;
+            const float x1 = (src != nullptr && k + 1 < K) ? src[k + 1] * sC : 0.f;
+            split_h2(x0, x1, hi[u], lo[u]);
         }
-        float4 hi, lo;
-        split4(x, hi, lo);
         const int chunk = n / TC_N, r = n - chunk * TC_N;
-        float4* base = out + (size_t)chunk * 2 * KQ * TC_N;
-        base[(size_t)kq * TC_N + r] = hi;
-        base[(size_t)(KQ + kq) * TC_N + r] = lo;
+        uint4* base = out + (size_t)chunk * 2 * KQ8 * TC_N;
+        base[(size_t)kq * TC_N + r] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        base[(size_t)(KQ8 + kq) * TC_N + r] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -304,7 +376,9 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
 // blockIdx.y == 1: L = A[a1], R = A[a2] (A[a1] with the model-C quirk) -> ev, one warp per example
 __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, int nbc, float4* __restrict__ out,
                                                     const float* __restrict__ A, const int32_t* __restrict__ a1,
-                                                    const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev) {
+                                                    const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev,
+                                                    uint32_t* __restrict__ scal) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) scal[TS_AMAX_L + threadIdx.x] = 0u;   // the transposes that follow accumulate
     if (blockIdx.y == 1) {
         const int lane = threadIdx.x & 31;
         for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
@@ -338,7 +412,8 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
 
 // ------------------------------------------------------------------------------------------------------------
 // forward contraction (also used for the backward recompute with L := a, R := c)
-// TMEM map: accumulator stages [0,256) (2 x 128 columns), P operand hi at [256, 256+Kp), lo at [256+Kp, 256+2Kp)
+// TMEM map: accumulator stages [0,256) (2 x 128 columns), P operand (FP16 pairs, two relations per column) hi at
+//           [256, 256 + KH/2), lo at [256 + KH/2, 256 + KH)
 // Work unit = one 128-row chunk of Cf = two 64-row half chunks; epilogue group g (4 warps) consumes half g of EVERY chunk
 // (accumulator columns [64 g, 64 g + 64)), so for DP = 128 group g always holds the column half j in [64 g, 64 g + 64).
 // ------------------------------------------------------------------------------------------------------------
@@ -347,14 +422,16 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
 // way; k_tc_combine transposes / sums them back into the row-major per-example vectors.  (Reading ev[b][...] directly
 // costs one L1 wavefront per lane, ~66 cycles per warp instruction: measured as 2/3 of the kernel's time.)
 struct TcArgs {
-    const float* qT;        // [Kp][B]  q transposed (rows >= K zero)
+    const float* qT;        // [K][B]  q transposed
     const float4* bop;      // B operand chunks
     const float* LT;        // [dp][B]  left vectors transposed  (L forward, a for the recompute pass)
     const float* RT;        // [dp][B]  right vectors transposed (R forward, c for the recompute pass)
-    float* ev_out;          // SP half chunks write c1 / c2 here (E_C1 / E_C2), row stride E_NV*dp
+    float* spT;             // [2][dp][B]        c1, c2 (the accumulator rows of the C1 / C2 half chunks), transposed
     float* vT;              // [2][dp][B]        v partial per epilogue group
     float* wT;              // [slot][2][dp][B]  w partial per (segment slot, group)
-    int B, K, d, dp, KQ;
+    const uint32_t* scal;   // device scalars (TcScal): |max| of the dense tensors -> operand scale
+    int B, K, d, dp;
+    int KH;                 // relations padded to a multiple of 16 (one kind::f16 MMA reduces over 16)
     int n_bil_half;         // half chunks holding bilinear rows
     int n_sp_half;          // half chunks holding C1/C2 rows (forward only; 0 for the recompute pass)
     int nbs;                // B-operand shared-memory stages
@@ -366,8 +443,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
-    const uint32_t B_BYTES = 2u * p.KQ * TC_N * 16u;
-    const uint32_t Kp = 4u * p.KQ;                          // relations padded to a multiple of 8
+    const uint32_t KQ8 = (uint32_t)p.KH / 8u;               // 16-byte planes (8 relations each) per hi / lo half of a chunk
+    const uint32_t B_BYTES = 2u * KQ8 * TC_N * 16u;
+    const uint32_t KC = (uint32_t)p.KH / 2u;                // TMEM columns of one P plane (two fp16 per column)
     const int nbs = p.nbs;
     uint8_t* smB = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nbs * B_BYTES);
@@ -416,45 +494,59 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
-        const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
-        const uint32_t a_hi = tmem_base + TC_FWD_ACOL, a_lo = a_hi + Kp;
-        const int ksteps = p.KQ / 2;
-        TcSegIter si(p.sch, blockIdx.x);
-        TcSeg sg;
-        int it = 0, seg = 0;
-        while (si.next(sg)) {
-            mbar_wait(a_full, seg & 1);             // this segment's P rows are in TMEM
-            tc_fence_after();
-            for (int c = sg.u0; c < sg.u1; ++c, ++it) {
-                const int s = it % nbs, ts = it % TC_TSTAGES;
-                mbar_wait(&t_empty[ts], ((it / TC_TSTAGES) & 1) ^ 1);
-                mbar_wait(&b_full[s], (it / nbs) & 1);
+        // ===== MMA issuer: ONE elected thread runs the whole loop.  The barrier waits of chunk c+1 are taken in the middle of
+        // chunk c's MMA sequence, while the tensor pipe still has queued work (waiting BETWEEN chunks drained the pipe for
+        // ~400 cycles per chunk: in-kernel trace, profiles/r02_trace_T.txt) =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(TC_M, TC_N);
+            const uint32_t a_hi = tmem_base + TC_FWD_ACOL, a_lo = a_hi + KC;
+            const int ksteps = p.KH / 16;
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0, seg = 0;
+            bool ready = false;                         // the barriers of chunk `it` have been acquired already
+            while (si.next(sg)) {
+                mbar_wait(a_full, seg & 1);             // this segment's P rows are in TMEM
                 tc_fence_after();
-                if (lane == 0 && it == 4) TC_TRACE(6);
-                if (lane == 0 && it == 12) TC_TRACE(10);
-                if (elect_one()) {
+                for (int c = sg.u0; c < sg.u1; ++c, ++it) {
+                    const int s = it % nbs, ts = it % TC_TSTAGES;
+                    if (!ready) {
+                        mbar_wait(&t_empty[ts], ((it / TC_TSTAGES) & 1) ^ 1);
+                        mbar_wait(&b_full[s], (it / nbs) & 1);
+                        tc_fence_after();
+                    }
+                    ready = false;
+                    if (it == 4) TC_TRACE(6);
+                    if (it == 12) TC_TRACE(10);
                     const uint32_t b_hi = smem_u32(smB + (size_t)s * B_BYTES);
                     uint64_t h0 = make_desc(b_hi, TC_N * 16u, 128u);
-                    uint64_t l0 = make_desc(b_hi + p.KQ * TC_N * 16u, TC_N * 16u, 128u);
+                    uint64_t l0 = make_desc(b_hi + KQ8 * TC_N * 16u, TC_N * 16u, 128u);
                     const uint32_t d0 = tmem_base + (uint32_t)(ts * TC_N);
+                    const bool has_next = c + 1 < sg.u1;
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, h0, idesc, ks > 0 ? 1u : 0u);      // hi * hi
-                        tc_mma_tf32_ts(d0, a_hi + 8u * ks, l0, idesc, 1u);                    // hi * lo
-                        tc_mma_tf32_ts(d0, a_lo + 8u * ks, h0, idesc, 1u);                    // lo * hi
+                        if (has_next && ks == ksteps / 2) {
+                            const int it1 = it + 1;
+                            mbar_wait(&t_empty[it1 % TC_TSTAGES], ((it1 / TC_TSTAGES) & 1) ^ 1);
+                            mbar_wait(&b_full[it1 % nbs], (it1 / nbs) & 1);
+                            tc_fence_after();
+                            ready = true;
+                        }
+                        tc_mma_f16_ts(d0, a_hi + 8u * ks, h0, idesc, ks > 0 ? 1u : 0u);      // hi * hi
+                        tc_mma_f16_ts(d0, a_hi + 8u * ks, l0, idesc, 1u);                    // hi * lo
+                        tc_mma_f16_ts(d0, a_lo + 8u * ks, h0, idesc, 1u);                    // lo * hi
                         h0 = desc_advance(h0, 2u * TC_N * 16u);
                         l0 = desc_advance(l0, 2u * TC_N * 16u);
                     }
                     tc_commit(&b_empty[s]);      // the stage is reusable once these MMAs have read it
                     tc_commit(&t_full[ts]);      // accumulators complete
+                    if (it == 4) TC_TRACE(7);
+                    if (it == 12) TC_TRACE(11);
                 }
-                __syncwarp();
-                if (lane == 0 && it == 4) TC_TRACE(7);
-                if (lane == 0 && it == 12) TC_TRACE(11);
+                ++seg;
             }
-            ++seg;
+            TC_TRACE(3);
         }
-        if (lane == 0) TC_TRACE(3);
+        __syncwarp();
     } else if (warp >= 4) {
         // ===== row-owning warps: P operand -> TMEM, then epilogue =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
@@ -463,6 +555,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
         constexpr int RW = (DP >= 64) ? 64 : 32;      // columns of R / w held per thread
         const int jbase = (DP == 128) ? 64 * g : 0;
+        const float inv = 1.f / (TC_QSCALE * pow2_scale(p.scal[TS_AMAX_C]));      // undoes the operand scales (a power of two)
         TcSegIter si(p.sch, blockIdx.x);
         TcSeg sg;
         int it = 0;
@@ -470,23 +563,23 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
             const int b = sg.tile * TC_M + row;
             const bool ok = b < p.B;
             {
-                // q row -> TF32 hi / lo planes of the A operand in TMEM.  Group g converts relations [56 g, 56 g + 56): all of
-                // a thread's loads are issued before the first conversion (one memory latency).  Segments after the first:
-                // this warp has seen t_full of the previous segment's last chunk, so every MMA that read the old rows is done.
+                // q row (scaled by 2^12) -> FP16 hi / lo planes of the A operand in TMEM, two relations per column.  Group g
+                // converts relations [56 g, 56 g + 56): all of a thread's loads are issued before the first conversion (one
+                // memory latency).  Segments after the first: this warp has seen t_full of the previous segment's last
+                // chunk, so every MMA that read the old rows is done.
                 const int kb = 56 * g;
                 float qh[56];
 #pragma unroll
-                for (int i = 0; i < 56; ++i) qh[i] = (ok && (uint32_t)(kb + i) < Kp) ? p.qT[(size_t)(kb + i) * p.B + b] : 0.f;
-                const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)kb, a_lo_col = a_hi_col + Kp;
+                for (int i = 0; i < 56; ++i) qh[i] = (ok && kb + i < p.K) ? p.qT[(size_t)(kb + i) * p.B + b] * TC_QSCALE : 0.f;
+                const uint32_t a_hi_col = lane_base + TC_FWD_ACOL + (uint32_t)(kb / 2), a_lo_col = a_hi_col + KC;
 #pragma unroll
-                for (int c8 = 0; c8 < 7; ++c8) {
-                    if ((uint32_t)(kb + 8 * c8) < Kp) {
-                        float x[8], hi[8], lo[8];
+                for (int c4 = 0; c4 < 7; ++c4) {
+                    if ((uint32_t)(kb / 2 + 4 * c4) < KC) {
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) x[u] = qh[8 * c8 + u];
-                        split8(x, hi, lo);
-                        tc_st8(a_hi_col + 8u * c8, hi);
-                        tc_st8(a_lo_col + 8u * c8, lo);
+                        for (int u = 0; u < 4; ++u) split_h2(qh[8 * c4 + 2 * u], qh[8 * c4 + 2 * u + 1], hi[u], lo[u]);
+                        tc_st4u(a_hi_col + 4u * c4, hi);
+                        tc_st4u(a_lo_col + 4u * c4, lo);
                     }
                 }
                 tc_wait_st();
@@ -495,7 +588,6 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                 if (lane == 0) mbar_arrive(a_full);
                 if (ew == 0 && lane == 0 && it == 0) TC_TRACE(2);
             }
-            float* o = p.ev_out + (size_t)(ok ? b : 0) * E_NV * p.dp;
             float Rr[RW], Wr[RW];
 #pragma unroll
             for (int c = 0; c < RW; ++c) {
@@ -553,36 +645,28 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
                                 v4[x & 3] = fmaf(t[x], Rr[x % RW], v4[x & 3]);
                                 Wr[x % RW] = fmaf(t[x], Lh, Wr[x % RW]);
                             }
-                            if (ok && i0 + hf < p.d) p.vT[((size_t)g * p.dp + i0 + hf) * p.B + b] = (v4[0] + v4[1]) + (v4[2] + v4[3]);
+                            if (ok && i0 + hf < p.d) p.vT[((size_t)g * p.dp + i0 + hf) * p.B + b] = inv * ((v4[0] + v4[1]) + (v4[2] + v4[3]));
                         }
                     } else if (ok) {
-                        // selectional-preference rows: the accumulator row IS c1 / c2
-                        if (DP == 128) {
-                            const int slot = (sc < 2) ? E_C1 : E_C2, jb = 64 * (sc & 1) + 32 * hf;
+                        // selectional-preference rows: the accumulator row IS c1 / c2 (x the operand scales)
+                        int which, jb;
+                        if (DP == 128) { which = sc >> 1; jb = 64 * (sc & 1) + 32 * hf; }
+                        else if (DP == 64) { which = sc; jb = 32 * hf; }
+                        else { which = hf; jb = 0; }
+                        float* o = p.spT + (size_t)which * p.dp * p.B + b;
 #pragma unroll
-                            for (int x = 0; x < 32; ++x)
-                                if (jb + x < p.d) o[slot * p.dp + jb + x] = t[x];
-                        } else if (DP == 64) {
-                            const int slot = (sc == 0) ? E_C1 : E_C2;
-#pragma unroll
-                            for (int x = 0; x < 32; ++x)
-                                if (32 * hf + x < p.d) o[slot * p.dp + 32 * hf + x] = t[x];
-                        } else {
-                            const int slot = hf == 0 ? E_C1 : E_C2;
-#pragma unroll
-                            for (int x = 0; x < 32; ++x)
-                                if (x < p.d) o[slot * p.dp + x] = t[x];
-                        }
+                        for (int x = 0; x < 32; ++x)
+                            if (jb + x < p.d) o[(size_t)(jb + x) * p.B] = inv * t[x];
                     }
                 }
-                if (DP >= 64 && bil && ok && i0 < p.d) p.vT[((size_t)g * p.dp + i0) * p.B + b] = vsum;
+                if (DP >= 64 && bil && ok && i0 < p.d) p.vT[((size_t)g * p.dp + i0) * p.B + b] = inv * vsum;
             }
             if (ok) {
                 float* wo = p.wT + ((size_t)sg.slot * 2 + g) * p.dp * p.B + b;
 #pragma unroll
                 for (int c = 0; c < RW; ++c) {
                     const int j = jbase + c;
-                    if (j < p.dp) wo[(size_t)j * p.B] = Wr[c];
+                    if (j < p.dp) wo[(size_t)j * p.B] = inv * Wr[c];
                 }
             }
             if (ew == 0 && lane == 0 && it <= (sg.u1 - sg.u0)) TC_TRACE(9);     // first segment done
@@ -617,40 +701,58 @@ constexpr uint32_t TC_BWD_ACC2 = 384;
 constexpr int TC_DC_MAX_STAGES = 16;   // stages (of 64 examples, 24 MMAs each) per accumulator: 384 MMAs
 constexpr int TC_DQ_MAX_STAGES = 64;   // dq: stages (of 64 reduction rows) per segment: 1536 MMAs; random-sign terms drift less
 
-// tiled transposes: job z copies src[b * stride + c] (b < B, c < cols) to dst[c * B + b], zero rows for cols <= c < cols_out.
-// They give the contraction kernels their [column][example] views (lane = example reads are coalesced).
-struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; };
+// tiled transposes: job z copies src[b * stride + c] (b < B, c < cols) to dst[c * B + b], zero rows for cols <= c < cols_out,
+// and folds |max| of the job's values into *amax (bits of a non-negative float; nullptr: skip).  They give the contraction
+// kernels their [column][example] views (lane = example reads are coalesced) and the scales of the FP16 operands.
+struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; uint32_t* amax; };
 struct TrJobs { TrJob j[4]; int B; };
 __global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
     __shared__ float tile[32][33];
+    __shared__ uint32_t red[8];
     const TrJob jb = jobs.j[blockIdx.z];
     const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     if (c0 >= jb.cols_out) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of 32
+    uint32_t m = 0;
     for (int r = ty; r < 32; r += 8) {
         const int b = b0 + r, c = c0 + tx;
-        tile[r][tx] = (b < jobs.B && c < jb.cols) ? jb.src[(size_t)b * jb.stride + c] : 0.f;
+        const float v = (b < jobs.B && c < jb.cols) ? jb.src[(size_t)b * jb.stride + c] : 0.f;
+        tile[r][tx] = v;
+        m = max(m, __float_as_uint(fabsf(v)));
+    }
+    if (jb.amax != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+        if (tx == 0) red[ty] = m;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int c = c0 + r, b = b0 + tx;
         if (c < jb.cols_out && b < jobs.B) jb.dst[(size_t)c * jobs.B + b] = tile[tx][r];
     }
+    if (jb.amax != nullptr && threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+        atomicMax(jb.amax, m);
+    }
 }
 
 // v, w of a contraction pass: transposed partial buffers -> row-major per-example vectors ev[b][slotV | slotW][j]
 //   vT [2][dp][B]        DP=128: both epilogue groups hold a half-row partial; DP=64: group j%2; DP=32: group (j/2)%2
 //   wT [slot][2][dp][B]  sum over the slots of the example's tile (DP=128: only group j/64 holds column j; else both groups)
-__global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT, const float* __restrict__ wT, float* __restrict__ ev,
-                                                    int B, int d, int dp, int DP, TcSched sch, int slotV, int slotW) {
-    __shared__ float tv[32][33], tw[32][33];
+//   spT [2][dp][B]       c1, c2 -> ev[b][E_C1 | E_C2][j] (forward pass only; nullptr otherwise)
+// zero_amax: the forward pass's combine also clears the |max| words the NEXT transposes (a, c, Y2) accumulate into
+__global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT, const float* __restrict__ wT, const float* __restrict__ spT,
+                                                    float* __restrict__ ev, int B, int d, int dp, int DP, TcSched sch, int slotV, int slotW,
+                                                    uint32_t* __restrict__ zero_amax) {
+    __shared__ float tv[32][33], tw[32][33], t1[32][33], t2[32][33];
+    if (zero_amax != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3) zero_amax[TS_AMAX_A + threadIdx.x] = 0u;
     const int b0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int ns = tcs_nslots(sch, b0 >> 7);                    // the 32 examples of a block share a 128-example tile
     const size_t plane = (size_t)dp * B;
     for (int r = ty; r < 32; r += 8) {
         const int j = j0 + r, b = b0 + tx;
-        float v = 0.f, w = 0.f;
+        float v = 0.f, w = 0.f, c1 = 0.f, c2 = 0.f;
         if (j < d && b < B) {
             const size_t idx = (size_t)j * B + b;
             if (DP == 128) v = vT[idx] + vT[plane + idx];
@@ -662,16 +764,21 @@ __global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT
             } else {
                 for (int s = 0; s < 2 * ns; ++s) w += wT[(size_t)s * plane + idx];
             }
+            if (spT != nullptr) { c1 = spT[idx]; c2 = spT[plane + idx]; }
         }
         tv[r][tx] = v;
         tw[r][tx] = w;
+        t1[r][tx] = c1;
+        t2[r][tx] = c2;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int b = b0 + r, j = j0 + tx;
         if (b < B && j < d) {
-            ev[((size_t)b * E_NV + slotV) * dp + j] = tv[tx][r];
-            ev[((size_t)b * E_NV + slotW) * dp + j] = tw[tx][r];
+            float* e = ev + (size_t)b * E_NV * dp;
+            e[slotV * dp + j] = tv[tx][r];
+            e[slotW * dp + j] = tw[tx][r];
+            if (spT != nullptr) { e[E_C1 * dp + j] = t1[tx][r]; e[E_C2 * dp + j] = t2[tx][r]; }
         }
     }
 }
@@ -779,26 +886,84 @@ __device__ __forceinline__ void bwd_publish(const BwdBars& br, int as, int lane)
 }
 
 struct TcDqArgs {
-    const float4* bop2;     // Cf^T chunks [c32][hi/lo][8][NK]
+    const uint4* bop2;      // Cf^T stages [st][hi/lo][oct 0..15][NK] x 16 B (FP16 pairs, scaled by s_C)
     const float* sc;
     const float* aT; const float* LT; const float* RT; const float* cT; const float* Y2T;   // [dp][B] transposed a, L, R, c, Y2
     float* dqT;             // [slot][NK][B]  dq partial per segment slot, transposed (coalesced stores)
+    const uint32_t* scal;   // device scalars (TcScal): |max| of the dense tensors and of L, R, a, c, Y2
+    float g_bound;          // S / Z: upper bound of G1_b, G2_b (sums of S terms in (0, 1/Z))
     int B, d, dp, K, NK;
-    int n_bil_rows;         // reduction rows holding bilinear rows (a multiple of 64)
-    TcSched sch;            // units = SPR stages (one bilinear row for DP >= 64), tiles = example tiles
+    int n_bil_rows;         // reduction rows holding bilinear rows (a multiple of 128)
+    TcSched sch;            // units = stages of 128 reduction rows, tiles = example tiles
 };
 
-// dq: rows = examples.  Generator thread = (row b, column group cg of the stage's 64 reduction rows: columns 16 cg .. +15);
-// the R / Y2 values it needs for every bilinear stage are cached in registers (X, Y), a_bi / L_bi come coalesced from
-// the transposed copies, one row ahead of their use.
+// MMAs of one dq segment: 24 kind::f16 MMAs per stage (8 k-steps of 16 reduction rows x {hi.hi, hi.lo, lo.hi}); issued by ONE
+// elected thread, which takes the barrier waits of stage lt+1 in the middle of stage lt's MMAs (the pipe keeps queued work)
+__device__ __forceinline__ void dq_mma_segment(const BwdBars& br, uint8_t* smB, uint32_t ST_BYTES, int NK, uint32_t tmem_base, int nst,
+                                               int it0) {
+    TC_TRACE_INIT();
+    constexpr int NAS = TC_DQ_ASTAGES;
+    const uint32_t idesc = make_idesc_f16(TC_M, NK);
+    bool ready = false;
+    for (int lt = 0; lt < nst; ++lt) {
+        const int git = it0 + lt, s = git % TC_BSTAGES, as = git % NAS;
+        if (!ready) {
+            mbar_wait(&br.a_full[as], (git / NAS) & 1);
+            mbar_wait(&br.b_full[s], (git / TC_BSTAGES) & 1);
+            tc_fence_after();
+        }
+        ready = false;
+        if (git == 8) TC_TRACE(22);
+        if (git == 24) TC_TRACE(27);
+        const uint32_t a_hi = tmem_base + TC_BWD_ACOL + 128u * as, a_lo = a_hi + 64u;
+        const uint32_t b_base = smem_u32(smB + (size_t)s * ST_BYTES);
+        uint64_t dbh = make_desc(b_base, (uint32_t)NK * 16u, 128u);
+        uint64_t dbl = make_desc(b_base + 16u * (uint32_t)NK * 16u, (uint32_t)NK * 16u, 128u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            if (ks == 4 && lt + 1 < nst) {
+                const int g1 = git + 1;
+                mbar_wait(&br.a_full[g1 % NAS], (g1 / NAS) & 1);
+                mbar_wait(&br.b_full[g1 % TC_BSTAGES], (g1 / TC_BSTAGES) & 1);
+                tc_fence_after();
+                ready = true;
+            }
+            tc_mma_f16_ts(tmem_base, a_hi + 8u * ks, dbh, idesc, (lt > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_f16_ts(tmem_base, a_hi + 8u * ks, dbl, idesc, 1u);
+            tc_mma_f16_ts(tmem_base, a_lo + 8u * ks, dbh, idesc, 1u);
+            dbh = desc_advance(dbh, 2u * (uint32_t)NK * 16u);
+            dbl = desc_advance(dbl, 2u * (uint32_t)NK * 16u);
+        }
+        tc_commit(&br.a_empty[as]);
+        tc_commit(&br.b_empty[s]);
+        if (lt == nst - 1) tc_commit(br.acc_full);
+        if (git == 8) TC_TRACE(23);
+        if (git == 24) TC_TRACE(28);
+    }
+}
+
+// 16 generated (scaled) values -> FP16 hi / lo pairs of A stage `as`, packed columns col8 .. col8 + 7
+__device__ __forceinline__ void dq_store16(uint32_t lane_base, int as, int col8, const float (&g)[16]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) split_h2(g[2 * u], g[2 * u + 1], hi[u], lo[u]);
+    const uint32_t col = lane_base + TC_BWD_ACOL + 128u * as + (uint32_t)col8;
+    tc_st8u(col, hi);
+    tc_st8u(col + 64u, lo);
+}
+
+// dq: rows = examples, 128 reduction rows per stage.  Generator thread = (row b, column group cg: reduction rows 32 cg .. +31
+// of the stage = 16 packed TMEM columns); the R / Y2 values it needs for every bilinear stage are cached in registers
+// (X, Y), a_bi / L_bi come coalesced from the transposed copies, one stage ahead of their use.  Bilinear stage st holds
+// 128 / DP rows i: the thread's row is i = (128 / DP) st + (32 cg) / DP, its columns j = (32 cg) % DP + 0..31.
 template <int DP>
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
     constexpr int NAS = TC_DQ_ASTAGES;
-    constexpr int SPR = DP >= 64 ? DP / 64 : 1;             // stages per schedule unit (= per bilinear row for DP >= 64)
-    const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
+    constexpr int RPS = 128 / DP;                            // bilinear rows i per stage
+    const uint32_t ST_BYTES = 2u * 16u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
     uint32_t tmem_base;
     if (threadIdx.x == 0) { TC_TRACE(16); TC_TRACE_NS(30); }
@@ -814,33 +979,45 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
             TcSeg sg;
             int it = 0;
             while (si.next(sg)) {
-                const int st0 = sg.u0 * SPR, nst = (sg.u1 - sg.u0) * SPR;
-                bwd_produce(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), ST_BYTES, st0, nst, it);
-                it += nst;
+                bwd_produce(br, smB, reinterpret_cast<const uint8_t*>(p.bop2), ST_BYTES, sg.u0, sg.u1 - sg.u0, it);
+                it += sg.u1 - sg.u0;
             }
         }
     } else if (warp == 1) {
-        TcSegIter si(p.sch, blockIdx.x);
-        TcSeg sg;
-        int it = 0, seg = 0;
-        while (si.next(sg)) {
-            const int nst = (sg.u1 - sg.u0) * SPR;
-            if (seg > 0) {                                   // the previous segment's accumulator has been drained
-                mbar_wait(br.acc_empty, (seg - 1) & 1);
-                tc_fence_after();
+        if (elect_one()) {
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0, seg = 0;
+            while (si.next(sg)) {
+                if (seg > 0) {                                   // the previous segment's accumulator has been drained
+                    mbar_wait(br.acc_empty, (seg - 1) & 1);
+                    tc_fence_after();
+                }
+                dq_mma_segment(br, smB, ST_BYTES, p.NK, tmem_base, sg.u1 - sg.u0, it);
+                it += sg.u1 - sg.u0;
+                ++seg;
             }
-            bwd_mma_segment<NAS>(br, smB, ST_BYTES, p.NK, tmem_base, nst, it, 1, 16);
-            it += nst;
-            ++seg;
+            TC_TRACE(19);
         }
-        if (lane == 0) TC_TRACE(19);
+        __syncwarp();
     } else if (warp >= 4) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int gw = warp - 4, q4 = gw & 3, cg = gw >> 2;          // lane quarter, column group
         const int row = q4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        const int rsel = (DP == 32) ? (cg >> 1) : 0;                 // DP = 32: a stage holds two rows i
-        const int n_bil_st = p.n_bil_rows / TC_SR;
+        const int rsel = (32 * cg) / DP, j0 = (32 * cg) % DP;        // which of the stage's rows, first column
+        const int n_bil_st = p.n_bil_rows / TC_M;
+        // operand scale of the generated values: a power of two from a bound of |G| (triangle inequality over the |max| of
+        // the factors; G1_b, G2_b <= S / Z) and the scale of the dense operand, undone in the epilogue
+        float sG, inv;
+        {
+            const float aL = __uint_as_float(p.scal[TS_AMAX_L]), aR = __uint_as_float(p.scal[TS_AMAX_R]);
+            const float aA = __uint_as_float(p.scal[TS_AMAX_A]), aC = __uint_as_float(p.scal[TS_AMAX_CV]);
+            const float aY = __uint_as_float(p.scal[TS_AMAX_Y2]);
+            const float bound = fmaxf(fmaf(aA, aR, aL * aY), fmaxf(fmaf(p.g_bound, aL, aA), fmaf(p.g_bound, aR, aC)));
+            sG = pow2_scale(__float_as_uint(bound));
+            inv = 1.f / (sG * pow2_scale(p.scal[TS_AMAX_C]));
+        }
         TcSegIter si(p.sch, blockIdx.x);
         TcSeg sg;
         int it = 0, seg = 0;
@@ -848,76 +1025,68 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
             const int b = sg.tile * TC_M + row;
             const bool ok = b < p.B;
             const float* scb = p.sc + (size_t)(ok ? b : 0) * SC_N;
-            // register cache: stage h of a row needs j = jc(h) + 0..15 (coalesced loads from the transposed copies)
-            float X[SPR][16], Y[SPR][16];
+            // register cache of the thread's 32 columns of R and Y2 (coalesced loads from the transposed copies)
+            float X[32], Y[32];
 #pragma unroll
-            for (int h = 0; h < SPR; ++h) {
-                const int j = (DP == 32) ? 16 * (cg & 1) : 64 * h + 16 * cg;
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const bool in = ok && j + u < p.dp;
-                    X[h][u] = in ? p.RT[(size_t)(j + u) * p.B + b] : 0.f;
-                    Y[h][u] = in ? p.Y2T[(size_t)(j + u) * p.B + b] : 0.f;
-                }
+            for (int u = 0; u < 32; ++u) {
+                const bool in = ok && j0 + u < p.dp;
+                X[u] = in ? p.RT[(size_t)(j0 + u) * p.B + b] : 0.f;
+                Y[u] = in ? p.Y2T[(size_t)(j0 + u) * p.B + b] : 0.f;
             }
-            const int st0 = sg.u0 * SPR, st1 = sg.u1 * SPR, nst = st1 - st0;
-            // bilinear rows: segments start and end at row boundaries, so every row contributes its SPR stages in order
-            // (static indexing of the register cache).  a_bi / L_bi are loaded one row AHEAD of their use.
+            const int st0 = sg.u0, st1 = sg.u1, nst = st1 - st0;
             const int nbil = max(0, min(st1, n_bil_st) - st0);
-            int lt = 0;
             float ai_n = 0.f, li_n = 0.f;
             {
-                const int i = (DP == 32) ? 2 * st0 + rsel : st0 / SPR;
+                const int i = RPS * st0 + rsel;
                 if (nbil > 0 && ok && i < p.dp) {
                     ai_n = p.aT[(size_t)i * p.B + b];
                     li_n = p.LT[(size_t)i * p.B + b];
                 }
             }
-            for (int cs = st0; lt < nbil; cs += SPR) {
-                const float ai = ai_n, li = li_n;
-                const int i_next = (DP == 32) ? 2 * (cs + 1) + rsel : cs / SPR + 1;
-                const bool more = ok && i_next < p.dp && lt + SPR < nbil;
+            int lt = 0;
+            for (; lt < nbil; ++lt) {
+                const int git = it + lt, as = git % NAS;
+                const float ai = ai_n * sG, li = li_n * sG;
+                const int i_next = RPS * (st0 + lt + 1) + rsel;
+                const bool more = ok && i_next < p.dp && lt + 1 < nbil;
                 ai_n = more ? p.aT[(size_t)i_next * p.B + b] : 0.f;
                 li_n = more ? p.LT[(size_t)i_next * p.B + b] : 0.f;
-#pragma unroll
-                for (int h = 0; h < SPR; ++h, ++lt) {
-                    const int git = it + lt, as = git % NAS;
-                    float g0[8], g1[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        g0[u] = fmaf(ai, X[h][u], li * Y[h][u]);
-                        g1[u] = fmaf(ai, X[h][8 + u], li * Y[h][8 + u]);
-                    }
-                    const bool tr = gw == 0 && lane == 0 && git == 8;
-                    if (tr) TC_TRACE(24);
-                    mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
-                    tc_fence_after();
-                    if (tr) TC_TRACE(25);
-                    bwd_store8(lane_base, as, 16 * cg, g0);
-                    bwd_store8(lane_base, as, 16 * cg + 8, g1);
-                    bwd_publish(br, as, lane);
-                    if (tr) TC_TRACE(26);
-                }
-            }
-            // selectional-preference rows (a few stages per tile): direct loads
-            for (; lt < nst; ++lt) {
-                const int git = it + lt, as = git % NAS;
-                const int m = (st0 + lt) * TC_SR - p.n_bil_rows + 16 * cg;
-                const int which = m / DP, j0 = m - which * DP;
-                const float* sx = which == 0 ? p.aT : p.cT;
-                const float* sy = which == 0 ? p.LT : p.RT;
-                const float s2 = ok ? (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
-                float g0[8], g1[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const bool in0 = ok && which < 2 && j0 + u < p.dp, in1 = ok && which < 2 && j0 + 8 + u < p.dp;
-                    g0[u] = in0 ? fmaf(s2, sy[(size_t)(j0 + u) * p.B + b], sx[(size_t)(j0 + u) * p.B + b]) : 0.f;
-                    g1[u] = in1 ? fmaf(s2, sy[(size_t)(j0 + 8 + u) * p.B + b], sx[(size_t)(j0 + 8 + u) * p.B + b]) : 0.f;
-                }
+                const bool tr = gw == 0 && lane == 0 && git == 8;
+                if (tr) TC_TRACE(24);
                 mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
                 tc_fence_after();
-                bwd_store8(lane_base, as, 16 * cg, g0);
-                bwd_store8(lane_base, as, 16 * cg + 8, g1);
+                if (tr) TC_TRACE(25);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float g[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) g[u] = fmaf(ai, X[16 * h + u], li * Y[16 * h + u]);
+                    dq_store16(lane_base, as, 16 * cg + 8 * h, g);
+                }
+                bwd_publish(br, as, lane);
+                if (tr) TC_TRACE(26);
+            }
+            // selectional-preference rows (at most two stages per tile): coalesced loads from the transposed copies
+            for (; lt < nst; ++lt) {
+                const int git = it + lt, as = git % NAS;
+                const int m = (st0 + lt) * TC_M - p.n_bil_rows + 32 * cg;
+                const int which = m / DP, jj = m - which * DP;
+                const float* sx = which == 0 ? p.aT : p.cT;
+                const float* sy = which == 0 ? p.LT : p.RT;
+                const float s2 = (ok && which < 2) ? sG * (which == 0 ? scb[SC_G2] : scb[SC_G1]) : 0.f;
+                mbar_wait(&br.a_empty[as], ((git / NAS) & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float g[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int j = jj + 16 * h + u;
+                        const bool in = ok && which < 2 && j < p.dp;
+                        g[u] = in ? fmaf(s2, sy[(size_t)j * p.B + b], sG * sx[(size_t)j * p.B + b]) : 0.f;
+                    }
+                    dq_store16(lane_base, as, 16 * cg + 8 * h, g);
+                }
                 bwd_publish(br, as, lane);
             }
             it += nst;
@@ -932,7 +1101,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
                     if (ok) {
 #pragma unroll
                         for (int x = 0; x < 32; ++x)
-                            if (c0 + x < p.NK) o[(size_t)(c0 + x) * p.B] = t[x];
+                            if (c0 + x < p.NK) o[(size_t)(c0 + x) * p.B] = inv * t[x];
                     }
                 }
                 tc_fence_before();
@@ -995,7 +1164,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                     if (n0 < p.n_bil_rows) {
                         const int i = n0 / p.DP;
                         if (i < p.d) { v1 = p.aT[(size_t)i * p.B + b]; v2 = p.LT[(size_t)i * p.B + b]; }
-                    } else if (n0 < p.n_rows_total) {
+                    } else if (n0 < p.n_rows_total && (n0 - p.n_bil_rows) / p.DP < 2) {
                         v1 = 1.f;
                         v2 = p.sc[(size_t)b * SC_N + ((n0 - p.n_bil_rows) / p.DP == 0 ? SC_G2 : SC_G1)];
                     }
@@ -1058,7 +1227,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                 const int m = n - p.n_bil_rows;
                 const int which = m / p.DP;
                 j = m - which * p.DP;
-                if (j < p.d) type = 1 + which;
+                if (j < p.d && which < 2) type = 1 + which;
             }
             int oX = 0, oY = 0;
             if (type == 0) { oX = E_R * p.dp + j; oY = E_Y2 * p.dp + j; }
@@ -1151,9 +1320,9 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
 }
 
 // per-example finishing of the backward: SP terms of dL/dR, dq (sum of the tile's slot partials) += entropy term, softmax
-// backward.  One CTA per 32 examples: the transposed dq partials dqT[slot][k][b] are read coalesced (lane = example) into a
-// shared tile, then one warp per example works on its row (4 examples per warp).
-__global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
+// backward.  One CTA of 32 warps per 32 examples: the transposed dq partials dqT[slot][k][b] are read coalesced (lane =
+// example) into a shared tile, then one warp per example works on its row.
+__global__ void __launch_bounds__(1024) k_tc_bwd_finish(float* __restrict__ ev, const float* __restrict__ sc, const float* __restrict__ q,
                                                        const float* __restrict__ logq, const float* __restrict__ dqT, float* __restrict__ dz,
                                                        float* __restrict__ dzsum_part, int B, int K, int NK, TcSched sch_dq, int d, int dp,
                                                        int hasSP, float ent_coef) {
@@ -1166,7 +1335,7 @@ __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, c
     {
         const int ns = tcs_nslots(sch_dq, b0 >> 7);
         const int b = b0 + lane;
-        for (int k = warp; k < K; k += 8) {
+        for (int k = warp; k < K; k += 32) {
             float v = 0.f;
             if (b < B)
                 for (int s = 0; s < ns; ++s) v += dqT[((size_t)s * NK + k) * B + b];
@@ -1174,7 +1343,8 @@ __global__ void __launch_bounds__(256) k_tc_bwd_finish(float* __restrict__ ev, c
         }
     }
     __syncthreads();
-    for (int e = warp * 4; e < warp * 4 + 4; ++e) {
+    {
+        const int e = warp;
         const int b = b0 + e;
         if (b < B) {
             float* evb = ev + (size_t)b * E_NV * dp;
@@ -1277,35 +1447,37 @@ int tc_init(rae_engine* h) {
     const int DP = tc_dp(h->d);
     TcState& t = h->tc;
     t.DP = DP;
-    t.KQ = 2 * ((h->K + 7) / 8);
-    const int di = (DP == 32) ? ((h->d + 1) & ~1) : h->d;
+    t.KH = (h->K + 15) & ~15;
+    // bilinear rows i padded so that the operand rows fill whole 128-row stages (DP = 64: pairs of rows, DP = 32: fours)
+    const int rps = 128 / DP;
+    const int di = (h->d + rps - 1) / rps * rps;
     t.n_bil_rows = di * DP;
     t.n_bil_half = t.n_bil_rows / TC_H;
     t.n_sp_half = h->hasSP ? (2 * DP) / TC_H : 0;
-    t.n_rows_total = (t.n_bil_half + t.n_sp_half) * TC_H;
+    t.n_rows_total = (t.n_bil_rows + (h->hasSP ? 2 * DP : 0) + TC_M - 1) / TC_M * TC_M;
     t.n_chunks_fwd = (t.n_bil_half + t.n_sp_half + 1) / 2;
-    t.n_chunks_rec = (t.n_bil_half + 1) / 2;
+    t.n_chunks_rec = t.n_bil_half / 2;
     t.ntile = (h->B + TC_M - 1) / TC_M;
-    // forward: as many 128-row operand stages as fit (2 at K = 100: 106 KB each)
-    const size_t b_bytes = (size_t)2 * t.KQ * TC_N * 16;
+    // forward: as many 128-row operand stages as fit (4 at K = 100: 57 KB each)
+    const size_t b_bytes = (size_t)2 * (t.KH / 8) * TC_N * 16;
     t.fwd_stages = (int)std::min<size_t>(4, ((size_t)h->max_smem_optin - 256) / b_bytes);
     if (t.fwd_stages < 2) return fail(h, RAE_EINVAL, "tensor path: K=%d needs %zu bytes per operand stage, two do not fit", h->K, b_bytes);
     t.smem = (size_t)t.fwd_stages * b_bytes + 256;
     t.sch_fwd = make_sched(t.ntile, t.n_chunks_fwd, h->num_sms, 0);
     t.sch_rec = make_sched(t.ntile, t.n_chunks_rec, h->num_sms, 0);
     t.slots_vw = std::max(sched_max_slots(t.sch_fwd), sched_max_slots(t.sch_rec));
-    // backward operands: NK = relations padded to a multiple of 16, reduction stages of 64 rows (two 32-row chunks)
+    // backward operands: NK = relations padded to a multiple of 16.  dq reduces over stages of 128 operand rows (FP16
+    // pairs), dC over stages of 64 examples (TF32 pairs): both 2 * 2 * 8 * NK * 16 bytes per stage
     t.NK = (h->K + 15) & ~15;
-    const int SPR = DP >= 64 ? DP / 64 : 1;
-    const int n_st = t.n_rows_total / TC_SR;
+    const int n_st = t.n_rows_total / TC_M;
     // accuracy bound of the dq reduction: the measured-safe chain is 1560 MMAs into one accumulator (4.5e-6 of
     // ||dW||_inf at the target shape); a segment never exceeds TC_DQ_MAX_STAGES stages = 1536 MMAs
-    t.sch_dq = make_sched(t.ntile, n_st / SPR, h->num_sms, std::max(1, TC_DQ_MAX_STAGES / SPR));
+    t.sch_dq = make_sched(t.ntile, n_st, h->num_sms, TC_DQ_MAX_STAGES);
     t.slots_dq = sched_max_slots(t.sch_dq);
     const size_t st_bytes = (size_t)2 * 2 * 8 * t.NK * 16;
     t.smem_dq = (size_t)TC_BSTAGES * st_bytes + 256;
     if (t.smem_dq > (size_t)h->max_smem_optin) return fail(h, RAE_EINVAL, "tensor path: backward operand stages do not fit in shared memory");
-    t.n_ntiles = (t.n_rows_total + TC_M - 1) / TC_M;
+    t.n_ntiles = t.n_rows_total / TC_M;
     t.n_bst = (h->B + TC_SR - 1) / TC_SR;
     // dC: accuracy bound (see TC_DC_MAX_STAGES) and the capacity of the per-example scalar staging area
     t.dc_nacc = 2;
@@ -1317,18 +1489,20 @@ int tc_init(rae_engine* h) {
     t.slots_dc = sched_max_slots(t.sch_dc);
     t.smem_dc = t.smem_dq + (size_t)t.dc_share * per_stage;
     cudaError_t e;
+    const size_t vec = (size_t)h->dp * h->B * sizeof(float);
     if ((e = cudaMalloc((void**)&t.bop, (size_t)t.n_chunks_fwd * b_bytes)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.vT, (size_t)2 * h->B * h->dp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.wT, (size_t)2 * t.slots_vw * h->B * h->dp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.vT, 2 * vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.wT, 2 * t.slots_vw * vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.spT, 2 * vec)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.bop2, (size_t)n_st * st_bytes)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.dqT, (size_t)t.slots_dq * h->B * t.NK * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bst * st_bytes)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.qT, (size_t)4 * t.KQ * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.aT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.LT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.RT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.cT, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.Y2T, (size_t)h->dp * h->B * sizeof(float))) != cudaSuccess)
+        (e = cudaMalloc((void**)&t.qT, (size_t)t.KH * h->B * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.aT, vec)) != cudaSuccess || (e = cudaMalloc((void**)&t.LT, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.RT, vec)) != cudaSuccess || (e = cudaMalloc((void**)&t.cT, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.Y2T, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.scal, TS_N * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemset(t.scal, 0, TS_N * sizeof(uint32_t))) != cudaSuccess)
         return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
 #define RAE_TC_ATTR(KERN, BYTES)                                                                                     \
     if ((e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) \
@@ -1343,36 +1517,40 @@ int tc_init(rae_engine* h) {
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3);
+    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.spT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3); cudaFree(t.scal);
     cudaFree(t.qT); cudaFree(t.aT); cudaFree(t.LT); cudaFree(t.RT); cudaFree(t.cT); cudaFree(t.Y2T);
     t = TcState{};
 }
 
-// pre-split / pre-arrange the dense operands (call whenever C, C1, C2 changed, i.e. once per step)
+// pre-split / pre-arrange the dense operands (call whenever C, C1, C2 changed, i.e. once per step): |max| -> scale -> FP16 pairs
 int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    const size_t total = (size_t)t.n_chunks_fwd * TC_N * t.KQ;
+    RAE_CUDA(h, cudaMemsetAsync(t.scal + TS_AMAX_C, 0, sizeof(uint32_t), st));
+    const size_t dd = h->hasM ? (size_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (size_t)h->d * h->K : 0;
+    k_tc_absmax<<<h->num_sms, 256, 0, st>>>(h->P[RAE_P_C], dd, h->P[RAE_P_C1], dk, h->P[RAE_P_C2], dk, t.scal + TS_AMAX_C);
+    const size_t total = (size_t)t.n_chunks_fwd * TC_N * (t.KH / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KQ, t.DP, t.n_bil_rows,
-                                                 t.n_chunks_fwd * TC_N, t.bop, t.NK, t.n_rows_total, t.bop2);
-    h->launches += 1;
+    k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KH / 8, t.DP, t.n_bil_rows,
+                                                 t.n_chunks_fwd * TC_N, reinterpret_cast<uint4*>(t.bop), t.NK, t.n_rows_total,
+                                                 reinterpret_cast<uint4*>(t.bop2), t.scal);
+    h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
 namespace {
-int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst, bool with_q, cudaStream_t st) {
+int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst, const int* amax_word, bool with_q, cudaStream_t st) {
     TcState& t = h->tc;
     TrJobs jobs{};
     jobs.B = h->B;
     int nj = 0, maxc = 0;
     for (int i = 0; i < n; ++i) {
-        jobs.j[nj++] = TrJob{h->ev + (size_t)slots[i] * h->dp, (size_t)E_NV * h->dp, h->d, h->dp, dst[i]};
+        jobs.j[nj++] = TrJob{h->ev + (size_t)slots[i] * h->dp, (size_t)E_NV * h->dp, h->d, h->dp, dst[i], t.scal + amax_word[i]};
         maxc = std::max(maxc, h->dp);
     }
     if (with_q) {
-        jobs.j[nj++] = TrJob{h->q, (size_t)h->K, h->K, 4 * t.KQ, t.qT};
-        maxc = std::max(maxc, 4 * t.KQ);
+        jobs.j[nj++] = TrJob{h->q, (size_t)h->K, h->K, h->K, t.qT, nullptr};
+        maxc = std::max(maxc, h->K);
     }
     k_tc_transpose<<<dim3((h->B + 31) / 32, (maxc + 31) / 32, nj), 256, 0, st>>>(jobs);
     h->launches++;
@@ -1388,12 +1566,13 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_qt<<<dim3(blocks3, 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
-                                                   h->quirk ? 1 : 0, h->ev);
+                                                   h->quirk ? 1 : 0, h->ev, t.scal);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     const int slots[2] = {E_L, E_R};
     float* const dst[2] = {t.LT, t.RT};
-    return tc_transpose_slots(h, 2, slots, dst, true, st);
+    const int words[2] = {TS_AMAX_L, TS_AMAX_R};
+    return tc_transpose_slots(h, 2, slots, dst, words, true, st);
 }
 
 // the q-dependent operand alone (only the dC contraction at the end of the step needs it: prepared off the critical path)
@@ -1403,7 +1582,7 @@ int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
-                                                   h->quirk ? 1 : 0, h->ev);
+                                                   h->quirk ? 1 : 0, h->ev, t.scal);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1414,8 +1593,8 @@ int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
 int tc_contract(rae_engine* h, const float* LT_in, const float* RT_in, int slotV, int slotW, bool with_sp, cudaStream_t st) {
     TcState& t = h->tc;
     TcArgs p{};
-    p.qT = t.qT; p.bop = t.bop; p.LT = LT_in; p.RT = RT_in; p.ev_out = h->ev; p.vT = t.vT; p.wT = t.wT;
-    p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KQ = t.KQ;
+    p.qT = t.qT; p.bop = t.bop; p.LT = LT_in; p.RT = RT_in; p.spT = t.spT; p.vT = t.vT; p.wT = t.wT; p.scal = t.scal;
+    p.B = h->B; p.K = h->K; p.d = h->d; p.dp = h->dp; p.KH = t.KH;
     p.n_bil_half = t.n_bil_half; p.n_sp_half = with_sp ? t.n_sp_half : 0;
     p.nbs = t.fwd_stages;
     p.sch = with_sp ? t.sch_fwd : t.sch_rec;
@@ -1423,7 +1602,8 @@ int tc_contract(rae_engine* h, const float* LT_in, const float* RT_in, int slotV
     else if (t.DP == 64) k_tc_bilinear<64><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
     else k_tc_bilinear<128><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
     RAE_CUDA(h, cudaGetLastError());
-    k_tc_combine<<<dim3((h->B + 31) / 32, (h->d + 31) / 32), 256, 0, st>>>(t.vT, t.wT, h->ev, h->B, h->d, h->dp, t.DP, p.sch, slotV, slotW);
+    k_tc_combine<<<dim3((h->B + 31) / 32, (h->d + 31) / 32), 256, 0, st>>>(t.vT, t.wT, (with_sp && h->hasSP) ? t.spT : nullptr, h->ev, h->B, h->d,
+                                                                          h->dp, t.DP, p.sch, slotV, slotW, with_sp ? t.scal : nullptr);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1438,7 +1618,8 @@ int tc_backward_recompute(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     const int slots[3] = {E_A, E_CV, E_Y2};
     float* const dst[3] = {t.aT, t.cT, t.Y2T};
-    int rc = tc_transpose_slots(h, 3, slots, dst, false, st);
+    const int words[3] = {TS_AMAX_A, TS_AMAX_CV, TS_AMAX_Y2};
+    int rc = tc_transpose_slots(h, 3, slots, dst, words, false, st);
     if (rc) return rc;
     return tc_contract(h, t.aT, t.cT, E_GA1, E_GA2, false, st);
 }
@@ -1446,7 +1627,8 @@ int tc_backward_recompute(rae_engine* h, cudaStream_t st) {
 int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     TcDqArgs p{};
-    p.bop2 = t.bop2; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.RT = t.RT; p.cT = t.cT; p.Y2T = t.Y2T; p.dqT = t.dqT;
+    p.bop2 = reinterpret_cast<const uint4*>(t.bop2); p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.RT = t.RT; p.cT = t.cT; p.Y2T = t.Y2T;
+    p.dqT = t.dqT; p.scal = t.scal; p.g_bound = (float)((double)h->S / h->Z);
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
     p.n_bil_rows = t.n_bil_rows;
     p.sch = t.sch_dq;
@@ -1464,7 +1646,7 @@ int tc_backward_finish(rae_engine* h, cudaStream_t st) {
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
     const size_t smem = sizeof(float) * 32 * ((size_t)(h->K | 1) + h->K);
-    k_tc_bwd_finish<<<blocks, 256, smem, st>>>(h->ev, h->sc, h->q, h->logq, t.dqT, h->dz, h->dzsum_part, h->B, h->K, t.NK, t.sch_dq,
+    k_tc_bwd_finish<<<blocks, 1024, smem, st>>>(h->ev, h->sc, h->q, h->logq, t.dqT, h->dz, h->dzsum_part, h->B, h->K, t.NK, t.sch_dq,
                                                h->d, h->dp, h->hasSP ? 1 : 0, (float)(2.0 * h->cfg.alpha / h->Z));
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());

@@ -313,8 +313,11 @@ int stage_host_negatives(rae_engine* h, const int32_t* neg1_host, int64_t ld1, c
     *d1_out = d1;
     *d2_out = d2;
     if (n == 0) return RAE_OK;
+    h->neg_direct = false;
     if (is_pinned_host(neg1_host) && is_pinned_host(neg2_host)) {
-        // page-locked caller memory: strided rows straight to the device, no host staging
+        // page-locked caller memory: strided rows straight to the device, no host staging (the copy reads the CALLER's
+        // buffer asynchronously: rae_train_step_host_ld waits for it before returning when no cost read does so already)
+        h->neg_direct = true;
         RAE_CUDA(h, cudaMemcpy2DAsync(d1, row, neg1_host, sizeof(int32_t) * (size_t)ld1, row, h->S, cudaMemcpyHostToDevice, sc));
         RAE_CUDA(h, cudaMemcpy2DAsync(d2, row, neg2_host, sizeof(int32_t) * (size_t)ld2, row, h->S, cudaMemcpyHostToDevice, sc));
     } else {
@@ -439,8 +442,9 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     RAE_CREATE_RC(dev_alloc(h, &h->cost_dev, 1));
     RAE_CREATE_CUDA(cudaMallocHost((void**)&h->cost_pinned, 4 * sizeof(double)));
     memset(h->cost_pinned, 0, 4 * sizeof(double));
-    h->gcost_pinned = h->cost_pinned + 1;                                  // same page-locked block: [cost | global cost | flag]
+    h->gcost_pinned = h->cost_pinned + 1;                                  // same page-locked block: [cost | global cost | flag | barrier status]
     h->neg_err_pinned = reinterpret_cast<int32_t*>(h->cost_pinned + 2);
+    h->peer_err_pinned = reinterpret_cast<int32_t*>(h->cost_pinned + 3);
     h->n_dz_part = h->B;   // upper bound on CTAs of the backward kernel (>= 8 examples per CTA)
     RAE_CREATE_RC(dev_alloc(h, &h->dzsum_part, (size_t)h->n_dz_part * h->K));
     const int64_t dd = h->hasM ? (int64_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (int64_t)h->d * h->K : 0;
@@ -633,6 +637,9 @@ int rae_train_step_host_ld(rae_engine* h, int64_t batch_index, const int32_t* ne
     rc = train_batch(h, batch_index, d1, d2, h->B, st);
     h->neg_wait = nullptr;
     if (rc) return rc;
+    // the caller may reuse its negative arrays as soon as this returns (the next epoch's sampler does): with a cost read
+    // the wait below is implied (the cost follows the scoring kernel, which follows the copy), without one it is explicit
+    if (cost_host == nullptr && h->neg_direct && h->S > 0) RAE_CUDA(h, cudaEventSynchronize(h->ev_neg));
     return finish_cost(h, cost_host, st);
 }
 

@@ -83,7 +83,7 @@ __host__ __device__ __forceinline__ int tcs_nslots(TcSched s, int tile) {
 struct TcState {
     bool ready = false;
     int DP = 0;            // columns per row of M, padded: 32 / 64 / 128
-    int KQ = 0;            // float4 planes along the relation axis (K padded to a multiple of 8, / 4)
+    int KH = 0;            // relations padded to a multiple of 16 (kind::f16 MMA depth)
     // operand rows n of Cf = [C rows (i, j) | C1 rows | C2 rows] in half chunks of 64 rows
     int n_bil_rows = 0, n_bil_half = 0, n_sp_half = 0;
     int n_rows_total = 0;  // (n_bil_half + n_sp_half) * 64: reduction length of dq, operand rows of dC
@@ -97,6 +97,8 @@ struct TcState {
     float4* bop = nullptr; // forward B operand chunks [chunk][hi/lo][KQ][128]
     float* vT = nullptr;   // [2][dp][B]            v partials, transposed (lane = example)
     float* wT = nullptr;   // [slots_vw][2][dp][B]  w partials, transposed
+    float* spT = nullptr;  // [2][dp][B]            c1, c2, transposed
+    uint32_t* scal = nullptr;   // device scalars: |max| words of the FP16 operand scales (rae_decoder_tc.cu: TcScal)
     int NK = 0; size_t smem_dq = 0, smem_dc = 0;
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
     float* dqT = nullptr;   // [slots_dq][NK][B]  dq partials, transposed
@@ -157,8 +159,10 @@ struct rae_engine {
     cudaEvent_t neg_wait;       // host-negatives copy in flight on a side stream: the scoring kernel waits for it
     bool cost_on_event;         // the last step recorded ev_cost behind its cost kernel
     bool neg_staged;            // ev_neg has been recorded at least once (pinned_neg may still be in flight)
+    bool neg_direct;            // the last host-negatives copy read the caller's page-locked arrays in place
     int stage_flip;             // which half of the double-buffered device staging the next host step fills
     int barrier_epoch; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
+    int32_t* peer_err_pinned;                      // page-locked copy of the status word: checked by every rae_dist_* call
     cudaEvent_t pending_wait;                      // if set: the step's main stream waits for it before the decoder reads A
     // explicit-step staging
     int32_t* stage_neg;                          // device [2 (flip)][2 (neg1, neg2)][S,B]

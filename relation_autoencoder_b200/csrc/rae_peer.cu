@@ -82,7 +82,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) k_pull_apply(float* __restrict__ table, float* __restrict__ acc, int width,
                                                     const int32_t* __restrict__ rows_local, const int32_t* __restrict__ ent_off,
                                                     const int32_t* __restrict__ ent_src, const int32_t* __restrict__ ent_slot,
-                                                    int n_rows, PeerPtrs grads, float lr, int adagrad) {
+                                                    int n_rows, PeerPtrs grads, float lr, int adagrad, const int32_t* __restrict__ abort) {
+    if (*abort != 0) return;      // a peer barrier of this handle timed out: the peers' gradient rows may be stale
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(256) k_pull_apply_scalars(float* __restrict__ 
                                                             const int32_t* __restrict__ rows_local,
                                                             const int32_t* __restrict__ ent_off, const int32_t* __restrict__ ent_src,
                                                             const int32_t* __restrict__ ent_slot, int n_rows, PeerPtrs grads,
-                                                            float lr, int adagrad) {
+                                                            float lr, int adagrad, const int32_t* __restrict__ abort) {
+    if (*abort != 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
         float g = 0.f;
         const int e1 = ent_off[i + 1];
@@ -193,15 +195,18 @@ __global__ void __launch_bounds__(256) k_pull_apply_scalars(float* __restrict__ 
 // One warp.  Lane r publishes `epoch` in rank r's flag word [my rank] (release, system scope: everything this GPU wrote
 // before - emitted gradient rows, updated table rows - is visible to a peer that observes the flag) and then waits until
 // rank r has published >= epoch in OUR word [r] (acquire).  Epochs only grow, so a rank that is already one barrier ahead
-// still satisfies the wait.  The spin is bounded (~2 s): on timeout the status word is set and the kernel returns.
+// still satisfies the wait.  The spin is bounded (~2 s).  A timeout is FATAL for the handle: the device status word makes
+// every later owner-side kernel (pulls, peer dense update) return without touching the tables - the peers' buffers may not
+// be emitted yet - and the page-locked copy makes the next rae_dist_* / rae_peer_* call on the host fail.
 struct FlagPtrs {
     int32_t* p[RAE_MAX_PEERS];
 };
 
-__global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, int32_t* __restrict__ status) {
+__global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, int32_t* __restrict__ status,
+                               volatile int32_t* __restrict__ status_host) {
     const int r = threadIdx.x;
     __threadfence_system();
-    if (r < world) {
+    if (r < world && *status == 0) {
         int32_t* dst = flags.p[r] + rank;
         asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
         const int32_t* src = flags.p[rank] + r;
@@ -212,6 +217,7 @@ __global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, i
             if (v >= epoch) break;
             if (clock64() - t0 > 4000000000LL) {
                 *status = 1;
+                *status_host = 1;
                 break;
             }
         }
@@ -257,7 +263,8 @@ struct DenseSeg { float* p; float* acc; size_t begin, end; };      // [begin, en
 struct DenseSegs { DenseSeg s[4]; int count; };
 
 __global__ void __launch_bounds__(256) k_dense_apply_peers(DenseSegs segs, PeerPtrs grads, int world, size_t n, float* __restrict__ sum_out,
-                                                           float lr, int adagrad) {
+                                                           float lr, int adagrad, const int32_t* __restrict__ abort) {
+    if (*abort != 0) return;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float x[RAE_MAX_PEERS];
 #pragma unroll
@@ -327,17 +334,24 @@ int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, co
     const int adagrad = h->adagrad ? 1 : 0;
     if (width == 1) {
         const int blocks = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)h->num_sms * 8);
-        k_pull_apply_scalars<<<blocks, 256, 0, st>>>(table, acc, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad);
+        k_pull_apply_scalars<<<blocks, 256, 0, st>>>(table, acc, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
     } else {
         const int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)h->num_sms * 16);
         if ((width & 3) == 0)
-            k_pull_apply<true><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad);
+            k_pull_apply<true><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
         else
-            k_pull_apply<false><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad);
+            k_pull_apply<false><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
     }
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
+}
+
+// a peer barrier of this handle has timed out (seen through the page-locked status word): every later call fails
+int peer_failed(rae_engine* h) {
+    if (*(volatile int32_t*)h->peer_err_pinned == 0) return RAE_OK;
+    return fail(h, RAE_ECUDA, "a peer barrier timed out: a rank of the node did not arrive within ~2 s; the sharded tables were left "
+                              "untouched from that step on - the run cannot continue");
 }
 
 int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st) {
@@ -349,7 +363,7 @@ int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, 
         fp.p[r] = static_cast<int32_t*>(const_cast<void*>(flag_bufs[r]));
     }
     h->barrier_epoch += 1;
-    k_peer_barrier<<<1, 32, 0, st>>>(fp, rank, world, h->barrier_epoch, h->peer_err_dev);
+    k_peer_barrier<<<1, 32, 0, st>>>(fp, rank, world, h->barrier_epoch, h->peer_err_dev, h->peer_err_pinned);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -373,7 +387,7 @@ int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int w
     add(RAE_P_WB, h->off_gWb, h->K);
     const size_t n = (size_t)h->n_dense;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 8);
-    k_dense_apply_peers<<<blocks, 256, 0, st>>>(segs, pp, world, n, nullptr, (float)h->cfg.lr, h->adagrad ? 1 : 0);
+    k_dense_apply_peers<<<blocks, 256, 0, st>>>(segs, pp, world, n, nullptr, (float)h->cfg.lr, h->adagrad ? 1 : 0, h->peer_err_dev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -460,11 +474,12 @@ int rae_peer_status(rae_engine* h, void* stream) {
     RAE_CUDA(h, cudaMemcpyAsync(&v, h->peer_err_dev, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     RAE_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
     if (v != 0) return fail(h, RAE_ECUDA, "a peer barrier timed out: a rank of the node did not arrive");
-    return RAE_OK;
+    return peer_failed(h);
 }
 
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_begin: null argument");
+    if (peer_failed(h)) return RAE_ECUDA;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool side = h->s1 != nullptr && !h->profiling;
@@ -508,6 +523,7 @@ int rae_dist_read_cost(rae_engine* h, double* cost_host) {
     if (!h || !cost_host) return fail(h, RAE_EINVAL, "rae_dist_read_cost: null argument");
     if (!h->gcost_pending) return fail(h, RAE_ENOTBOUND, "rae_dist_read_cost: no step with global_cost set has been issued");
     RAE_CUDA(h, cudaEventSynchronize(h->ev_gcost));
+    if (peer_failed(h)) return RAE_ECUDA;
     *cost_host = *(volatile double*)h->gcost_pinned;
     if (*(volatile int32_t*)h->neg_err_pinned != 0) {
         *(volatile int32_t*)h->neg_err_pinned = 0;
@@ -518,6 +534,7 @@ int rae_dist_read_cost(rae_engine* h, double* cost_host) {
 
 int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_end: null argument");
+    if (peer_failed(h)) return RAE_ECUDA;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool flags = d->flag_bufs != nullptr;
