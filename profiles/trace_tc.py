@@ -33,13 +33,35 @@ buf = torch.zeros(NCTA * 64, dtype=torch.int64, device="cuda")
 lib = C.CDLL(L.LIB_PATH)
 lib.rae_debug_set_trace.argtypes = [C.c_void_p]
 assert lib.rae_debug_set_trace(C.c_void_p(buf.data_ptr())) == 0
+# knock-out runs (measurement build only; results are garbage, timing is the point): per-kernel wall time and median CTA cycles
+if os.environ.get("TRACE_KNOCK"):
+    print("knock-out runs: 1 = no operand copies after the first fills, 2 = no MMAs, 4 = no epilogue / generator arithmetic")
+    for bits in (0, 1, 2, 4, 3, 6, 7):
+        lib.rae_debug_set_knock(bits)
+        buf.zero_()
+        eng.train_device(4, want_cost=False)
+        torch.cuda.synchronize()
+        tk = buf.cpu().numpy().reshape(NCTA, 64)
+        row = []
+        for kname, base in (("fwd/rec", 0), ("dq", 16), ("dC", 32)):
+            live = [c for c in range(NCTA) if tk[c, base] != 0]
+            if live:
+                wall = (max(tk[c, base + 15] for c in live) - min(tk[c, base + 14] for c in live)) / 1e3
+                med = int(np.median([tk[c, base + 5] - tk[c, base] for c in live]))
+                row.append("%s %.1f us / %d cyc" % (kname, wall, med))
+        print("  knock %d: %s" % (bits, "; ".join(row)))
+    lib.rae_debug_set_knock(0)
+    buf.zero_()
+    # the knocked-out steps leave garbage in the parameters: timing only from here on
 eng.train_device(4, want_cost=False)
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(NCTA, 64)
 KERNELS = {
-    "fwd/rec": (0, {0: "entry", 1: "setup done", 2: "first P in TMEM", 6: "mma c4 ready", 7: "mma c4 issued", 10: "mma c12 ready",
-                    11: "mma c12 issued", 9: "first segment epilogue done", 3: "all MMAs issued", 4: "epilogue done", 5: "exit"}),
-    "dq": (16, {16: "entry", 17: "setup done", 22: "mma s8 ready", 23: "mma s8 issued", 27: "mma s24 ready", 28: "mma s24 issued",
+    "fwd/rec": (0, {0: "entry", 1: "setup done", 12: "q loads start", 13: "q loads done", 8: "R loads done", 2: "first P in TMEM", 6: "mma c4 ready", 7: "mma c4 issued", 10: "mma c12 ready",
+                    11: "mma c12 issued", 51: "mma c8 start", 48: "mma c8 mid: wait next t_empty", 49: "mma c8 mid: t_empty ok",
+                    50: "mma c8 mid: b_full ok", 52: "mma c9 start", 53: "epi c8 wait t_full", 54: "epi c8 t_full ok",
+                    55: "epi c8 arrived t_empty", 56: "epi c8 done", 9: "first segment epilogue done", 3: "all MMAs issued", 4: "epilogue done", 5: "exit"}),
+    "dq": (16, {16: "entry", 17: "setup done", 29: "X/Y loads done", 18: "stage 0 published", 22: "mma s8 ready", 23: "mma s8 issued", 27: "mma s24 ready", 28: "mma s24 issued",
                 24: "gen s8 computed", 25: "gen s8 slot acquired", 26: "gen s8 published", 19: "all MMAs issued", 20: "gen+drain done", 21: "exit"}),
     "dC": (32, {32: "entry", 33: "staging+setup done", 38: "mma s8 ready", 39: "mma s8 issued", 43: "mma s24 ready", 44: "mma s24 issued",
                 40: "gen s8 wait slot", 41: "gen s8 slot acquired", 42: "gen s8 published", 35: "all MMAs issued", 36: "gen+drain done", 37: "exit"}),
