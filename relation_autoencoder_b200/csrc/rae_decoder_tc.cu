@@ -326,9 +326,21 @@ __global__ void __launch_bounds__(256) k_tc_absmax(const float* __restrict__ C, 
     __shared__ uint32_t red[8];
     uint32_t m = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = t0; i < nC; i += stride) m = max(m, __float_as_uint(fabsf(C[i])));
-    for (size_t i = t0; i < n1; i += stride) m = max(m, __float_as_uint(fabsf(C1[i])));
-    for (size_t i = t0; i < n2; i += stride) m = max(m, __float_as_uint(fabsf(C2[i])));
+    auto scan = [&](const float* p, size_t n) {
+        if (p == nullptr || n == 0) return;
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            for (size_t i = t0; i < n / 4; i += stride) {
+                const float4 v = p4[i];
+                m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+            }
+        } else {
+            for (size_t i = t0; i < n; i += stride) m = max(m, __float_as_uint(fabsf(p[i])));
+        }
+    };
+    scan(C, nC);
+    scan(C1, n1);
+    scan(C2, n2);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -395,8 +407,30 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
 __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q, int B, int K, int NK, int nbc, float4* __restrict__ out,
                                                     const float* __restrict__ A, const int32_t* __restrict__ a1,
                                                     const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev,
-                                                    uint32_t* __restrict__ scal) {
+                                                    uint32_t* __restrict__ scal, uint4* __restrict__ out4) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) scal[TS_AMAX_L + threadIdx.x] = 0u;   // the transposes that follow accumulate
+    if (blockIdx.y == 2) {
+        // FP16 pair operand of the two-tile dC kernel: [stage of 64 examples][hi/lo][oct 0..7][krow 0..NK-1] x 16 B = examples
+        // 64 st + 8 oct + 0..7 at relation krow, q scaled by 2^12
+        const size_t total4 = (size_t)(nbc / 2) * 8 * NK;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (size_t)gridDim.x * blockDim.x) {
+            const int krow = (int)(idx % NK);
+            const int oct = (int)((idx / NK) % 8);
+            const int st = (int)(idx / ((size_t)8 * NK));
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = st * 64 + 8 * oct + 2 * u;
+                const float x0 = (b < B && krow < K) ? q[(size_t)b * K + krow] * TC_QSCALE : 0.f;
+                const float x1 = (b + 1 < B && krow < K) ? q[(size_t)(b + 1) * K + krow] * TC_QSCALE : 0.f;
+                split_h2(x0, x1, hi[u], lo[u]);
+            }
+            uint4* base = out4 + (size_t)st * 2 * 8 * NK;
+            base[(size_t)oct * NK + krow] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            base[(size_t)(8 + oct) * NK + krow] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        return;
+    }
     if (blockIdx.y == 1) {
         const int lane = threadIdx.x & 31;
         for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
@@ -755,7 +789,11 @@ constexpr int TC_DQ_MAX_STAGES = 64;   // dq: stages (of 64 reduction rows) per 
 // tiled transposes: job z copies src[b * stride + c] (b < B, c < cols) to dst[c * B + b], zero rows for cols <= c < cols_out,
 // and folds |max| of the job's values into *amax (bits of a non-negative float; nullptr: skip).  They give the contraction
 // kernels their [column][example] views (lane = example reads are coalesced) and the scales of the FP16 operands.
-struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; uint32_t* amax; };
+// img != 0: the destination is a stack of STAGE IMAGES [b / 64][c < cols_out][TC_IMG_LD] (64 examples per row, padded to 68
+// floats so that 16-byte shared-memory reads of consecutive rows are conflict-free): one contiguous block per stage that the
+// dC kernel fetches with a single bulk copy
+constexpr int TC_IMG_LD = 68;
+struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; uint32_t* amax; int img; };
 struct TrJobs { TrJob j[4]; int B; };
 __global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
     __shared__ float tile[32][33];
@@ -779,7 +817,10 @@ __global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int c = c0 + r, b = b0 + tx;
-        if (c < jb.cols_out && b < jobs.B) jb.dst[(size_t)c * jobs.B + b] = tile[tx][r];
+        if (c < jb.cols_out && b < jobs.B) {
+            if (jb.img) jb.dst[((size_t)(b >> 6) * jb.cols_out + c) * TC_IMG_LD + (b & 63)] = tile[tx][r];
+            else jb.dst[(size_t)c * jobs.B + b] = tile[tx][r];
+        }
     }
     if (jb.amax != nullptr && threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) m = max(m, red[w]);
@@ -801,21 +842,27 @@ __global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int ns = tcs_nslots(sch, b0 >> 7);                    // the 32 examples of a block share a 128-example tile
     const size_t plane = (size_t)dp * B;
+    constexpr int MAXP = 16;                                    // partial planes summed per element (slots x groups)
     for (int r = ty; r < 32; r += 8) {
         const int j = j0 + r, b = b0 + tx;
         float v = 0.f, w = 0.f, c1 = 0.f, c2 = 0.f;
         if (j < d && b < B) {
             const size_t idx = (size_t)j * B + b;
-            if (DP == 128) v = vT[idx] + vT[plane + idx];
-            else if (DP == 64) v = vT[(size_t)(j & 1) * plane + idx];
-            else v = vT[(size_t)((j >> 1) & 1) * plane + idx];
-            if (DP == 128) {
-                const int g = j >> 6;
-                for (int s = 0; s < ns; ++s) w += wT[(size_t)(2 * s + g) * plane + idx];
-            } else {
-                for (int s = 0; s < 2 * ns; ++s) w += wT[(size_t)s * plane + idx];
-            }
+            // every load of the element is issued before the first add (one memory latency, not one per slot)
+            float v0, v1 = 0.f;
+            if (DP == 128) { v0 = vT[idx]; v1 = vT[plane + idx]; }
+            else if (DP == 64) v0 = vT[(size_t)(j & 1) * plane + idx];
+            else v0 = vT[(size_t)((j >> 1) & 1) * plane + idx];
+            const int np = DP == 128 ? ns : 2 * ns;                     // planes of wT that hold column j
+            const int first = DP == 128 ? (j >> 6) : 0, step = DP == 128 ? 2 : 1;
+            float wv[MAXP];
+#pragma unroll
+            for (int s = 0; s < MAXP; ++s) wv[s] = s < np ? wT[(size_t)(first + step * s) * plane + idx] : 0.f;
+            for (int s = MAXP; s < np; ++s) w += wT[(size_t)(first + step * s) * plane + idx];      // (more than 16 planes: tiny tiles only)
             if (spT != nullptr) { c1 = spT[idx]; c2 = spT[plane + idx]; }
+            v = v0 + v1;
+#pragma unroll
+            for (int s = 0; s < MAXP; ++s) w += wv[s];
         }
         tv[r][tx] = v;
         tw[r][tx] = w;
@@ -1193,8 +1240,9 @@ struct TcDcArgs {
     int n_bil_rows, n_rows_total, hasM;
     int nacc;               // TMEM accumulators the example stages are dealt over (1 or 2)
     int share;              // most stages one CTA handles (sizes the per-example scalar staging)
+    int tile0;              // first 128-row tile this launch covers (the C1 / C2 tiles when k_tc_dc2 takes the bilinear rows)
     size_t split_stride;    // units*d*K
-    TcSched sch;            // units = stages of 64 examples, tiles = 128-row tiles of the operand rows
+    TcSched sch;            // units = stages of 64 examples, tiles = 128-row tiles of the operand rows (from tile0 on)
 };
 
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
@@ -1221,7 +1269,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
             for (int idx = threadIdx.x; idx < nsrc * ne; idx += blockDim.x) {
                 const int src = idx / ne, bl = idx - src * ne;
                 const int b = sg.u0 * TC_SR + bl;
-                const int n0 = sg.tile * TC_M + src * p.DP;
+                const int n0 = (sg.tile + p.tile0) * TC_M + src * p.DP;
                 float v1 = 0.f, v2 = 0.f;
                 if (b < p.B) {
                     if (n0 < p.n_bil_rows) {
@@ -1280,7 +1328,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
         TcSeg sg;
         int it = 0, seg = 0, off = 0;
         while (si.next(sg)) {
-            const int n = sg.tile * TC_M + row;
+            const int n = (sg.tile + p.tile0) * TC_M + row;
             // decode the row once: g(b) = P1(b) * X(b) + P2(b) * Y(b)
             int type = -1, i = 0, j = 0;          // -1: padding row (zero)
             if (n < p.n_bil_rows) {
@@ -1368,6 +1416,301 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(br.acc_empty);
+            }
+            ++seg;
+        }
+        if (gw == 0 && lane == 0) TC_TRACE(36);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { TC_TRACE(37); TC_TRACE_NS(47); }
+    if (warp == TC_BWD_WORKERS + 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dC of the bilinear rows, FP16 pairs, TWO 128-row tiles per CTA (rows n of tiles 2 tp and 2 tp + 1: the same columns j,
+// different rows i): every R_bj / Y2_bj the generators read serves both tiles, and nothing in the loop is a per-thread
+// global load - the one-tile kernel above spent its time on lane-strided L2 reads (47 % of the MMA floor, in-kernel trace).
+//   per stage of 64 examples: bulk copies bring the stage images of R and Y2 ([j][64 examples], rows padded to 68 floats),
+//   the per-example scalars a_bi, L_bi of the tiles' rows i (64 floats each, straight from the transposed copies) and the
+//   q^T operand stage into shared memory; generator thread = (tile row n_l = lane + 32 q4, example group cg): 16 examples
+//   per stage, both tiles; TMEM: accumulators [0,128) (tile A) and [128,256) (tile B), A stage s: tile t at
+//   [256 + 128 s + 64 t, +64) = 32 packed hi + 32 packed lo columns.  One accumulator per tile: a segment never exceeds
+//   TC_DC2_MAX_STAGES stages = 384 MMAs per accumulator (the chain bound of profiles/r01_accum_chain.md).
+// Needs B % 4 == 0 (16-byte aligned slices of the transposed copies); other batches and the C1 / C2 rows use k_tc_dc.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TC_DC2_BSTAGES = 3;      // q^T operand stages (28 KB each at K = 100)
+constexpr int TC_DC2_XSTAGES = 2;      // image stages (R, Y2: 34 KB each at d = 128, + scalars)
+constexpr int TC_DC2_MAX_STAGES = 32;
+constexpr uint32_t TC_DC2_ACOL = 256;
+
+struct TcDc2Args {
+    const uint4* pop4;      // q^T stages [st][hi/lo][oct 0..7][NK] x 16 B
+    const float* Rimg; const float* Yimg;     // stage images [st][j < DP][TC_IMG_LD]
+    const float* aT; const float* LT;         // [dp][B] (+ 64 floats of slack)
+    float* out;             // gC_part [slot][units*d*K]
+    const uint32_t* scal; float g_bound;
+    int B, d, dp, K, NK, DP;
+    int n_bil_tiles;
+    size_t split_stride;
+    TcSched sch;            // units = stages of 64 examples, tiles = PAIRS of 128-row tiles
+};
+
+__global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc2(TcDc2Args p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_TRACE_INIT();
+    const int DP = p.DP, nsrc = TC_M / DP;
+    const uint32_t STB = 2u * 8u * (uint32_t)p.NK * 16u;                 // q^T operand stage
+    const uint32_t IMG = (uint32_t)DP * TC_IMG_LD * 4u;                  // one stage image
+    const uint32_t PAREA = 2u * (uint32_t)nsrc * 2u * 256u;              // [tile][source][a | L][64 examples]
+    const uint32_t XST = 2u * IMG + PAREA;
+    uint8_t* smB = smem_raw;
+    uint8_t* smX = smem_raw + TC_DC2_BSTAGES * STB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smX + TC_DC2_XSTAGES * XST);
+    uint64_t* a_full = bars;            // [2] 16 generator-warp arrivals
+    uint64_t* a_empty = bars + 2;       // [2] tcgen05.commit
+    uint64_t* b_full = bars + 4;        // [3] bulk-copy tx
+    uint64_t* b_empty = bars + 7;       // [3] tcgen05.commit
+    uint64_t* x_full = bars + 10;       // [2] bulk-copy tx
+    uint64_t* x_empty = bars + 12;      // [2] 16 generator-warp arrivals (their reads of the stage are done)
+    uint64_t* acc_full = bars + 14;
+    uint64_t* acc_empty = bars + 15;    // 4 drain-warp arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    if (threadIdx.x == 0) { TC_TRACE(32); TC_TRACE_NS(46); }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1); mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 16); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_BWD_WORKERS + 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(33);
+
+    if (warp >= TC_BWD_WORKERS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    }
+    if (warp == TC_BWD_WORKERS + 1) {
+        // ===== producer of the q^T operand ring =====
+        if (lane == 0) {
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0;
+            while (si.next(sg)) {
+                for (int st = sg.u0; st < sg.u1; ++st, ++it) {
+                    const int s = it % TC_DC2_BSTAGES;
+                    mbar_wait(&b_empty[s], ((it / TC_DC2_BSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(&b_full[s], STB);
+                    bulk_g2s(smB + (size_t)s * STB, reinterpret_cast<const uint8_t*>(p.pop4) + (size_t)st * STB, STB, &b_full[s]);
+                }
+            }
+        }
+    } else if (warp == TC_BWD_WORKERS + 3) {
+        // ===== producer of the image ring: R image, Y2 image, and the 64-example slices of a_i / L_i of the tiles' rows =====
+        if (lane == 0) {
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0;
+            while (si.next(sg)) {
+                const int i0 = (2 * sg.tile * TC_M) / DP;          // first row i of tile A; tile B starts nsrc rows later
+                for (int st = sg.u0; st < sg.u1; ++st, ++it) {
+                    const int xs = it % TC_DC2_XSTAGES;
+                    mbar_wait(&x_empty[xs], ((it / TC_DC2_XSTAGES) & 1) ^ 1);
+                    uint32_t bytes = 2u * IMG;
+                    for (int ts = 0; ts < 2 * nsrc; ++ts)
+                        if (i0 + ts < p.dp) bytes += 512u;
+                    mbar_expect_tx(&x_full[xs], bytes);
+                    uint8_t* dst = smX + (size_t)xs * XST;
+                    bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.Rimg) + (size_t)st * IMG, IMG, &x_full[xs]);
+                    bulk_g2s(dst + IMG, reinterpret_cast<const uint8_t*>(p.Yimg) + (size_t)st * IMG, IMG, &x_full[xs]);
+                    for (int ts = 0; ts < 2 * nsrc; ++ts) {
+                        const int i = i0 + ts;                  // (tile, source) -> row i
+                        if (i < p.dp) {
+                            bulk_g2s(dst + 2 * IMG + (size_t)ts * 512, p.aT + (size_t)i * p.B + (size_t)st * TC_SR, 256u, &x_full[xs]);
+                            bulk_g2s(dst + 2 * IMG + (size_t)ts * 512 + 256, p.LT + (size_t)i * p.B + (size_t)st * TC_SR, 256u, &x_full[xs]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == TC_BWD_WORKERS) {
+        // ===== MMA issuer: one elected thread, fully unrolled (see k_tc_bilinear) =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(TC_M, p.NK);
+            TcSegIter si(p.sch, blockIdx.x);
+            TcSeg sg;
+            int it = 0, seg = 0;
+            while (si.next(sg)) {
+                const bool hasB = 2 * sg.tile + 1 < p.n_bil_tiles;
+                const int nst = sg.u1 - sg.u0;
+                if (seg > 0) {                                   // the previous segment's accumulators have been drained
+                    mbar_wait(acc_empty, (seg - 1) & 1);
+                    tc_fence_after();
+                }
+                bool ready = false;
+                for (int lt = 0; lt < nst; ++lt) {
+                    const int git = it + lt, s = git % TC_DC2_BSTAGES, as = git & 1;
+                    if (!ready) {
+                        mbar_wait(&a_full[as], (git >> 1) & 1);
+                        mbar_wait(&b_full[s], (git / TC_DC2_BSTAGES) & 1);
+                        tc_fence_after();
+                    }
+                    ready = false;
+                    if (git == 8) TC_TRACE(38);
+                    if (git == 24) TC_TRACE(43);
+                    const uint32_t b_base = smem_u32(smB + (size_t)s * STB);
+                    const uint64_t h0 = make_desc(b_base, (uint32_t)p.NK * 16u, 128u);
+                    const uint64_t l0 = make_desc(b_base + 8u * (uint32_t)p.NK * 16u, (uint32_t)p.NK * 16u, 128u);
+                    const uint32_t a0 = tmem_base + TC_DC2_ACOL + 128u * as;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        if (t == 1) {
+                            if (lt + 1 < nst) {                  // the next stage's barriers, while this stage's MMAs are queued
+                                const int g1 = git + 1;
+                                mbar_wait(&a_full[g1 & 1], (g1 >> 1) & 1);
+                                mbar_wait(&b_full[g1 % TC_DC2_BSTAGES], (g1 / TC_DC2_BSTAGES) & 1);
+                                tc_fence_after();
+                                ready = true;
+                            }
+                            if (!hasB) break;
+                        }
+                        const uint32_t acc = tmem_base + 128u * t, at = a0 + 64u * t;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (TC_KNOCK(2)) continue;
+                            const uint64_t hk = desc_advance(h0, (uint32_t)ks * 2u * (uint32_t)p.NK * 16u);
+                            const uint64_t lk = desc_advance(l0, (uint32_t)ks * 2u * (uint32_t)p.NK * 16u);
+                            tc_mma_f16_ts(acc, at + 8u * ks, hk, idesc, (lt > 0 || ks > 0) ? 1u : 0u);
+                            tc_mma_f16_ts(acc, at + 8u * ks, lk, idesc, 1u);
+                            tc_mma_f16_ts(acc, at + 32u + 8u * ks, hk, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&a_empty[as]);
+                    tc_commit(&b_empty[s]);
+                    if (lt == nst - 1) tc_commit(acc_full);
+                    if (git == 8) TC_TRACE(39);
+                    if (git == 24) TC_TRACE(44);
+                }
+                it += nst;
+                ++seg;
+            }
+            TC_TRACE(35);
+        }
+        __syncwarp();
+    } else if (warp < TC_BWD_WORKERS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+        const int gw = warp, q4 = gw & 3, cg = gw >> 2;         // lane quarter; examples 16 cg .. 16 cg + 15 of a stage
+        const int nl = q4 * 32 + lane;                          // row of the tile
+        const int j = nl % DP, srcl = nl / DP;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float sG, inv;
+        {
+            const float aL = __uint_as_float(p.scal[TS_AMAX_L]), aR = __uint_as_float(p.scal[TS_AMAX_R]);
+            const float aA = __uint_as_float(p.scal[TS_AMAX_A]), aY = __uint_as_float(p.scal[TS_AMAX_Y2]);
+            sG = pow2_scale(__float_as_uint(fmaf(aA, aR, aL * aY)));
+            inv = 1.f / (sG * TC_QSCALE);
+        }
+        TcSegIter si(p.sch, blockIdx.x);
+        TcSeg sg;
+        int it = 0, seg = 0;
+        while (si.next(sg)) {
+            const bool hasB = 2 * sg.tile + 1 < p.n_bil_tiles;
+            const int iA = (2 * sg.tile * TC_M) / DP + srcl, iB = iA + nsrc;
+            const bool vA = iA < p.d && j < p.d, vB = hasB && iB < p.d && j < p.d;
+            const int nst = sg.u1 - sg.u0;
+            for (int lt = 0; lt < nst; ++lt) {
+                const int git = it + lt, xs = git & 1, as = git & 1;
+                const uint8_t* stg = smX + (size_t)xs * XST;
+                const float* Xr = reinterpret_cast<const float*>(stg) + (size_t)j * TC_IMG_LD + 16 * cg;
+                const float* Yr = reinterpret_cast<const float*>(stg + IMG) + (size_t)j * TC_IMG_LD + 16 * cg;
+                const float* Pa = reinterpret_cast<const float*>(stg + 2 * IMG) + (size_t)srcl * 128 + 16 * cg;     // tile A: [a | L]
+                const float* Pb = Pa + (size_t)nsrc * 128;                                                             // tile B
+                const bool tr = gw == 0 && lane == 0 && git == 8;
+                if (tr) TC_TRACE(40);
+                mbar_wait(&x_full[xs], (git >> 1) & 1);
+                if (tr) TC_TRACE(41);
+                const int b0 = (sg.u0 + lt) * TC_SR + 16 * cg;
+                const bool full = b0 + 16 <= p.B;
+                float x[16], y[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(Xr + 4 * v4), yv = *reinterpret_cast<const float4*>(Yr + 4 * v4);
+                    x[4 * v4] = xv.x * sG; x[4 * v4 + 1] = xv.y * sG; x[4 * v4 + 2] = xv.z * sG; x[4 * v4 + 3] = xv.w * sG;
+                    y[4 * v4] = yv.x * sG; y[4 * v4 + 1] = yv.y * sG; y[4 * v4 + 2] = yv.z * sG; y[4 * v4 + 3] = yv.w * sG;
+                }
+                float gA[16], gB[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const float4 a1 = *reinterpret_cast<const float4*>(Pa + 4 * v4), l1 = *reinterpret_cast<const float4*>(Pa + 64 + 4 * v4);
+                    const float4 a2 = *reinterpret_cast<const float4*>(Pb + 4 * v4), l2 = *reinterpret_cast<const float4*>(Pb + 64 + 4 * v4);
+                    const float pa[4] = {a1.x, a1.y, a1.z, a1.w}, pl[4] = {l1.x, l1.y, l1.z, l1.w};
+                    const float qa[4] = {a2.x, a2.y, a2.z, a2.w}, ql[4] = {l2.x, l2.y, l2.z, l2.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = 4 * v4 + u;
+                        const bool in = full || b0 + e < p.B;
+                        gA[e] = (vA && in && !TC_KNOCK(4)) ? fmaf(pa[u], x[e], pl[u] * y[e]) : 0.f;
+                        gB[e] = (vB && in && !TC_KNOCK(4)) ? fmaf(qa[u], x[e], ql[u] * y[e]) : 0.f;
+                    }
+                }
+                // this warp's reads of the image stage are done (the values above depend on every one of them)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_empty[xs]);
+                mbar_wait(&a_empty[as], ((git >> 1) & 1) ^ 1);
+                tc_fence_after();
+                {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) split_h2(gA[2 * u], gA[2 * u + 1], hi[u], lo[u]);
+                    const uint32_t col = lane_base + TC_DC2_ACOL + 128u * as + 8u * cg;
+                    tc_st8u(col, hi);
+                    tc_st8u(col + 32u, lo);
+                    if (hasB) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) split_h2(gB[2 * u], gB[2 * u + 1], hi[u], lo[u]);
+                        tc_st8u(col + 64u, hi);
+                        tc_st8u(col + 96u, lo);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
+                if (tr) TC_TRACE(42);
+            }
+            it += nst;
+            if (gw < 4) {
+                // ===== epilogue: both tiles' accumulator rows -> the segment's slot of the partial gradient =====
+                mbar_wait(acc_full, seg & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int i = t == 0 ? iA : iB;
+                    const bool valid = t == 0 ? vA : vB;
+                    if (t == 1 && !hasB) break;
+                    float* o = p.out + (size_t)sg.slot * p.split_stride + ((size_t)i * p.d + j) * p.K;
+                    for (int c0 = 0; c0 < p.NK; c0 += 32) {
+                        float tt[32];
+                        tc_ld32(lane_base + 128u * t + (uint32_t)c0, tt);
+#pragma unroll
+                        for (int xx = 0; xx < 32; ++xx) tt[xx] *= inv;
+                        if (valid) store_row32(o + c0, tt, p.K - c0, (p.K & 3) == 0);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
             }
             ++seg;
         }
@@ -1548,9 +1891,24 @@ int tc_init(rae_engine* h) {
     const size_t per_stage = (size_t)(TC_M / DP) * 2 * TC_SR * sizeof(float);
     const int cap = (int)(((size_t)h->max_smem_optin - t.smem_dq) / per_stage);
     if (cap < 1) return fail(h, RAE_EINVAL, "tensor path: no shared memory left for the dC staging area");
-    t.sch_dc = make_sched(t.n_ntiles, t.n_bst, h->num_sms, std::min(t.dc_nacc * TC_DC_MAX_STAGES, cap));
-    t.dc_share = sched_max_share(t.sch_dc);
-    t.slots_dc = sched_max_slots(t.sch_dc);
+    // the bilinear rows go to the two-tile FP16 kernel (needs 16-byte aligned slices of the transposed copies: B % 4 == 0);
+    // the C1 / C2 tiles - and everything when that kernel cannot run - to the one-tile kernel
+    const int n_bil_tiles = t.n_bil_rows / TC_M;
+    t.dc2 = (h->B % 4 == 0) && n_bil_tiles > 0;
+    t.smem_dc2 = (size_t)TC_DC2_BSTAGES * (2 * 8 * t.NK * 16) + (size_t)TC_DC2_XSTAGES * (2 * (size_t)DP * TC_IMG_LD * 4 + 2 * (TC_M / DP) * 2 * 256) + 256;
+    if (t.smem_dc2 > (size_t)h->max_smem_optin) t.dc2 = false;
+    t.dc_tile0 = t.dc2 ? n_bil_tiles : 0;
+    t.slots_dc = 1;
+    if (t.dc2) {
+        t.sch_dc2 = make_sched((n_bil_tiles + 1) / 2, t.n_bst, h->num_sms, TC_DC2_MAX_STAGES);
+        t.slots_dc = sched_max_slots(t.sch_dc2);
+    }
+    t.dc_tiles = t.n_ntiles - t.dc_tile0;                    // tiles left to the one-tile kernel (may be none: model A)
+    if (t.dc_tiles > 0) {
+        t.sch_dc = make_sched(t.dc_tiles, t.n_bst, h->num_sms, std::min(t.dc_nacc * TC_DC_MAX_STAGES, cap));
+        t.dc_share = sched_max_share(t.sch_dc);
+        t.slots_dc = std::max(t.slots_dc, sched_max_slots(t.sch_dc));
+    }
     t.smem_dc = t.smem_dq + (size_t)t.dc_share * per_stage;
     cudaError_t e;
     const size_t vec = (size_t)h->dp * h->B * sizeof(float);
@@ -1562,7 +1920,13 @@ int tc_init(rae_engine* h) {
         (e = cudaMalloc((void**)&t.dqT, (size_t)t.slots_dq * h->B * t.NK * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.pop3, (size_t)t.n_bst * st_bytes)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.qT, (size_t)t.KH * h->B * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&t.aT, vec)) != cudaSuccess || (e = cudaMalloc((void**)&t.LT, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.aT, vec + 256)) != cudaSuccess || (e = cudaMalloc((void**)&t.LT, vec + 256)) != cudaSuccess ||
+        (e = cudaMemset(t.aT, 0, vec + 256)) != cudaSuccess || (e = cudaMemset(t.LT, 0, vec + 256)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.pop4, (size_t)t.n_bst * 2 * 8 * t.NK * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.Rimg, (size_t)t.n_bst * DP * TC_IMG_LD * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&t.Yimg, (size_t)t.n_bst * DP * TC_IMG_LD * sizeof(float))) != cudaSuccess ||
+        (e = cudaMemset(t.Rimg, 0, (size_t)t.n_bst * DP * TC_IMG_LD * sizeof(float))) != cudaSuccess ||
+        (e = cudaMemset(t.Yimg, 0, (size_t)t.n_bst * DP * TC_IMG_LD * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.RT, vec)) != cudaSuccess || (e = cudaMalloc((void**)&t.cT, vec)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.Y2T, vec)) != cudaSuccess ||
         (e = cudaMalloc((void**)&t.scal, TS_N * sizeof(uint32_t))) != cudaSuccess ||
@@ -1574,6 +1938,7 @@ int tc_init(rae_engine* h) {
     RAE_TC_ATTR(k_tc_bilinear<32>, t.smem) RAE_TC_ATTR(k_tc_bilinear<64>, t.smem) RAE_TC_ATTR(k_tc_bilinear<128>, t.smem)
     RAE_TC_ATTR(k_tc_dq<32>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<64>, t.smem_dq) RAE_TC_ATTR(k_tc_dq<128>, t.smem_dq)
     RAE_TC_ATTR(k_tc_dc, t.smem_dc)
+    if (t.dc2) { RAE_TC_ATTR(k_tc_dc2, t.smem_dc2) }
 #undef RAE_TC_ATTR
     t.ready = true;
     return RAE_OK;
@@ -1581,7 +1946,7 @@ int tc_init(rae_engine* h) {
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.spT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3); cudaFree(t.scal);
+    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.spT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3); cudaFree(t.scal); cudaFree(t.pop4); cudaFree(t.Rimg); cudaFree(t.Yimg);
     cudaFree(t.qT); cudaFree(t.aT); cudaFree(t.LT); cudaFree(t.RT); cudaFree(t.cT); cudaFree(t.Y2T);
     t = TcState{};
 }
@@ -1591,7 +1956,7 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     RAE_CUDA(h, cudaMemsetAsync(t.scal + TS_AMAX_C, 0, sizeof(uint32_t), st));
     const size_t dd = h->hasM ? (size_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (size_t)h->d * h->K : 0;
-    k_tc_absmax<<<h->num_sms, 256, 0, st>>>(h->P[RAE_P_C], dd, h->P[RAE_P_C1], dk, h->P[RAE_P_C2], dk, t.scal + TS_AMAX_C);
+    k_tc_absmax<<<h->num_sms * 8, 256, 0, st>>>(h->P[RAE_P_C], dd, h->P[RAE_P_C1], dk, h->P[RAE_P_C2], dk, t.scal + TS_AMAX_C);
     const size_t total = (size_t)t.n_chunks_fwd * TC_N * (t.KH / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KH / 8, t.DP, t.n_bil_rows,
@@ -1603,18 +1968,24 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
 }
 
 namespace {
-int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst, const int* amax_word, bool with_q, cudaStream_t st) {
+// img_slot >= 0: that slot is ALSO written as the stack of stage images the two-tile dC kernel fetches
+int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst, const int* amax_word, bool with_q, int img_slot,
+                       float* img_dst, cudaStream_t st) {
     TcState& t = h->tc;
     TrJobs jobs{};
     jobs.B = h->B;
     int nj = 0, maxc = 0;
     for (int i = 0; i < n; ++i) {
-        jobs.j[nj++] = TrJob{h->ev + (size_t)slots[i] * h->dp, (size_t)E_NV * h->dp, h->d, h->dp, dst[i], t.scal + amax_word[i]};
+        jobs.j[nj++] = TrJob{h->ev + (size_t)slots[i] * h->dp, (size_t)E_NV * h->dp, h->d, h->dp, dst[i], t.scal + amax_word[i], 0};
         maxc = std::max(maxc, h->dp);
     }
     if (with_q) {
-        jobs.j[nj++] = TrJob{h->q, (size_t)h->K, h->K, h->K, t.qT, nullptr};
+        jobs.j[nj++] = TrJob{h->q, (size_t)h->K, h->K, h->K, t.qT, nullptr, 0};
         maxc = std::max(maxc, h->K);
+    }
+    if (img_slot >= 0 && t.dc2) {
+        jobs.j[nj++] = TrJob{h->ev + (size_t)img_slot * h->dp, (size_t)E_NV * h->dp, h->d, t.DP, img_dst, nullptr, 1};
+        maxc = std::max(maxc, t.DP);
     }
     k_tc_transpose<<<dim3((h->B + 31) / 32, (maxc + 31) / 32, nj), 256, 0, st>>>(jobs);
     h->launches++;
@@ -1629,14 +2000,14 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
     const int nbc = 2 * t.n_bst;
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<dim3(blocks3, 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
-                                                   h->quirk ? 1 : 0, h->ev, t.scal);
+    k_tc_prep_qt<<<dim3(blocks3, t.dc2 ? 3 : 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
+                                                              h->quirk ? 1 : 0, h->ev, t.scal, reinterpret_cast<uint4*>(t.pop4));
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     const int slots[2] = {E_L, E_R};
     float* const dst[2] = {t.LT, t.RT};
     const int words[2] = {TS_AMAX_L, TS_AMAX_R};
-    return tc_transpose_slots(h, 2, slots, dst, words, true, st);
+    return tc_transpose_slots(h, 2, slots, dst, words, true, E_R, t.Rimg, st);
 }
 
 // the q-dependent operand alone (only the dC contraction at the end of the step needs it: prepared off the critical path)
@@ -1646,7 +2017,7 @@ int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
     k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
-                                                   h->quirk ? 1 : 0, h->ev, t.scal);
+                                                   h->quirk ? 1 : 0, h->ev, t.scal, nullptr);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -1683,7 +2054,7 @@ int tc_backward_recompute(rae_engine* h, cudaStream_t st) {
     const int slots[3] = {E_A, E_CV, E_Y2};
     float* const dst[3] = {t.aT, t.cT, t.Y2T};
     const int words[3] = {TS_AMAX_A, TS_AMAX_CV, TS_AMAX_Y2};
-    int rc = tc_transpose_slots(h, 3, slots, dst, words, false, st);
+    int rc = tc_transpose_slots(h, 3, slots, dst, words, false, E_Y2, t.Yimg, st);
     if (rc) return rc;
     return tc_contract(h, t.aT, t.cT, E_GA1, E_GA2, false, st);
 }
@@ -1717,20 +2088,36 @@ int tc_backward_finish(rae_engine* h, cudaStream_t st) {
     return RAE_OK;
 }
 
-// dC, dC1, dC2 partials on the tensor path (k_dense_finalize sums the slots of every row tile)
+// dC, dC1, dC2 partials on the tensor path (k_dense_finalize sums the slots of every row tile / tile pair): the bilinear
+// rows through the two-tile FP16 kernel, the C1 / C2 tiles (or everything, when B % 4 != 0) through the one-tile kernel
 int tc_grad_dense(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
-    TcDcArgs p{};
-    p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
-    p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
-    p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.hasM = h->hasM ? 1 : 0;
-    p.nacc = t.dc_nacc;
-    p.share = t.dc_share;
-    p.split_stride = (size_t)h->off_gWb;
-    p.sch = t.sch_dc;
-    k_tc_dc<<<p.sch.G, TC_BWD_THREADS, t.smem_dc, st>>>(p);
-    h->launches++;
-    RAE_CUDA(h, cudaGetLastError());
+    if (t.dc2) {
+        TcDc2Args p{};
+        p.pop4 = reinterpret_cast<const uint4*>(t.pop4); p.Rimg = t.Rimg; p.Yimg = t.Yimg; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
+        p.scal = t.scal; p.g_bound = (float)((double)h->S / h->Z);
+        p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
+        p.n_bil_tiles = t.n_bil_rows / TC_M;
+        p.split_stride = (size_t)h->off_gWb;
+        p.sch = t.sch_dc2;
+        k_tc_dc2<<<p.sch.G, TC_BWD_THREADS, t.smem_dc2, st>>>(p);
+        h->launches++;
+        RAE_CUDA(h, cudaGetLastError());
+    }
+    if (t.dc_tiles > 0) {
+        TcDcArgs p{};
+        p.pop3 = t.pop3; p.ev = h->ev; p.sc = h->sc; p.aT = t.aT; p.LT = t.LT; p.out = h->gC_part;
+        p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK; p.DP = t.DP;
+        p.n_bil_rows = t.n_bil_rows; p.n_rows_total = t.n_rows_total; p.hasM = h->hasM ? 1 : 0;
+        p.nacc = t.dc_nacc;
+        p.share = t.dc_share;
+        p.tile0 = t.dc_tile0;
+        p.split_stride = (size_t)h->off_gWb;
+        p.sch = t.sch_dc;
+        k_tc_dc<<<p.sch.G, TC_BWD_THREADS, t.smem_dc, st>>>(p);
+        h->launches++;
+        RAE_CUDA(h, cudaGetLastError());
+    }
     return RAE_OK;
 }
 

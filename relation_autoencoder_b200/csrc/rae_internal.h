@@ -92,7 +92,7 @@ struct TcState {
     int ntile = 0;         // example tiles of 128
     int fwd_stages = 2;    // B-operand shared-memory stages of the forward kernel
     size_t smem = 0;
-    TcSched sch_fwd{}, sch_rec{}, sch_dq{}, sch_dc{};
+    TcSched sch_fwd{}, sch_rec{}, sch_dq{}, sch_dc{}, sch_dc2{};
     int slots_vw = 0, slots_dq = 0, slots_dc = 0;   // partial-result slots per tile (maximum over tiles)
     float4* bop = nullptr; // forward B operand chunks [chunk][hi/lo][KQ][128]
     float* vT = nullptr;   // [2][dp][B]            v partials, transposed (lane = example)
@@ -103,6 +103,8 @@ struct TcState {
     float4* bop2 = nullptr; // Cf^T chunks [c32][hi/lo][8][NK]
     float* dqT = nullptr;   // [slots_dq][NK][B]  dq partials, transposed
     int n_ntiles = 0, n_bst = 0, dc_nacc = 2, dc_share = 0;   // dC: 128-row tiles, 64-example stages, accumulators, stages per CTA
+    bool dc2 = false; int dc_tile0 = 0, dc_tiles = 0; size_t smem_dc2 = 0;   // two-tile FP16 dC kernel on the bilinear rows; tiles left to the one-tile kernel
+    float4* pop4 = nullptr; float* Rimg = nullptr; float* Yimg = nullptr;     // its q^T operand and the stage images of R, Y2
     float4* pop3 = nullptr; // q^T chunks [bc][hi/lo][8][NK]
     float* qT = nullptr;    // [4 KQ][B]  q transposed
     float* aT = nullptr; float* LT = nullptr; float* RT = nullptr; float* cT = nullptr; float* Y2T = nullptr;   // [dp][B] views

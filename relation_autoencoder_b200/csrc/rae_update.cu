@@ -559,15 +559,18 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
 // shared-memory tree combines the 256 values (deterministic).
 // slots of the partial buffer that hold element i0 of [C | C1 | C2]: uniform (SIMT path, sch.G == 0) or, on the tensor
 // path, the slot count of the 128-row operand tile the element's row n = (i, j) | C1 row | C2 row falls in
-struct DenseSlots { TcSched sch; int d, K, DP, n_bil_rows, hasM; };
+struct DenseSlots { TcSched sch; TcSched sch2; int pair2, tile0; int d, K, DP, n_bil_rows, hasM; };
 __device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
-    if (ds.sch.G == 0) return ds.sch.upt;
+    if (ds.pair2 == 0 && ds.sch.G == 0) return ds.sch.upt;
     const int r = (int)(i0 / (size_t)ds.K);                    // row of the [units*d, K] layout
     const int nb = ds.hasM ? ds.d * ds.d : 0;
     int n;
     if (r < nb) { const int i = r / ds.d; n = i * ds.DP + (r - i * ds.d); }
     else { const int m = r - nb, which = m / ds.d; n = ds.n_bil_rows + which * ds.DP + (m - which * ds.d); }
-    return tcs_nslots(ds.sch, n >> 7);
+    // bilinear rows may belong to the two-tile kernel's schedule (tiles = pairs of 128-row tiles); the other rows to the
+    // one-tile kernel's, whose tiles are counted from tile0
+    if (ds.pair2 && n < ds.n_bil_rows) return tcs_nslots(ds.sch2, n >> 8);
+    return tcs_nslots(ds.sch, (n >> 7) - ds.tile0);
 }
 
 __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, DenseSlots ds, size_t n_units_elems,
@@ -868,7 +871,10 @@ int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
     DenseSlots ds{};
     ds.sch = TcSched{0, h->gC_nsplit, 1};
     ds.d = h->d; ds.K = h->K; ds.hasM = h->hasM ? 1 : 0;
-    if (h->use_tc) { ds.sch = h->tc.sch_dc; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows; }
+    if (h->use_tc) {
+        ds.sch = h->tc.sch_dc; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows;
+        ds.sch2 = h->tc.sch_dc2; ds.pair2 = h->tc.dc2 ? 1 : 0; ds.tile0 = h->tc.dc_tile0;
+    }
     k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, ds, n_units, h->dzsum_part, h->dz_part_used, h->K,
                                                           h->dense_grad, (size_t)h->off_gWb, n_elem_blocks);
     h->launches++;
