@@ -41,6 +41,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "rae_common.cuh"
 #include "rae_internal.h"
@@ -58,6 +59,7 @@ __device__ unsigned long long* g_tc_trace = nullptr;
 __device__ int g_tc_knock = 0;
 #define TC_KNOCK(bit) ((g_tc_knock & (bit)) != 0)
 #define TC_TRACE_INIT() unsigned long long* const tc_trace_ptr_ = g_tc_trace
+#define TC_TRACE_INIT_IF(cond) unsigned long long* const tc_trace_ptr_ = (cond) ? g_tc_trace : nullptr
 #define TC_TRACE(slot)                                                                                         \
     do {                                                                                                       \
         if (tc_trace_ptr_ != nullptr && (slot) < 64) tc_trace_ptr_[(size_t)blockIdx.x * 64 + (slot)] = clock64(); \
@@ -75,6 +77,7 @@ __device__ int g_tc_knock = 0;
 #define TC_KNOCK(bit) false
 #define TC_TRACE_NS(slot) do { } while (0)
 #define TC_TRACE_INIT() do { } while (0)
+#define TC_TRACE_INIT_IF(cond) do { } while (0)
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
@@ -1248,7 +1251,7 @@ struct TcDcArgs {
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TC_TRACE_INIT();
+    TC_TRACE_INIT_IF(p.tile0 == 0);      // (as the C1 / C2 helper of k_tc_dc2 it leaves the trace slots to that kernel)
     constexpr int NAS = TC_DC_ASTAGES;
     const uint32_t ST_BYTES = 2u * 2u * 8u * (uint32_t)p.NK * 16u;
     uint8_t* smB = smem_raw;
@@ -1312,7 +1315,7 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
                 mbar_wait(br.acc_empty, (seg - 1) & 1);
                 tc_fence_after();
             }
-            bwd_mma_segment<NAS>(br, smB, ST_BYTES, p.NK, tmem_base, sg.u1 - sg.u0, it, p.nacc, 32);
+            bwd_mma_segment<NAS>(br, smB, ST_BYTES, p.NK, tmem_base, sg.u1 - sg.u0, it, p.nacc, p.tile0 == 0 ? 32 : 64);
             it += sg.u1 - sg.u0;
             ++seg;
         }
@@ -1932,6 +1935,15 @@ int tc_init(rae_engine* h) {
         (e = cudaMalloc((void**)&t.scal, TS_N * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemset(t.scal, 0, TS_N * sizeof(uint32_t))) != cudaSuccess)
         return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
+    {
+        // partial slots of every 128-row tile: the pair's count for tiles of the two-tile kernel, the tile's own otherwise
+        std::vector<int32_t> ts((size_t)t.n_ntiles, 1);
+        for (int nt = 0; nt < t.n_ntiles; ++nt)
+            ts[nt] = (t.dc2 && nt < n_bil_tiles) ? tcs_nslots(t.sch_dc2, nt / 2) : tcs_nslots(t.sch_dc, nt - t.dc_tile0);
+        if ((e = cudaMalloc((void**)&t.tile_slots, ts.size() * sizeof(int32_t))) != cudaSuccess ||
+            (e = cudaMemcpy(t.tile_slots, ts.data(), ts.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return fail(h, RAE_ENOMEM, "tensor-path workspace: %s", cudaGetErrorString(e));
+    }
 #define RAE_TC_ATTR(KERN, BYTES)                                                                                     \
     if ((e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) \
         return fail(h, RAE_ECUDA, "cudaFuncSetAttribute(" #KERN "): %s", cudaGetErrorString(e));
@@ -1946,7 +1958,7 @@ int tc_init(rae_engine* h) {
 
 void tc_free(rae_engine* h) {
     TcState& t = h->tc;
-    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.spT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3); cudaFree(t.scal); cudaFree(t.pop4); cudaFree(t.Rimg); cudaFree(t.Yimg);
+    cudaFree(t.bop); cudaFree(t.vT); cudaFree(t.wT); cudaFree(t.spT); cudaFree(t.bop2); cudaFree(t.dqT); cudaFree(t.pop3); cudaFree(t.scal); cudaFree(t.pop4); cudaFree(t.Rimg); cudaFree(t.Yimg); cudaFree(t.tile_slots);
     cudaFree(t.qT); cudaFree(t.aT); cudaFree(t.LT); cudaFree(t.RT); cudaFree(t.cT); cudaFree(t.Y2T);
     t = TcState{};
 }

@@ -221,7 +221,7 @@ constexpr int ROWS_TILE = 128;     // columns per pass (one float4 per lane)
 // bias scalar).  VEC: the table rows are 16-byte aligned (width % 4 == 0).
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
-    extern __shared__ float4 slab4[];                      // [8 warps][32 runs][slab_cols / 4]
+    extern __shared__ float4 slab4[];                      // [warps of the CTA][32 runs][slab_cols / 4]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
             // ---- phase 1: accumulate runs in position order ----
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             int r = -1;
-            constexpr int UN = 8;
+            constexpr int UN = 16;     // payload rows in flight per warp (one CTA of 8 warps per SM: registers are plentiful)
             for (int b0 = 0; b0 < cnt; b0 += UN) {
                 float4 v[UN];
                 float cf[UN];
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
             if (r >= 0 && lane < sq) S[r * sq + lane] = a;
             __syncwarp();
             // ---- phase 2: one optimiser read-modify-write (or one emitted gradient row) per run ----
-            constexpr int RN = 4;
+            constexpr int RN = 8;      // table + accumulator rows in flight per warp
             unsigned hm = heads;                          // run heads still to visit (lowest set bit = next run)
             for (int r0 = 0; r0 < nr; r0 += RN) {
                 float4 w[RN], ac[RN];
@@ -557,20 +557,18 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
 // blocks [0, n_elem_blocks): 4 consecutive elements per thread (float4 when aligned), the splits summed in split order;
 // blocks [n_elem_blocks, +K): one CTA per column k of dWb - thread t sums partial rows t, t+256, ... and a fixed-shape
 // shared-memory tree combines the 256 values (deterministic).
-// slots of the partial buffer that hold element i0 of [C | C1 | C2]: uniform (SIMT path, sch.G == 0) or, on the tensor
-// path, the slot count of the 128-row operand tile the element's row n = (i, j) | C1 row | C2 row falls in
-struct DenseSlots { TcSched sch; TcSched sch2; int pair2, tile0; int d, K, DP, n_bil_rows, hasM; };
+// slots of the partial buffer that hold element i0 of [C | C1 | C2]: uniform (SIMT path, tile_slots == nullptr) or, on the
+// tensor path, the slot count of the 128-row operand tile the element's row n = (i, j) | C1 row | C2 row falls in (a small
+// per-tile table made at create time: rae_decoder_tc.cu)
+struct DenseSlots { const int32_t* tile_slots; int uniform; int d, K, DP, n_bil_rows, hasM; };
 __device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
-    if (ds.pair2 == 0 && ds.sch.G == 0) return ds.sch.upt;
+    if (ds.tile_slots == nullptr) return ds.uniform;
     const int r = (int)(i0 / (size_t)ds.K);                    // row of the [units*d, K] layout
     const int nb = ds.hasM ? ds.d * ds.d : 0;
     int n;
     if (r < nb) { const int i = r / ds.d; n = i * ds.DP + (r - i * ds.d); }
     else { const int m = r - nb, which = m / ds.d; n = ds.n_bil_rows + which * ds.DP + (m - which * ds.d); }
-    // bilinear rows may belong to the two-tile kernel's schedule (tiles = pairs of 128-row tiles); the other rows to the
-    // one-tile kernel's, whose tiles are counted from tile0
-    if (ds.pair2 && n < ds.n_bil_rows) return tcs_nslots(ds.sch2, n >> 8);
-    return tcs_nslots(ds.sch, (n >> 7) - ds.tile0);
+    return ds.tile_slots[n >> 7];
 }
 
 __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, DenseSlots ds, size_t n_units_elems,
@@ -581,10 +579,17 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
         if (i0 >= n_units_elems) return;
         if ((n_units_elems & 3) == 0 && (K & 3) == 0) {        // the 4 elements share a row
             const int nsplit = dense_slots_of(ds, i0);
-            float4 s = *reinterpret_cast<const float4*>(part + i0);
-            for (int sp = 1; sp < nsplit; ++sp) {
-                const float4 x = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
-                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            // all slot loads are issued before the first add (one memory latency, not one per slot); summed in slot order
+            float4 x[8];
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp)
+                x[sp] = sp < nsplit ? *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 s = x[0];
+#pragma unroll
+            for (int sp = 1; sp < 8; ++sp) { s.x += x[sp].x; s.y += x[sp].y; s.z += x[sp].z; s.w += x[sp].w; }
+            for (int sp = 8; sp < nsplit; ++sp) {
+                const float4 y = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
+                s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
             }
             *reinterpret_cast<float4*>(out + i0) = s;
         } else {
@@ -765,16 +770,20 @@ template <int MODE>
 static int launch_rows_chunk(rae_engine* h, RowsArgs& p, cudaStream_t st) {
     const int64_t nchunks = ((int64_t)p.n + 31) / 32;
     const int slab_cols = std::min(ROWS_TILE, (p.width + 3) & ~3);
-    const size_t smem = (size_t)8 * 32 * slab_cols * sizeof(float);
+    // The kernel is bound by DRAM latency (one optimiser read-modify-write per unique row) and the per-warp slab limits how
+    // many warps an SM holds: CTAs of TWO warps pack 7 CTAs = 14 warps into the 227 KB of an SM where one CTA of 8 warps
+    // (128 KB at 128 columns) left room for nothing else.
+    constexpr int WARPS = 2;
+    const size_t smem = (size_t)WARPS * 32 * slab_cols * sizeof(float);
     const bool vec = (p.width & 3) == 0;
     auto kern = vec ? k_rows_chunk<MODE, true> : k_rows_chunk<MODE, false>;
     static bool attr_done[2][2] = {{false, false}, {false, false}};
     if (!attr_done[MODE][vec ? 1 : 0]) {
-        RAE_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * ROWS_TILE * (int)sizeof(float)));
+        RAE_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * 32 * ROWS_TILE * (int)sizeof(float)));
         attr_done[MODE][vec ? 1 : 0] = true;
     }
-    const int blocks = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
-    kern<<<blocks, 256, smem, st>>>(p, slab_cols);
+    const int blocks = (int)std::min<int64_t>((nchunks + WARPS - 1) / WARPS, (int64_t)h->num_sms * 32);
+    kern<<<blocks, 32 * WARPS, smem, st>>>(p, slab_cols);
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
@@ -869,12 +878,9 @@ int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
     const size_t n_units = (size_t)h->off_gWb;   // elements of [C | C1 | C2]
     const int n_elem_blocks = (int)((n_units + 1023) / 1024);
     DenseSlots ds{};
-    ds.sch = TcSched{0, h->gC_nsplit, 1};
+    ds.uniform = h->gC_nsplit;
     ds.d = h->d; ds.K = h->K; ds.hasM = h->hasM ? 1 : 0;
-    if (h->use_tc) {
-        ds.sch = h->tc.sch_dc; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows;
-        ds.sch2 = h->tc.sch_dc2; ds.pair2 = h->tc.dc2 ? 1 : 0; ds.tile0 = h->tc.dc_tile0;
-    }
+    if (h->use_tc) { ds.tile_slots = h->tc.tile_slots; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows; }
     k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, ds, n_units, h->dzsum_part, h->dz_part_used, h->K,
                                                           h->dense_grad, (size_t)h->off_gWb, n_elem_blocks);
     h->launches++;
