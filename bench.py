@@ -331,7 +331,7 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
                                 l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, rank=rank, world=world)
     else:
         eng = Engine(wl["model"], wl["K"], wl["d"], wl["S"], B, wl["F"], wl["N"], wl["N_train"], lr=0.1,
-                     l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank)
+                     l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, flags=128 if args.no_pdl else 0)
     eng.set_params_numpy(params)
     del params
 
@@ -402,6 +402,7 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
     # ---- (3) per-phase device times for the roofline of the dominant kernel ----
     phase_ms = None
     dist_phase_ms = None
+    timeline = None
     if with_phases and world > 1:
         eng.set_profiling(True)
         for s in range(20):
@@ -418,6 +419,17 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
         eng.set_profiling(False)
         phase_ms = acc
         st = eng.stats()
+        # the overlapped step's real schedule: an event behind every kernel group on its own stream (median of 9 steps)
+        eng.set_profiling(2)
+        tls = []
+        for r in range(7):
+            # several steps back to back, the LAST one read: the host runs ahead as in the timed loop (a step read right
+            # after a synchronise starts with ~40 us of launch latency that the steady state does not have)
+            for s in range(6):
+                eng.train_device((2 * (warmup + steps) + prof_steps + 6 * r + s) % nb, want_cost=False)
+            tls.append(eng.timeline())
+        eng.set_profiling(False)
+        timeline = [[tls[0][i][0], tls[0][i][1], round(float(np.median([t[i][2] for t in tls])), 1)] for i in range(len(tls[0]))]
 
     p_cpu = eng.get_params_numpy() if (world == 1 and not args.no_cpu_baseline and with_e2e) else None
     eng.close()                      # collective for N > 1 (nobody unmaps peer memory while a peer may still read it)
@@ -456,6 +468,8 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
         frag["dist_phase_ms"] = {k: round(v, 5) for k, v in dist_phase_ms.items()}
     if phase_ms is not None:
         frag["phase_ms"] = {k: round(v, 5) for k, v in phase_ms.items()}
+    if timeline is not None:
+        frag["timeline_us"] = timeline
     return frag, st, phase_ms, p_cpu, (data, neg1, neg2)
 
 
@@ -482,7 +496,7 @@ def _run_ours(args, wl, rank, world, local_rank):
         f2, st2, ph2, _, _ = _measure(args, wl2, "cfg2", rank, world, local_rank, dist, steps, warmup, args.min_time / 2,
                                       with_e2e=False, with_phases=True)
         extra["cfg2"] = {"config": _config(wl2, args, world, "cfg2"), "value": f2["value"], "unit": UNIT, "ms_per_step": f2["ms_per_step"],
-                         "rounds": f2["rounds"], "step_roofline": f2["step_roofline"], "phase_ms": f2.get("phase_ms"),
+                         "rounds": f2["rounds"], "step_roofline": f2["step_roofline"], "phase_ms": f2.get("phase_ms"), "timeline_us": f2.get("timeline_us"),
                          "step_stats": f2["step_stats"]}
     if dist is not None:
         dist.destroy_process_group()
@@ -496,7 +510,7 @@ def _run_ours(args, wl, rank, world, local_rank):
         "data": "synthetic", "config": _config(wl, args, world, args.workload),
     }
     for k in ("rounds", "timed_region_s", "round_ms_min_med_max", "clocks", "e2e", "gpu_launches", "step_stats", "step_roofline",
-              "setup_s", "epoch_level", "dist_phase_ms", "phase_ms"):
+              "setup_s", "epoch_level", "dist_phase_ms", "phase_ms", "timeline_us"):
         if k in frag:
             line[k] = frag[k]
     if parity is not None:
@@ -609,6 +623,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra cfg2 record")
     ap.add_argument("--uniform", action="store_true", help="uniform instead of Zipf feature ids")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="RAE_FLAG_NO_PDL: plain stream-order launches (A/B of programmatic dependent launch)")
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU work allowed for the CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -68,6 +68,7 @@ extern "C" {
 #define RAE_FLAG_NO_FEATURE_CACHE 16u /* re-sort the batch's (feature, example) pairs every step instead of once at bind */
 #define RAE_FLAG_CLUSTER_MULTICAST 64u /* tcgen05 path: thread-block clusters, streamed operand fetched once per cluster (multicast).
                                          * Measured on B200: no gain (the kernels are not operand-traffic bound) -> off by default */
+#define RAE_FLAG_NO_PDL 128u        /* launch the step's kernels in plain stream order (no programmatic dependent launch): A/B measurements */
 #define RAE_FLAG_EMIT_ONLY 32u      /* row-sharded multi-GPU: W/A/Ab are per-step compact copies; emit per-row gradients, apply nothing */
 
 typedef struct rae_config {
@@ -298,6 +299,10 @@ int rae_get_step_stats(rae_engine* h, rae_step_stats* out);
  * Profiling serialises the side streams and adds event records between kernels: never on for a timed run. */
 #define RAE_NUM_PHASES 15
 int rae_set_profiling(rae_engine* h, int32_t on);
+/* on == 2: timeline mode - the step keeps its normal multi-stream overlap and an event is recorded behind every kernel
+ * group on the stream it ran on; rae_get_timeline writes one line per mark, "name stream microseconds-since-step-start"
+ * (stream 0 = the caller's, 1 = entity side stream, 2 = W / operand side stream), NUL-terminated, into buf[len]. */
+int rae_get_timeline(rae_engine* h, char* buf, int64_t len);
 /* milliseconds of each phase of the last profiled step (synchronises); ms must hold RAE_NUM_PHASES floats */
 int rae_get_phase_times(rae_engine* h, float* ms);
 const char* rae_phase_name(int32_t phase);

@@ -26,6 +26,7 @@ RAE_FLAG_FORCE_TENSOR = 8
 RAE_FLAG_NO_FEATURE_CACHE = 16
 RAE_FLAG_EMIT_ONLY = 32
 RAE_FLAG_CLUSTER_MULTICAST = 64
+RAE_FLAG_NO_PDL = 128
 RAE_ENODEVICE = -5
 RAE_NUM_PHASES = 15
 RAE_FLAG_WORDS = 32
@@ -104,6 +105,7 @@ _SIGNATURES = {
     "rae_sample_negatives": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, C.c_int64, _P, _P]),
     "rae_set_profiling": (C.c_int, [_P, C.c_int32]),
     "rae_get_phase_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "rae_get_timeline": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "rae_phase_name": (C.c_char_p, [C.c_int32]),
 }
 

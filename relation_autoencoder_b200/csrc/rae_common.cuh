@@ -8,6 +8,32 @@ namespace rae {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+// ---- programmatic dependent launch (the step is a chain of ~20 dependent kernels, most of them 5-60 us) ----
+// Every kernel of the step starts with pdl_enter(): it lets the NEXT kernel of the stream be scheduled already (its CTAs
+// become resident as SM resources free up and park in griddepcontrol.wait) and then waits until the PREVIOUS kernel of the
+// stream has completed and flushed its memory - before this kernel's first global access, so the data dependencies are
+// exactly those of plain stream order.  What overlaps is launch latency, CTA placement and the tail of the previous
+// kernel's last wave.  A kernel launched without the attribute executes both instructions as no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+#ifdef __CUDACC__
+extern bool g_pdl_enabled;      // rae_engine.cu; cleared by RAE_FLAG_NO_PDL (A/B measurements)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(static_cast<Args&&>(args))...);
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

@@ -486,6 +486,7 @@ struct ScoreArgs {
 // recompute the cheap positive score; each gathers only its own S negative rows, UN rows in flight per lane.
 template <int DT>
 __global__ void __launch_bounds__(256) k_score(ScoreArgs p) {
+    pdl_enter();
     __shared__ double wl[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int side = warp & 1;
@@ -793,10 +794,10 @@ int launch_score(rae_engine* h, const int32_t* a1, const int32_t* a2, const int3
     const int blocks = (h->B + 3) / 4;
     if (blocks > h->n_loss_part) return fail(h, RAE_EINVAL, "internal: loss_part too small");
     const int dt = (h->d + 31) / 32;
-    if (dt <= 1) k_score<1><<<blocks, 256, 0, st>>>(p);
-    else if (dt <= 2) k_score<2><<<blocks, 256, 0, st>>>(p);
-    else if (dt <= 4) k_score<4><<<blocks, 256, 0, st>>>(p);
-    else if (dt <= 8) k_score<8><<<blocks, 256, 0, st>>>(p);
+    if (dt <= 1) launch_pdl(k_score<1>, dim3(blocks), dim3(256), 0, st, p);
+    else if (dt <= 2) launch_pdl(k_score<2>, dim3(blocks), dim3(256), 0, st, p);
+    else if (dt <= 4) launch_pdl(k_score<4>, dim3(blocks), dim3(256), 0, st, p);
+    else if (dt <= 8) launch_pdl(k_score<8>, dim3(blocks), dim3(256), 0, st, p);
     else return fail(h, RAE_EINVAL, "d=%d > 256 is not supported", h->d);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());

@@ -326,6 +326,7 @@ __device__ __forceinline__ const float* cf_row(const float* C, const float* C1, 
 // atomic is deterministic)
 __global__ void __launch_bounds__(256) k_tc_absmax(const float* __restrict__ C, size_t nC, const float* __restrict__ C1, size_t n1,
                                                    const float* __restrict__ C2, size_t n2, uint32_t* __restrict__ out) {
+    pdl_enter();
     __shared__ uint32_t red[8];
     uint32_t m = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_c(const float* __restrict__ C, 
                                                    const float* __restrict__ C2, int d, int K, int KQ8, int DP, int n_bil_rows,
                                                    int n_rows_fwd, uint4* __restrict__ out, int NK, int n_rows_bwd,
                                                    uint4* __restrict__ out2, const uint32_t* __restrict__ scal) {
+    pdl_enter();
     const float sC = pow2_scale(scal[TS_AMAX_C]);
     if (blockIdx.y == 1) {
         const size_t total2 = (size_t)(n_rows_bwd / 8) * NK;
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_qt(const float* __restrict__ q,
                                                     const float* __restrict__ A, const int32_t* __restrict__ a1,
                                                     const int32_t* __restrict__ a2, int d, int dp, int quirk, float* __restrict__ ev,
                                                     uint32_t* __restrict__ scal, uint4* __restrict__ out4) {
+    pdl_enter();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) scal[TS_AMAX_L + threadIdx.x] = 0u;   // the transposes that follow accumulate
     if (blockIdx.y == 2) {
         // FP16 pair operand of the two-tile dC kernel: [stage of 64 examples][hi/lo][oct 0..7][krow 0..NK-1] x 16 B = examples
@@ -495,6 +498,7 @@ struct TcArgs {
 
 template <int DP>
 __global__ void __launch_bounds__(TC_FWD_THREADS, 1) k_tc_bilinear(TcArgs p) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
@@ -799,6 +803,7 @@ constexpr int TC_IMG_LD = 68;
 struct TrJob { const float* src; size_t stride; int cols, cols_out; float* dst; uint32_t* amax; int img; };
 struct TrJobs { TrJob j[4]; int B; };
 __global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
+    pdl_enter();
     __shared__ float tile[32][33];
     __shared__ uint32_t red[8];
     const TrJob jb = jobs.j[blockIdx.z];
@@ -839,6 +844,7 @@ __global__ void __launch_bounds__(256) k_tc_transpose(TrJobs jobs) {
 __global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT, const float* __restrict__ wT, const float* __restrict__ spT,
                                                     float* __restrict__ ev, int B, int d, int dp, int DP, TcSched sch, int slotV, int slotW,
                                                     uint32_t* __restrict__ zero_amax) {
+    pdl_enter();
     __shared__ float tv[32][33], tw[32][33], t1[32][33], t2[32][33];
     if (zero_amax != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3) zero_amax[TS_AMAX_A + threadIdx.x] = 0u;
     const int b0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
@@ -1061,6 +1067,7 @@ __device__ __forceinline__ void dq_store16(uint32_t lane_base, int as, int col8,
 // 128 / DP rows i: the thread's row is i = (128 / DP) st + (32 cg) / DP, its columns j = (32 cg) % DP + 0..31.
 template <int DP>
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dq(TcDqArgs p) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
@@ -1249,6 +1256,7 @@ struct TcDcArgs {
 };
 
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc(TcDcArgs p) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT_IF(p.tile0 == 0);      // (as the C1 / C2 helper of k_tc_dc2 it leaves the trace slots to that kernel)
@@ -1463,6 +1471,7 @@ struct TcDc2Args {
 };
 
 __global__ void __launch_bounds__(TC_BWD_THREADS, 1) k_tc_dc2(TcDc2Args p) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE_INIT();
@@ -1735,6 +1744,7 @@ __global__ void __launch_bounds__(1024) k_tc_bwd_finish(float* __restrict__ ev, 
                                                        const float* __restrict__ logq, const float* __restrict__ dqT, float* __restrict__ dz,
                                                        float* __restrict__ dzsum_part, int B, int K, int NK, TcSched sch_dq, int d, int dp,
                                                        int hasSP, float ent_coef) {
+    pdl_enter();
     extern __shared__ float fin_smem[];
     const int KS = K | 1;                  // odd row stride: conflict-free transposed writes
     float* sdq = fin_smem;                 // [32][KS]
@@ -1968,10 +1978,10 @@ int tc_prepare_c(rae_engine* h, cudaStream_t st) {
     TcState& t = h->tc;
     RAE_CUDA(h, cudaMemsetAsync(t.scal + TS_AMAX_C, 0, sizeof(uint32_t), st));
     const size_t dd = h->hasM ? (size_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (size_t)h->d * h->K : 0;
-    k_tc_absmax<<<h->num_sms * 8, 256, 0, st>>>(h->P[RAE_P_C], dd, h->P[RAE_P_C1], dk, h->P[RAE_P_C2], dk, t.scal + TS_AMAX_C);
+    launch_pdl(k_tc_absmax, dim3(h->num_sms * 8), dim3(256), 0, st, h->P[RAE_P_C], dd, h->P[RAE_P_C1], dk, h->P[RAE_P_C2], dk, t.scal + TS_AMAX_C);
     const size_t total = (size_t)t.n_chunks_fwd * TC_N * (t.KH / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_c<<<dim3(blocks, 2), 256, 0, st>>>(h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KH / 8, t.DP, t.n_bil_rows,
+    launch_pdl(k_tc_prep_c, dim3(blocks, 2), dim3(256), 0, st, h->P[RAE_P_C], h->P[RAE_P_C1], h->P[RAE_P_C2], h->d, h->K, t.KH / 8, t.DP, t.n_bil_rows,
                                                  t.n_chunks_fwd * TC_N, reinterpret_cast<uint4*>(t.bop), t.NK, t.n_rows_total,
                                                  reinterpret_cast<uint4*>(t.bop2), t.scal);
     h->launches += 2;
@@ -1999,7 +2009,7 @@ int tc_transpose_slots(rae_engine* h, int n, const int* slots, float* const* dst
         jobs.j[nj++] = TrJob{h->ev + (size_t)img_slot * h->dp, (size_t)E_NV * h->dp, h->d, t.DP, img_dst, nullptr, 1};
         maxc = std::max(maxc, t.DP);
     }
-    k_tc_transpose<<<dim3((h->B + 31) / 32, (maxc + 31) / 32, nj), 256, 0, st>>>(jobs);
+    launch_pdl(k_tc_transpose, dim3((h->B + 31) / 32, (maxc + 31) / 32, nj), dim3(256), 0, st, jobs);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -2012,7 +2022,7 @@ int tc_prepare_p(rae_engine* h, const int32_t* a1, const int32_t* a2, cudaStream
     const int nbc = 2 * t.n_bst;
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<dim3(blocks3, t.dc2 ? 3 : 2), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
+    launch_pdl(k_tc_prep_qt, dim3(blocks3, t.dc2 ? 3 : 2), dim3(256), 0, st, h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], a1, a2, h->d, h->dp,
                                                               h->quirk ? 1 : 0, h->ev, t.scal, reinterpret_cast<uint4*>(t.pop4));
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
@@ -2028,7 +2038,7 @@ int tc_prepare_qt(rae_engine* h, cudaStream_t st) {
     const int nbc = 2 * t.n_bst;
     const size_t total3 = (size_t)nbc * 8 * t.NK;
     const int blocks3 = (int)std::min<size_t>((total3 + 255) / 256, (size_t)h->num_sms * 8);
-    k_tc_prep_qt<<<dim3(blocks3, 1), 256, 0, st>>>(h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
+    launch_pdl(k_tc_prep_qt, dim3(blocks3, 1), dim3(256), 0, st, h->q, h->B, h->K, t.NK, nbc, t.pop3, h->P[RAE_P_A], nullptr, nullptr, h->d, h->dp,
                                                    h->quirk ? 1 : 0, h->ev, t.scal, nullptr);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
@@ -2045,11 +2055,11 @@ int tc_contract(rae_engine* h, const float* LT_in, const float* RT_in, int slotV
     p.n_bil_half = t.n_bil_half; p.n_sp_half = with_sp ? t.n_sp_half : 0;
     p.nbs = t.fwd_stages;
     p.sch = with_sp ? t.sch_fwd : t.sch_rec;
-    if (t.DP == 32) k_tc_bilinear<32><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
-    else if (t.DP == 64) k_tc_bilinear<64><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
-    else k_tc_bilinear<128><<<p.sch.G, TC_FWD_THREADS, t.smem, st>>>(p);
+    if (t.DP == 32) launch_pdl(k_tc_bilinear<32>, dim3(p.sch.G), dim3(TC_FWD_THREADS), t.smem, st, p);
+    else if (t.DP == 64) launch_pdl(k_tc_bilinear<64>, dim3(p.sch.G), dim3(TC_FWD_THREADS), t.smem, st, p);
+    else launch_pdl(k_tc_bilinear<128>, dim3(p.sch.G), dim3(TC_FWD_THREADS), t.smem, st, p);
     RAE_CUDA(h, cudaGetLastError());
-    k_tc_combine<<<dim3((h->B + 31) / 32, (h->d + 31) / 32), 256, 0, st>>>(t.vT, t.wT, (with_sp && h->hasSP) ? t.spT : nullptr, h->ev, h->B, h->d,
+    launch_pdl(k_tc_combine, dim3((h->B + 31) / 32, (h->d + 31) / 32), dim3(256), 0, st, t.vT, t.wT, (with_sp && h->hasSP) ? t.spT : nullptr, h->ev, h->B, h->d,
                                                                           h->dp, t.DP, p.sch, slotV, slotW, with_sp ? t.scal : nullptr);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
@@ -2079,9 +2089,9 @@ int tc_backward_dq(rae_engine* h, cudaStream_t st) {
     p.B = h->B; p.d = h->d; p.dp = h->dp; p.K = h->K; p.NK = t.NK;
     p.n_bil_rows = t.n_bil_rows;
     p.sch = t.sch_dq;
-    if (t.DP == 32) k_tc_dq<32><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
-    else if (t.DP == 64) k_tc_dq<64><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
-    else k_tc_dq<128><<<p.sch.G, TC_BWD_THREADS, t.smem_dq, st>>>(p);
+    if (t.DP == 32) launch_pdl(k_tc_dq<32>, dim3(p.sch.G), dim3(TC_BWD_THREADS), t.smem_dq, st, p);
+    else if (t.DP == 64) launch_pdl(k_tc_dq<64>, dim3(p.sch.G), dim3(TC_BWD_THREADS), t.smem_dq, st, p);
+    else launch_pdl(k_tc_dq<128>, dim3(p.sch.G), dim3(TC_BWD_THREADS), t.smem_dq, st, p);
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -2093,7 +2103,7 @@ int tc_backward_finish(rae_engine* h, cudaStream_t st) {
     if (blocks > h->n_dz_part) return fail(h, RAE_EINVAL, "internal: dzsum_part too small");
     h->dz_part_used = blocks;
     const size_t smem = sizeof(float) * 32 * ((size_t)(h->K | 1) + h->K);
-    k_tc_bwd_finish<<<blocks, 1024, smem, st>>>(h->ev, h->sc, h->q, h->logq, t.dqT, h->dz, h->dzsum_part, h->B, h->K, t.NK, t.sch_dq,
+    launch_pdl(k_tc_bwd_finish, dim3(blocks), dim3(1024), smem, st, h->ev, h->sc, h->q, h->logq, t.dqT, h->dz, h->dzsum_part, h->B, h->K, t.NK, t.sch_dq,
                                                h->d, h->dp, h->hasSP ? 1 : 0, (float)(2.0 * h->cfg.alpha / h->Z));
     h->launches += 1;
     RAE_CUDA(h, cudaGetLastError());
@@ -2112,7 +2122,7 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st) {
         p.n_bil_tiles = t.n_bil_rows / TC_M;
         p.split_stride = (size_t)h->off_gWb;
         p.sch = t.sch_dc2;
-        k_tc_dc2<<<p.sch.G, TC_BWD_THREADS, t.smem_dc2, st>>>(p);
+        launch_pdl(k_tc_dc2, dim3(p.sch.G), dim3(TC_BWD_THREADS), t.smem_dc2, st, p);
         h->launches++;
         RAE_CUDA(h, cudaGetLastError());
     }
@@ -2126,7 +2136,7 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st) {
         p.tile0 = t.dc_tile0;
         p.split_stride = (size_t)h->off_gWb;
         p.sch = t.sch_dc;
-        k_tc_dc<<<p.sch.G, TC_BWD_THREADS, t.smem_dc, st>>>(p);
+        launch_pdl(k_tc_dc, dim3(p.sch.G), dim3(TC_BWD_THREADS), t.smem_dc, st, p);
         h->launches++;
         RAE_CUDA(h, cudaGetLastError());
     }

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) k_encoder_forward_v4(const int32_t* __res
                                                             int B, int K, float alpha, float* __restrict__ q,
                                                             float* __restrict__ logq, float* __restrict__ sc_ent,
                                                             int sc_stride, int64_t* __restrict__ labels) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;
@@ -205,7 +206,7 @@ int launch_encoder_forward(rae_engine* h, const int32_t* indptr, const int32_t* 
     if (vec) {
         const int qt = (K / 4 + 31) / 32;
 #define RAE_ENC4(QT)                                                                                                 \
-    k_encoder_forward_v4<QT><<<blocks, threads, 0, st>>>(indptr, indices, W, Wb, B, K, alpha, q, logq, sc_ent, SC_N, \
+    launch_pdl(k_encoder_forward_v4<QT>, dim3(blocks), dim3(threads), 0, st, indptr, indices, W, Wb, B, K, alpha, q, logq, sc_ent, SC_N, \
                                                           labels)
         if (qt <= 1) RAE_ENC4(1);
         else if (qt <= 2) RAE_ENC4(2);

@@ -10,6 +10,8 @@
 
 namespace rae {
 
+bool g_pdl_enabled = true;      // process-wide: cleared when any handle is created with RAE_FLAG_NO_PDL
+
 static char g_create_err[512] = "";
 
 int fail(rae_engine* h, int code, const char* fmt, ...) {
@@ -96,6 +98,15 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_phase[phase], st));        \
         ++phase;                                                                       \
     } while (0)
+    h->tl_n = 0;
+#define RAE_MARK(name, strm, sid)                                                          \
+    do {                                                                                   \
+        if (h->timeline && h->tl_n < RAE_TL_MAX) {                                         \
+            RAE_CUDA(h, cudaEventRecord(h->tl_ev[h->tl_n], strm));                         \
+            h->tl_name[h->tl_n] = name; h->tl_stream[h->tl_n] = sid; ++h->tl_n;            \
+        }                                                                                  \
+    } while (0)
+    RAE_MARK("start", st, 0);
     // Independent branches run on two handle-owned side streams (forked from / joined into the caller's stream):
     //   s1: entity keys + stable sort (needs only the indices) ... entity-row update
     //   s2: W-row update
@@ -115,12 +126,15 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
             RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork0, 0));
             if ((rc = tc_prepare_c(h, h->s2))) return rc;
             RAE_CUDA(h, cudaEventRecord(h->ev_prepc, h->s2));
+            RAE_MARK("prep_c", h->s2, 2);
         }
         if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
         if ((rc = sort_pairs(h, h->ent, n_occ, se, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
+        RAE_MARK("entity_sort", se, 1);
     }
     RAE_PHASE();   // 0 encoder forward: q, log q, entropy
     if ((rc = launch_encoder_forward(h, indptr, indices, h->B, h->q, h->logq, h->sc + SC_ENT, nullptr, st))) return rc;
+    RAE_MARK("encoder", st, 0);
     RAE_PHASE();   // 1 entity occurrence keys -> stable sort -> segments (depends on the indices only)
     if (!overlap) {
         if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
@@ -143,6 +157,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if (prepc_side) RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_prepc, 0));
         else if ((rc = tc_prepare_c(h, st))) return rc;
         if ((rc = tc_prepare_p(h, a1, a2, st))) return rc;
+        RAE_MARK("prep_p", st, 0);
     }
     RAE_PHASE();   // 4 forward contraction: v = M R, w = M^T L, c1, c2
     if (h->use_tc) {
@@ -150,6 +165,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     } else {
         if ((rc = launch_bilinear_forward_simt(h, a1, a2, st))) return rc;
     }
+    RAE_MARK("contract_forward", st, 0);
     RAE_PHASE();   // 5 scoring / loss / d cost / d score
     if (h->neg_wait) {
         // rae_train_step_host: the negatives were copied on the entity stream, beside the encoder
@@ -157,6 +173,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         h->neg_wait = nullptr;
     }
     if ((rc = launch_score(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
+    RAE_MARK("score", st, 0);
     h->cost_on_event = false;
     if (overlap) {
         // The cost needs the score partials and the pre-update parameters only: it is reduced beside the backward pass
@@ -166,6 +183,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_score, 0));
         if ((rc = launch_cost(h, h->s2))) return rc;
         RAE_CUDA(h, cudaEventRecord(h->ev_cost, h->s2));
+        RAE_MARK("cost", h->s2, 2);
         h->cost_on_event = true;
     }
     RAE_PHASE();   // 6 (profiling / no-overlap order only) entity-row update, see below
@@ -176,10 +194,13 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     } else {
         if ((rc = launch_bilinear_backward_simt(h, st))) return rc;
     }
+    RAE_MARK("contract_recompute", st, 0);
     RAE_PHASE();   // 9 backward: dq contraction
     if (h->use_tc && (rc = tc_backward_dq(h, st))) return rc;
+    RAE_MARK("contract_dq", st, 0);
     RAE_PHASE();   // 10 backward: per-example finish -> dz
     if (h->use_tc && (rc = tc_backward_finish(h, st))) return rc;
+    RAE_MARK("backward_finish", st, 0);
     if (overlap) {
         // dz and the per-example vectors are final: the sparse-row updates can start on their own streams
         RAE_CUDA(h, cudaEventRecord(h->ev_fork1, st));
@@ -187,8 +208,10 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_fork1, 0));
         if ((rc = launch_entity_update(h, h->ent.keys_s, h->ent.vals_s, n_occ, h->emit_only, !h->emit_only, se))) return rc;
         RAE_CUDA(h, cudaEventRecord(h->ev_join1, h->s1));
+        RAE_MARK("entity_update", h->s1, 1);
         if ((rc = launch_w_update(h, f_keys_s, f_vals_s, nnz, emit, !h->emit_only, sw))) return rc;
         RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
+        RAE_MARK("w_update", h->s2, 2);
     }
     RAE_PHASE();   // 11 dense-parameter gradients: dC contraction
     if (h->use_tc) {
@@ -196,8 +219,12 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     } else {
         if ((rc = launch_grad_dense_simt(h, st))) return rc;
     }
+    RAE_MARK("contract_dc", st, 0);
     RAE_PHASE();   // 12 sum of the batch-split partials
-    if ((rc = launch_dense_finalize(h, st))) return rc;
+    // without a regulariser nothing reads the dense parameters between here and their update: the optimiser rule is
+    // applied by the same kernel that sums the partials
+    if ((rc = launch_dense_finalize(h, st, finish_dense && h->cfg.l1 == 0.0 && h->cfg.l2 == 0.0))) return rc;
+    RAE_MARK("dense_finalize", st, 0);
     RAE_PHASE();   // 13 cost (uses the pre-update parameters for the regulariser value); overlapped order: see phase 5
     if (!overlap && (rc = launch_cost(h, st))) return rc;
     // emit-only (row-sharded multi-GPU): the tables are per-step compact copies whose every row is touched, so the
@@ -219,12 +246,15 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     }
     RAE_PHASE();   // 14 dense-parameter optimiser step
     if (finish_dense && (rc = launch_dense_apply(h, st))) return rc;
+    RAE_MARK("dense_apply", st, 0);
     if (overlap) {
         RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
         RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
     }
+    RAE_MARK("end", st, 0);
     RAE_PHASE();   // end
 #undef RAE_PHASE
+#undef RAE_MARK
     h->stats.nnz = nnz;
     h->stats.entity_occ = n_occ;
     h->stats.kernel_launches = h->launches;
@@ -417,6 +447,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     }
     h->tc = TcState{};
     h->use_tc = false;
+    g_pdl_enabled = !(cfg->flags & RAE_FLAG_NO_PDL);
     if (!(cfg->flags & RAE_FLAG_FORCE_SIMT) && tc_supported(h)) {
         RAE_CREATE_RC(tc_init(h));
         h->use_tc = true;
@@ -510,6 +541,9 @@ void rae_destroy(rae_engine* h) {
     if (h->ev_created) {
         for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_upd[i]);
+    }
+    if (h->tl_created) {
+        for (int i = 0; i < RAE_TL_MAX; ++i) cudaEventDestroy(h->tl_ev[i]);
     }
     if (h->s1) cudaStreamDestroy(h->s1);
     if (h->s2) cudaStreamDestroy(h->s2);
@@ -836,7 +870,28 @@ int rae_set_profiling(rae_engine* h, int32_t on) {
         for (int i = 0; i < 3; ++i) RAE_CUDA(h, cudaEventCreate(&h->ev_upd[i]));
         h->ev_created = true;
     }
-    h->profiling = on != 0;
+    if (on == 2 && !h->tl_created) {
+        for (int i = 0; i < RAE_TL_MAX; ++i) RAE_CUDA(h, cudaEventCreate(&h->tl_ev[i]));
+        h->tl_created = true;
+    }
+    h->profiling = on == 1;
+    h->timeline = on == 2;
+    return RAE_OK;
+}
+
+int rae_get_timeline(rae_engine* h, char* buf, int64_t len) {
+    if (!h || !buf || len <= 0) return RAE_EINVAL;
+    buf[0] = 0;
+    if (!h->tl_created || h->tl_n == 0) return fail(h, RAE_EINVAL, "rae_get_timeline: no step ran with rae_set_profiling(h, 2)");
+    int64_t off = 0;
+    for (int i = 0; i < h->tl_n; ++i) {
+        RAE_CUDA(h, cudaEventSynchronize(h->tl_ev[i]));
+        float ms = 0.f;
+        RAE_CUDA(h, cudaEventElapsedTime(&ms, h->tl_ev[0], h->tl_ev[i]));
+        const int w = snprintf(buf + off, (size_t)(len - off), "%s %d %.3f\n", h->tl_name[i], h->tl_stream[i], ms * 1e3f);
+        if (w < 0 || off + w >= len) break;
+        off += w;
+    }
     return RAE_OK;
 }
 

@@ -113,6 +113,7 @@ struct TcState {
 
 }  // namespace rae
 
+constexpr int RAE_TL_MAX = 48;
 struct rae_engine {
     rae_config cfg;
     int K, d, S, B;
@@ -142,6 +143,7 @@ struct rae_engine {
     float* dzsum_part; int n_dz_part; int dz_part_used;   // [n_dz_part, K]; rows written by the last backward
     float* dense_grad;  // flat [C | C1 | C2 | Wb]
     int64_t off_gC, off_gC1, off_gC2, off_gWb, n_dense;
+    bool dense_fused;           // this step's k_dense_finalize applied the optimiser itself (launch_dense_apply has only W left)
     float* gC_part; int gC_nsplit;       // [nsplit, units*d*K]
     // debug / regularised dense gradients of the sparse tables
     float* gW_dense; float* gA_dense; float* gAb_dense;
@@ -174,6 +176,9 @@ struct rae_engine {
     // bookkeeping
     rae_step_stats stats;
     bool profiling; cudaEvent_t ev_phase[RAE_NUM_PHASES + 1]; cudaEvent_t ev_upd[3]; bool ev_created;
+    // timeline (rae_set_profiling(h, 2)): the step runs with its normal three-stream overlap and an event is recorded behind
+    // every kernel group on the stream it ran on -> the real concurrent schedule (rae_get_timeline)
+    bool timeline; int tl_n; cudaEvent_t tl_ev[RAE_TL_MAX]; const char* tl_name[RAE_TL_MAX]; int tl_stream[RAE_TL_MAX]; bool tl_created;
     const uint32_t* last_f_keys_s; int64_t last_f_n;   // sorted feature keys of the last step (statistics)
     int32_t* stat_dev;   // [2] device scratch for unique-row counts
     int launches;
@@ -246,7 +251,7 @@ int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, co
                       cudaStream_t st);
 int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st);
 int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st);
-int launch_dense_finalize(rae_engine* h, cudaStream_t st);  // sum partials -> dense_grad
+int launch_dense_finalize(rae_engine* h, cudaStream_t st, bool fuse_apply);  // sum partials -> dense_grad, or (fused) straight into the optimiser rule
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int stage_host_negatives(rae_engine* h, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host, int64_t ld2,
                          cudaStream_t sc, int32_t** d1_out, int32_t** d2_out);   // host [S,B] ids -> device staging, records ev_neg

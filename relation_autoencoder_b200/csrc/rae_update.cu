@@ -21,6 +21,7 @@ namespace {
 __global__ void k_entity_keys(const int32_t* __restrict__ a1, const int32_t* __restrict__ a2,
                               const int32_t* __restrict__ neg1, const int32_t* __restrict__ neg2, int64_t neg_ld, int B,
                               int S, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_enter();
     // occurrence id o = slot*B + b ; slot 0: args1, 1: args2, 2+s: neg1[s], 2+S+s: neg2[s]
     const int n = (2 + 2 * S) * B;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
@@ -110,8 +111,11 @@ __global__ void k_count_heads(const uint32_t* __restrict__ keys_s, int n, int32_
 //            taken from the ballot of the keys - the finished run's sum is parked in the warp's shared-memory slab;
 //   phase 2  the runs are visited 4 at a time: table + accumulator rows of 4 runs are in flight together, the optimiser
 //            rule is applied once per row and the row is written back coalesced (or the reduced gradient row is emitted).
-//   Runs that continue from the previous chunk / into the next one park their partial row in scratch slot 2c / 2c+1.
-// Level 2 (k_*_long2): the CTA of the chunk in which a multi-chunk segment STARTS finds its extent, sums the partial rows
+//   A segment that spans exactly TWO chunks (about every second chunk boundary cuts one) is ABSORBED by the chunk it starts
+//   in: that warp reads on through the segment's positions in the next chunk (at most 32 more) and the next chunk skips
+//   them - both sides take the decision from the sorted keys alone.  Only segments spanning three or more chunks (rows with
+//   more than 32 occurrences) park their per-chunk partial rows in scratch slot 2c / 2c+1.
+// Level 2 (k_*_long2): the CTA of the chunk in which such a long segment STARTS finds its extent, sums the partial rows
 // in chunk order and applies the update.  Hot rows (Zipf) are thereby spread over many warps; the summation order is a
 // fixed function of the sorted layout -> bitwise reproducible.  No atomics.
 
@@ -135,6 +139,8 @@ __device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ k
     const uint32_t keyl = keys_s[p0 + cnt - 1];
     if (keys_s[p0 + cnt] != keyl) return -1;          // last run ends with the chunk
     *row = keyl;
+    const bool starts_here = !(keys_s[p0] == keyl && p0 > 0 && keys_s[p0 - 1] == keyl);
+    if (starts_here && (p0 + 64 >= n || keys_s[p0 + 64] != keyl)) return -1;     // spans two chunks: absorbed by level 1
     if (keys_s[p0] == keyl) {                          // run covers the chunk from its first position
         if (p0 > 0 && keys_s[p0 - 1] == keyl) return -1;   // ... and continues an earlier chunk: not the start
         return 2 * c;
@@ -221,6 +227,7 @@ constexpr int ROWS_TILE = 128;     // columns per pass (one float4 per lane)
 // bias scalar).  VEC: the table rows are 16-byte aligned (width % 4 == 0).
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
+    pdl_enter();
     extern __shared__ float4 slab4[];                      // [warps of the CTA][32 runs][slab_cols / 4]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -240,24 +247,61 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
         const uint32_t key0 = __shfl_sync(kFull, s.key, 0), keyl = __shfl_sync(kFull, s.key, cnt - 1);
         const bool cont_prev = p0 > 0 && p.keys_s[p0 - 1] == key0;
         const bool cont_next = p0 + cnt < p.n && p.keys_s[p0 + cnt] == keyl;
-        int off_m;
-        float coef_m = 1.f;
-        if (MODE == 0) {
-            off_m = (int)mine * p.width;
-        } else {
-            const int slot_m = (int)(mine / (uint32_t)p.B);
-            const int b_m = (int)(mine - (uint32_t)slot_m * (uint32_t)p.B);
-            int vs; float bias;
-            if (slot_m == 0) { vs = E_GA1; coef_m = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU1]; }
-            else if (slot_m == 1) { vs = E_GA2; coef_m = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU2]; }
-            else if (slot_m < 2 + p.S) { vs = E_V1; coef_m = p.gn1[(size_t)(slot_m - 2) * p.B + b_m]; bias = coef_m; }
-            else { vs = E_V2; coef_m = p.gn2[(size_t)(slot_m - 2 - p.S) * p.B + b_m]; bias = coef_m; }
-            if (!s.live) { coef_m = 0.f; bias = 0.f; }
-            off_m = (b_m * E_NV + vs) * p.dp;
+        // two-chunk segments: absorbed by their first chunk, skipped by the second (header comment); cnt == 32 whenever
+        // the chunk has a successor
+        const bool single = nr == 1;
+        bool absorb = false, skip = false;
+        if (cont_next && !(single && cont_prev)) absorb = p0 + 64 >= p.n || p.keys_s[p0 + 64] != keyl;
+        if (cont_prev && !(single && cont_next)) skip = p.keys_s[p0 - 32] != key0 || p0 == 32 || p.keys_s[p0 - 33] != key0;
+        const int skipn = skip ? ((heads & ~1u) ? (__ffs(heads & ~1u) - 1) : cnt) : 0;     // positions of the skipped first run
+        int ext = 0;                    // positions of the absorbed tail in the next chunk
+        uint32_t mine_x = 0u;
+        if (absorb) {
+            const int px = p0 + 32 + lane;
+            const bool same = px < p.n && p.keys_s[px] == keyl;
+            const unsigned bal = __ballot_sync(kFull, same);
+            ext = (bal == 0xffffffffu) ? 32 : (__ffs(~bal) - 1);
+            if (lane < ext) mine_x = p.vals_s[px];
+        }
+        // occurrence -> payload row offset, coefficient, bias contribution
+        auto decode = [&](uint32_t occ, bool live, int& off, float& coef, float& bias) {
+            coef = 1.f; bias = 0.f;
+            if (MODE == 0) {
+                off = (int)occ * p.width;
+            } else {
+                const int slot_m = (int)(occ / (uint32_t)p.B);
+                const int b_m = (int)(occ - (uint32_t)slot_m * (uint32_t)p.B);
+                int vs;
+                if (slot_m == 0) { vs = E_GA1; coef = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU1]; }
+                else if (slot_m == 1) { vs = E_GA2; coef = 1.f; bias = p.sc[(size_t)b_m * SC_N + SC_GU2]; }
+                else if (slot_m < 2 + p.S) { vs = E_V1; coef = p.gn1[(size_t)(slot_m - 2) * p.B + b_m]; bias = coef; }
+                else { vs = E_V2; coef = p.gn2[(size_t)(slot_m - 2 - p.S) * p.B + b_m]; bias = coef; }
+                if (!live) { coef = 0.f; bias = 0.f; }
+                off = (b_m * E_NV + vs) * p.dp;
+            }
+        };
+        int off_m, off_x = 0;
+        float coef_m, coef_x = 0.f, bias_m, bias_x = 0.f;
+        decode(mine, s.live, off_m, coef_m, bias_m);
+        if (absorb) decode(mine_x, lane < ext, off_x, coef_x, bias_x);
+        if (MODE == 1) {
             // bias column: lane = position, segmented scan, the last lane of a run applies / parks it
-            const float gb = seg_scan(bias, s.same);
-            if (s.is_last) {
-                if (s.partial) {
+            float gb = seg_scan(bias_m, s.same);
+            if (absorb) {
+                // the absorbed tail's bias terms, summed in position order (lanes below ext), added to the last run
+                float xs = bias_x;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const float t = __shfl_up_sync(kFull, xs, 1 << i);
+                    if (lane >= (1 << i)) xs += t;
+                }
+                xs = __shfl_sync(kFull, xs, ext - 1);
+                if (lane == cnt - 1) gb += xs;
+            }
+            const bool in_first = (s.slot & 1) == 0;
+            const bool parked = s.partial && !(lane == cnt - 1 && absorb);
+            if (s.is_last && !(in_first && skip)) {
+                if (parked) {
                     p.part[(size_t)s.slot * p.pitch + p.dp] = gb;
                 } else {
                     if (p.emit) p.gb_out[s.key] = gb;
@@ -292,7 +336,7 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
                     const int off = __shfl_sync(kFull, off_m, pp);
                     cf[u] = __shfl_sync(kFull, coef_m, pp);
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b0 + u < cnt && inq) {
+                    if (b0 + u < cnt && b0 + u >= skipn && inq) {
                         const float* src = p.payload + (size_t)off + q;
                         if (pay_vec) {
                             v[u] = *reinterpret_cast<const float4*>(src);
@@ -318,6 +362,36 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
                     }
                 }
             }
+            // absorbed tail: the last run continues through `ext` positions of the next chunk
+            for (int b0 = 0; b0 < ext; b0 += UN) {
+                float4 v[UN];
+                float cf[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int pp = (b0 + u) & 31;
+                    const int off = __shfl_sync(kFull, off_x, pp);
+                    cf[u] = __shfl_sync(kFull, coef_x, pp);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + u < ext && inq) {
+                        const float* src = p.payload + (size_t)off + q;
+                        if (pay_vec) {
+                            v[u] = *reinterpret_cast<const float4*>(src);
+                        } else {
+                            v[u].x = src[0];
+                            if (q + 1 < p.width) v[u].y = src[1];
+                            if (q + 2 < p.width) v[u].z = src[2];
+                            if (q + 3 < p.width) v[u].w = src[3];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (b0 + u < ext) {
+                        if (MODE == 0) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                        else { a.x = fmaf(cf[u], v[u].x, a.x); a.y = fmaf(cf[u], v[u].y, a.y); a.z = fmaf(cf[u], v[u].z, a.z); a.w = fmaf(cf[u], v[u].w, a.w); }
+                    }
+                }
+            }
             if (r >= 0 && lane < sq) S[r * sq + lane] = a;
             __syncwarp();
             // ---- phase 2: one optimiser read-modify-write (or one emitted gradient row) per run ----
@@ -337,8 +411,9 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
                         const int hp = __ffs(hm) - 1;                   // position of the rr-th run head
                         hm &= hm - 1;
                         row[u] = __shfl_sync(kFull, s.key, hp);
-                        const bool partial = (rr == 0 && cont_prev) || (rr == nr - 1 && cont_next);
+                        const bool partial = (rr == 0 && cont_prev) || (rr == nr - 1 && cont_next && !absorb);
                         kind[u] = partial ? (hp == 0 ? 2 : 3) : 1;
+                        if (rr == 0 && skip) kind[u] = 0;            // absorbed by the previous chunk
                         if (kind[u] == 1 && p.apply && inq) {
                             const size_t idx = (size_t)row[u] * p.width + q;
                             if (VEC) {
@@ -431,22 +506,28 @@ __device__ __forceinline__ int long_extent(const uint32_t* __restrict__ keys_s, 
 }
 
 __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
+    pdl_enter();
     extern __shared__ float red[];      // [8][K]
-    __shared__ int sh_slot, sh_m;
-    __shared__ uint32_t sh_row;
+    __shared__ int sh_slot[8], sh_m[8];
+    __shared__ uint32_t sh_row[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (p.n + 31) >> 5;
-    for (int c0 = blockIdx.x; c0 < nchunks; c0 += gridDim.x) {
-        if (warp == 0) {
+    // a CTA looks at 8 consecutive chunks at a time, one per warp (long segments are rare once the two-chunk ones are
+    // absorbed by level 1: most CTAs find nothing and leave after one round of key probes)
+    for (int cb = blockIdx.x * 8; cb < nchunks; cb += gridDim.x * 8) {
+        {
+            const int c = cb + warp;
             uint32_t row = 0;
-            const int slot0 = long_segment_start(p.keys_s, p.n, c0, &row);
-            int m = 0;
-            if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c0, row, lane);
-            if (lane == 0) { sh_slot = slot0; sh_m = m; sh_row = row; }
+            int slot0 = -1, m = 0;
+            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row);
+            if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
+            if (lane == 0) { sh_slot[warp] = slot0; sh_m[warp] = m; sh_row[warp] = row; }
         }
         __syncthreads();
-        const int slot0 = sh_slot, m = sh_m;
-        const uint32_t row = sh_row;
+        for (int ci = 0; ci < 8; ++ci) {
+        const int c0 = cb + ci;
+        const int slot0 = sh_slot[ci], m = sh_m[ci];
+        const uint32_t row = sh_row[ci];
         if (slot0 >= 0) {
             // warp w sums partial rows of chunks c0+1+w, c0+1+w+8, ...
             for (int k0 = 0; k0 < p.K; k0 += 32) {
@@ -484,29 +565,37 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
                     p.W[idx] = wv;
                 }
             }
+            __syncthreads();        // `red` is reused by the CTA's next segment
         }
-        __syncthreads();
+        }
+        __syncthreads();            // sh_* are rewritten by the next round
     }
 }
 
 __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
+    pdl_enter();
     extern __shared__ float red[];      // [8][PE]
-    __shared__ int sh_slot, sh_m;
-    __shared__ uint32_t sh_row;
+    __shared__ int sh_slot[8], sh_m[8];
+    __shared__ uint32_t sh_row[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (p.n + 31) >> 5;
     const int PE = p.dp + 4;
-    for (int c0 = blockIdx.x; c0 < nchunks; c0 += gridDim.x) {
-        if (warp == 0) {
+    // a CTA looks at 8 consecutive chunks at a time, one per warp (long segments are rare once the two-chunk ones are
+    // absorbed by level 1: most CTAs find nothing and leave after one round of key probes)
+    for (int cb = blockIdx.x * 8; cb < nchunks; cb += gridDim.x * 8) {
+        {
+            const int c = cb + warp;
             uint32_t row = 0;
-            const int slot0 = long_segment_start(p.keys_s, p.n, c0, &row);
-            int m = 0;
-            if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c0, row, lane);
-            if (lane == 0) { sh_slot = slot0; sh_m = m; sh_row = row; }
+            int slot0 = -1, m = 0;
+            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row);
+            if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
+            if (lane == 0) { sh_slot[warp] = slot0; sh_m[warp] = m; sh_row[warp] = row; }
         }
         __syncthreads();
-        const int slot0 = sh_slot, m = sh_m;
-        const uint32_t row = sh_row;
+        for (int ci = 0; ci < 8; ++ci) {
+        const int c0 = cb + ci;
+        const int slot0 = sh_slot[ci], m = sh_m[ci];
+        const uint32_t row = sh_row[ci];
         if (slot0 >= 0) {
             for (int j0 = 0; j0 <= p.dp; j0 += 32) {       // column dp holds the bias partial
                 const int j = j0 + lane;
@@ -547,8 +636,10 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
                     *P = wv;
                 }
             }
+            __syncthreads();        // `red` is reused by the CTA's next segment
         }
-        __syncthreads();
+        }
+        __syncthreads();            // sh_* are rewritten by the next round
     }
 }
 
@@ -571,12 +662,51 @@ __device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
     return ds.tile_slots[n >> 7];
 }
 
+// fused optimiser step (single-GPU production path): the summed gradient goes straight into the AdaGrad / SGD rule of its
+// element of C | C1 | C2 | Wb instead of through the flat gradient buffer and a second kernel (Optimizers.py:29-32,51).
+// Only taken when every tensor is 16-byte aligned and K % 4 == 0 (launch_dense_finalize checks).
+struct DenseFuse { float* p[4]; float* acc[4]; size_t off[4]; float lr, r1, r2; int adagrad; int on; };
+__device__ __forceinline__ void dense_rule(float& w, float& a, float g, const DenseFuse& f, bool reg) {
+    if (reg) {
+        const float sgn = (w > 0.f) ? 1.f : ((w < 0.f) ? -1.f : 0.f);
+        g += f.r1 * sgn + 2.f * f.r2 * w;
+    }
+    if (f.adagrad) adagrad_apply(w, a, g, f.lr);
+    else w -= f.lr * g;
+}
+
 __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict__ part, DenseSlots ds, size_t n_units_elems,
                                                         const float* __restrict__ dzsum_part, int n_dz_part, int K,
-                                                        float* __restrict__ out, size_t off_wb, int n_elem_blocks) {
+                                                        float* __restrict__ out, size_t off_wb, int n_elem_blocks, DenseFuse fz) {
+    pdl_enter();
     if ((int)blockIdx.x < n_elem_blocks) {
         const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
         if (i0 >= n_units_elems) return;
+        if (fz.on) {
+            const int t = i0 >= fz.off[2] ? 2 : (i0 >= fz.off[1] ? 1 : 0);
+            const size_t li = i0 - fz.off[t];
+            // parameter / accumulator loads issued beside the slot loads (one memory latency)
+            float4 w = *reinterpret_cast<const float4*>(fz.p[t] + li);
+            float4 a = fz.adagrad ? *reinterpret_cast<const float4*>(fz.acc[t] + li) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int nsplit = dense_slots_of(ds, i0);
+            float4 x[8];
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp)
+                x[sp] = sp < nsplit ? *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 s = x[0];
+#pragma unroll
+            for (int sp = 1; sp < 8; ++sp) { s.x += x[sp].x; s.y += x[sp].y; s.z += x[sp].z; s.w += x[sp].w; }
+            for (int sp = 8; sp < nsplit; ++sp) {
+                const float4 y = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
+                s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
+            }
+            const bool reg = fz.r1 != 0.f || fz.r2 != 0.f;
+            dense_rule(w.x, a.x, s.x, fz, reg); dense_rule(w.y, a.y, s.y, fz, reg);
+            dense_rule(w.z, a.z, s.z, fz, reg); dense_rule(w.w, a.w, s.w, fz, reg);
+            *reinterpret_cast<float4*>(fz.p[t] + li) = w;
+            if (fz.adagrad) *reinterpret_cast<float4*>(fz.acc[t] + li) = a;
+            return;
+        }
         if ((n_units_elems & 3) == 0 && (K & 3) == 0) {        // the 4 elements share a row
             const int nsplit = dense_slots_of(ds, i0);
             // all slot loads are issued before the first add (one memory latency, not one per slot); summed in slot order
@@ -614,7 +744,16 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[off_wb + k] = (float)red[0];
+    if (threadIdx.x == 0) {
+        if (fz.on) {
+            float w = fz.p[3][k], a = fz.adagrad ? fz.acc[3][k] : 0.f;
+            dense_rule(w, a, (float)red[0], fz, false);
+            fz.p[3][k] = w;
+            if (fz.adagrad) fz.acc[3][k] = a;
+        } else {
+            out[off_wb + k] = (float)red[0];
+        }
+    }
 }
 
 // elementwise optimiser over up to 5 dense tensors in one launch (blockIdx.y = tensor):
@@ -624,6 +763,7 @@ struct DenseJob { float* p; float* acc; float* grad; size_t n; float reg_l1, reg
 struct DenseJobs { DenseJob j[5]; int count; float lr; int adagrad; };
 
 __global__ void __launch_bounds__(256) k_dense_apply(DenseJobs jobs) {
+    pdl_enter();
     const DenseJob jb = jobs.j[blockIdx.y];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += (size_t)gridDim.x * blockDim.x) {
         float w = jb.p[i];
@@ -668,6 +808,7 @@ __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ loss_pa
                                               const double* __restrict__ reg_part, int n_reg, double invZ,
                                               double adj_l1, double adj_l2, double* __restrict__ cost,
                                               double* __restrict__ cost_mapped) {
+    pdl_enter();
     __shared__ double s0[256], s1[256], s2[256];
     double a = 0.0, b = 0.0, c = 0.0;
     for (int i = threadIdx.x; i < n_loss; i += 256) a += loss_part[i];
@@ -715,7 +856,7 @@ int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const
                       int64_t neg_ld, cudaStream_t st) {
     const int n = (2 + 2 * h->S) * h->B;
     const int blocks = std::min((n + 255) / 256, 4 * h->num_sms);
-    k_entity_keys<<<blocks, 256, 0, st>>>(a1, a2, neg1, neg2, neg_ld, h->B, h->S, h->ent.keys, h->ent.vals);
+    launch_pdl(k_entity_keys, dim3(blocks), dim3(256), 0, st, a1, a2, neg1, neg2, neg_ld, h->B, h->S, h->ent.keys, h->ent.vals);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -783,7 +924,7 @@ static int launch_rows_chunk(rae_engine* h, RowsArgs& p, cudaStream_t st) {
         attr_done[MODE][vec ? 1 : 0] = true;
     }
     const int blocks = (int)std::min<int64_t>((nchunks + WARPS - 1) / WARPS, (int64_t)h->num_sms * 32);
-    kern<<<blocks, 32 * WARPS, smem, st>>>(p, slab_cols);
+    launch_pdl(kern, dim3(blocks), dim3(32 * WARPS), smem, st, p, slab_cols);
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
@@ -810,8 +951,8 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
     r.B = h->B; r.S = h->S; r.dp = h->dp; r.sc = h->sc; r.gn1 = h->gn1; r.gn2 = h->gn2;
     r.tableb = p.Ab; r.accb = p.accAb; r.gb_out = p.gAb_dense;
     if ((rc = launch_rows_chunk<1>(h, r, st))) return rc;
-    const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
-    k_entity_long2<<<blocks2, 256, sizeof(float) * 8 * (h->dp + 4), st>>>(p);
+    const int blocks2 = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
+    launch_pdl(k_entity_long2, dim3(blocks2), dim3(256), sizeof(float) * 8 * (h->dp + 4), st, p);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -836,8 +977,8 @@ static int rows_update(rae_engine* h, float* table, float* acc, float* g_out, in
     r.table = table; r.acc = acc; r.g_out = g_out; r.part = p.part;
     r.lr = p.lr; r.adagrad = p.adagrad; r.emit = emit; r.apply = apply;
     if ((rc = launch_rows_chunk<0>(h, r, st))) return rc;
-    const int blocks2 = (int)std::min<int64_t>(nchunks, (int64_t)h->num_sms * 16);
-    k_w_long2<<<blocks2, 256, sizeof(float) * 8 * width, st>>>(p);
+    const int blocks2 = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
+    launch_pdl(k_w_long2, dim3(blocks2), dim3(256), sizeof(float) * 8 * width, st, p);
     h->launches += 2;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -874,15 +1015,37 @@ int launch_rows_apply(rae_engine* h, float* table, float* acc, int width, const 
     return rows_update(h, table, acc, nullptr, width, keys_s, vals_s, grads, n, false, true, st);
 }
 
-int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
+int launch_dense_finalize(rae_engine* h, cudaStream_t st, bool fuse_apply) {
     const size_t n_units = (size_t)h->off_gWb;   // elements of [C | C1 | C2]
+    DenseFuse fz{};
+    h->dense_fused = false;
+    if (fuse_apply && !h->debug_dense && !h->emit_only && (n_units & 3) == 0 && (h->K & 3) == 0) {
+        const bool regdec = (h->cfg.l1 != 0.0 || h->cfg.l2 != 0.0) && h->cfg.ext_reg;
+        fz.lr = (float)h->cfg.lr; fz.adagrad = h->adagrad;
+        fz.r1 = regdec ? (float)(h->cfg.adj * h->cfg.l1) : 0.f;
+        fz.r2 = regdec ? (float)(h->cfg.adj * h->cfg.l2) : 0.f;
+        // tensors in the order of the flat layout [C | C1 | C2]; absent ones have zero extent (their offsets coincide)
+        const int pid[4] = {RAE_P_C, RAE_P_C1, RAE_P_C2, RAE_P_WB};
+        const size_t off[4] = {(size_t)h->off_gC, (size_t)h->off_gC1, (size_t)h->off_gC2, (size_t)h->off_gWb};
+        bool ok = true;
+        for (int t = 0; t < 4; ++t) {
+            fz.p[t] = h->P[pid[t]]; fz.acc[t] = h->ACC[pid[t]]; fz.off[t] = off[t];
+            const bool present = t == 3 || (t == 0 ? h->hasM : h->hasSP);
+            if (!present) continue;
+            if (fz.p[t] == nullptr || (h->adagrad && fz.acc[t] == nullptr)) ok = false;
+            if (t < 3 && (((uintptr_t)fz.p[t] | (uintptr_t)fz.acc[t]) & 15)) ok = false;
+        }
+        if (!h->hasM) fz.off[0] = 0;      // C absent: element 0 belongs to C1 (off_gC1 == 0)
+        fz.on = ok ? 1 : 0;
+        h->dense_fused = ok;
+    }
     const int n_elem_blocks = (int)((n_units + 1023) / 1024);
     DenseSlots ds{};
     ds.uniform = h->gC_nsplit;
     ds.d = h->d; ds.K = h->K; ds.hasM = h->hasM ? 1 : 0;
     if (h->use_tc) { ds.tile_slots = h->tc.tile_slots; ds.DP = h->tc.DP; ds.n_bil_rows = h->tc.n_bil_rows; }
-    k_dense_finalize<<<n_elem_blocks + h->K, 256, 0, st>>>(h->gC_part, ds, n_units, h->dzsum_part, h->dz_part_used, h->K,
-                                                          h->dense_grad, (size_t)h->off_gWb, n_elem_blocks);
+    launch_pdl(k_dense_finalize, dim3(n_elem_blocks + h->K), dim3(256), 0, st, h->gC_part, ds, n_units, h->dzsum_part, h->dz_part_used, h->K,
+                                                          h->dense_grad, (size_t)h->off_gWb, n_elem_blocks, fz);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -890,6 +1053,7 @@ int launch_dense_finalize(rae_engine* h, cudaStream_t st) {
 
 int launch_dense_apply(rae_engine* h, cudaStream_t st) {
     const bool reg = (h->cfg.l1 != 0.0 || h->cfg.l2 != 0.0);
+    if (h->dense_fused && !h->dense_w) return RAE_OK;      // applied inside k_dense_finalize
     const bool regdec = reg && h->cfg.ext_reg;
     const size_t dd = (size_t)h->d * h->d * h->K, dk = (size_t)h->d * h->K;
     const float r1 = (float)(h->cfg.adj * h->cfg.l1), r2 = (float)(h->cfg.adj * h->cfg.l2);
@@ -906,16 +1070,18 @@ int launch_dense_apply(rae_engine* h, cudaStream_t st) {
         j.write_back = h->debug_dense ? 1 : 0;
         nmax = std::max(nmax, n);
     };
-    if (h->hasM) add(RAE_P_C, h->dense_grad + h->off_gC, dd, regdec);
-    if (h->hasSP) {
-        add(RAE_P_C1, h->dense_grad + h->off_gC1, dk, regdec);
-        add(RAE_P_C2, h->dense_grad + h->off_gC2, dk, regdec);
+    if (!h->dense_fused) {
+        if (h->hasM) add(RAE_P_C, h->dense_grad + h->off_gC, dd, regdec);
+        if (h->hasSP) {
+            add(RAE_P_C1, h->dense_grad + h->off_gC1, dk, regdec);
+            add(RAE_P_C2, h->dense_grad + h->off_gC2, dk, regdec);
+        }
+        add(RAE_P_WB, h->dense_grad + h->off_gWb, (size_t)h->K, false);
     }
-    add(RAE_P_WB, h->dense_grad + h->off_gWb, (size_t)h->K, false);
     // regulariser makes dW dense: gW_dense holds the data gradient (zero rows elsewhere)
     if (h->dense_w) add(RAE_P_W, h->gW_dense, (size_t)h->cfg.F * h->K, reg);
     const int bx = (int)std::min<size_t>((nmax + 255) / 256, (size_t)h->num_sms * 8);
-    k_dense_apply<<<dim3(bx, jobs.count), 256, 0, st>>>(jobs);
+    launch_pdl(k_dense_apply, dim3(bx, jobs.count), dim3(256), 0, st, jobs);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -946,7 +1112,7 @@ int launch_cost(rae_engine* h, cudaStream_t st) {
         }
     }
     const int n_loss = h->n_loss_part;
-    k_cost<<<1, 256, 0, st>>>(h->loss_part, n_loss, h->reg_part, n_reg, 1.0 / h->Z, h->cfg.adj * h->cfg.l1,
+    launch_pdl(k_cost, dim3(1), dim3(256), 0, st, h->loss_part, n_loss, h->reg_part, n_reg, 1.0 / h->Z, h->cfg.adj * h->cfg.l1,
                               h->cfg.adj * h->cfg.l2, h->cost_dev, h->cost_pinned);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());

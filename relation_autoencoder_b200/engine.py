@@ -236,8 +236,19 @@ class Engine:
         torch.cuda.synchronize(self.device)
         return rows.cpu().numpy(), occ.cpu().numpy(), seg.cpu().numpy()[: b.value + 1]
 
-    def set_profiling(self, on: bool):
-        self._check(self.lib.rae_set_profiling(self._h, 1 if on else 0), "rae_set_profiling")
+    def set_profiling(self, on):
+        """False / 0 = off, True / 1 = per-phase (serialised), 2 = timeline of the overlapped step (``timeline()``)."""
+        self._check(self.lib.rae_set_profiling(self._h, int(on)), "rae_set_profiling")
+
+    def timeline(self):
+        """[(mark, stream, microseconds since the step's start)] of the last step run under ``set_profiling(2)``."""
+        buf = C.create_string_buffer(8192)
+        self._check(self.lib.rae_get_timeline(self._h, buf, len(buf)), "rae_get_timeline")
+        out = []
+        for ln in buf.value.decode().splitlines():
+            n, s, t = ln.split()
+            out.append((n, int(s), float(t)))
+        return out
 
     def phase_times_ms(self) -> Dict[str, float]:
         buf = (C.c_float * L.RAE_NUM_PHASES)()
