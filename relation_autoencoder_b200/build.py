@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librae.so")
-SOURCES = ["rae_engine.cu", "rae_encoder.cu", "rae_decoder_simt.cu", "rae_decoder_tc.cu", "rae_update.cu", "rae_peer.cu", "rae_sampler.cu"]
+SOURCES = ["rae_engine.cu", "rae_encoder.cu", "rae_decoder_simt.cu", "rae_decoder_tc.cu", "rae_update.cu", "rae_sort.cu", "rae_peer.cu", "rae_sampler.cu"]
 HEADERS = ["rae_common.cuh", "rae_internal.h", os.path.join("..", "..", "include", "rae.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -128,8 +128,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
             RAE_CUDA(h, cudaEventRecord(h->ev_prepc, h->s2));
             RAE_MARK("prep_c", h->s2, 2);
         }
-        if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
-        if ((rc = sort_pairs(h, h->ent, n_occ, se, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
+        if ((rc = sort_entities(h, a1, a2, neg1, neg2, neg_ld, se))) return rc;
         RAE_MARK("entity_sort", se, 1);
     }
     RAE_PHASE();   // 0 encoder forward: q, log q, entropy
@@ -137,8 +136,7 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
     RAE_MARK("encoder", st, 0);
     RAE_PHASE();   // 1 entity occurrence keys -> stable sort -> segments (depends on the indices only)
     if (!overlap) {
-        if ((rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
-        if ((rc = sort_pairs(h, h->ent, n_occ, st, h->ent_cub_tmp, h->ent_cub_bytes))) return rc;
+        if ((rc = sort_entities(h, a1, a2, neg1, neg2, neg_ld, st))) return rc;
     }
     RAE_PHASE();   // 2 feature sort (skipped when the per-batch transposed index was cached at bind time)
     if (f_keys_s == nullptr) {
@@ -433,6 +431,7 @@ int rae_create(const rae_config* cfg, rae_engine** out) {
     cudaDeviceProp prop;
     RAE_CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
+    h->coop_launch = prop.cooperativeLaunch != 0;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (prop.major < 10) {
         fail(nullptr, RAE_ENODEVICE, "device %d is sm_%d%d: librae is built for sm_100a only", cfg->device, prop.major, prop.minor);

@@ -183,6 +183,7 @@ struct rae_engine {
     int32_t* stat_dev;   // [2] device scratch for unique-row counts
     int launches;
     int num_sms;
+    bool coop_launch;           // the device supports cooperative launches (rae_sort.cu)
     int max_smem_optin;
     char err[512];
 };
@@ -227,6 +228,17 @@ int tc_grad_dense(rae_engine* h, cudaStream_t st);
 
 // ---- sort / segment / updates (rae_update.cu) ----
 size_t segwork_temp_bytes(int64_t n);
+constexpr int64_t RAE_OWN_SORT_MAX = 1 << 20;
+// rae_sort.cu: one cooperative kernel, stable, ceil(key_bits / 8) passes
+size_t radix_sort_temp_bytes(int64_t n, int num_sms);
+int radix_sort_pairs(rae_engine* h, const uint32_t* keys, const uint32_t* vals, uint32_t* keys_s, uint32_t* vals_s, int64_t n,
+                     int key_bits, cudaStream_t st, void* tmp, size_t tmp_bytes);
+int radix_sort_entities(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
+                        int64_t neg_ld, uint32_t* keys_s, uint32_t* vals_s, int key_bits, cudaStream_t st, void* tmp,
+                        size_t tmp_bytes);
+// entity occurrences -> h->ent.keys_s / vals_s (rows ascending, equal rows in occurrence order)
+int sort_entities(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                  cudaStream_t st);
 int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
                       int64_t neg_ld, cudaStream_t st);
 int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indices, cudaStream_t st);

@@ -132,7 +132,7 @@ struct EntArgs {
 
 
 // does a multi-chunk segment start in chunk c?  returns its first partial slot (or -1) and its row
-__device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ keys_s, int n, int c, uint32_t* row) {
+__device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ keys_s, int n, int c, uint32_t* row, bool absorbing) {
     const int p0 = c << 5;
     const int cnt = min(32, n - p0);
     if (p0 + cnt >= n) return -1;
@@ -140,7 +140,7 @@ __device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ k
     if (keys_s[p0 + cnt] != keyl) return -1;          // last run ends with the chunk
     *row = keyl;
     const bool starts_here = !(keys_s[p0] == keyl && p0 > 0 && keys_s[p0 - 1] == keyl);
-    if (starts_here && (p0 + 64 >= n || keys_s[p0 + 64] != keyl)) return -1;     // spans two chunks: absorbed by level 1
+    if (absorbing && starts_here && (p0 + 64 >= n || keys_s[p0 + 64] != keyl)) return -1;     // spans two chunks: absorbed by level 1
     if (keys_s[p0] == keyl) {                          // run covers the chunk from its first position
         if (p0 > 0 && keys_s[p0 - 1] == keyl) return -1;   // ... and continues an earlier chunk: not the start
         return 2 * c;
@@ -222,6 +222,7 @@ struct RowsArgs {
 };
 
 constexpr int ROWS_TILE = 128;     // columns per pass (one float4 per lane)
+#define ROWS_ABSORB(MODE) ((MODE) == 0)
 
 // MODE 0: feature rows (payload row = dz[val,:], coefficient 1).  MODE 1: entity rows (occurrence decode, coefficient,
 // bias scalar).  VEC: the table rows are 16-byte aligned (width % 4 == 0).
@@ -250,9 +251,12 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
         // two-chunk segments: absorbed by their first chunk, skipped by the second (header comment); cnt == 32 whenever
         // the chunk has a successor
         const bool single = nr == 1;
+        // (feature rows only: measured, the probes and the tail pass cost the entity kernel more than level 2 saves)
         bool absorb = false, skip = false;
-        if (cont_next && !(single && cont_prev)) absorb = p0 + 64 >= p.n || p.keys_s[p0 + 64] != keyl;
-        if (cont_prev && !(single && cont_next)) skip = p.keys_s[p0 - 32] != key0 || p0 == 32 || p.keys_s[p0 - 33] != key0;
+        if (ROWS_ABSORB(MODE)) {
+            if (cont_next && !(single && cont_prev)) absorb = p0 + 64 >= p.n || p.keys_s[p0 + 64] != keyl;
+            if (cont_prev && !(single && cont_next)) skip = p.keys_s[p0 - 32] != key0 || p0 == 32 || p.keys_s[p0 - 33] != key0;
+        }
         const int skipn = skip ? ((heads & ~1u) ? (__ffs(heads & ~1u) - 1) : cnt) : 0;     // positions of the skipped first run
         int ext = 0;                    // positions of the absorbed tail in the next chunk
         uint32_t mine_x = 0u;
@@ -488,9 +492,14 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
 }
 
 
-// level 2, one CTA per chunk: if a multi-chunk segment starts here, lanes of warp 0 probe the first key of the next
-// chunks 32 at a time to find its extent, the 8 warps sum disjoint strided subsets of its partial rows, and the CTA
-// combines them in warp order.
+// level 2: a CTA looks at 8 consecutive chunks at a time, one per warp.  If a multi-chunk segment starts in the warp's chunk,
+// its lanes probe the first key of the next chunks 32 at a time to find its extent m.  Short segments (m <= LONG_WARP_MAX
+// following chunks - nearly all of them: a run cut by one chunk boundary) are finished by the warp itself: the partial rows,
+// the table row and the accumulator row are all in flight together, summed in chunk order, one optimiser read-modify-write.
+// The few hot rows (Zipf head, hundreds of chunks) are left to the whole CTA: 8 warps sum disjoint strided subsets of the
+// partial rows and the CTA combines them in warp order.
+constexpr int LONG_WARP_MAX = 8;
+
 template <int ROWLEN_MAX>
 __device__ __forceinline__ int long_extent(const uint32_t* __restrict__ keys_s, int nchunks, int c0, uint32_t row, int lane) {
     int m = 0;
@@ -505,6 +514,53 @@ __device__ __forceinline__ int long_extent(const uint32_t* __restrict__ keys_s, 
     return m;
 }
 
+// warp path: row[0..width) of (table, acc) updated with part[slot0] + sum_{i<m} part[2 (c0+1+i)] (pitch floats per slot)
+__device__ __forceinline__ void long2_warp_row(const float* __restrict__ part, int pitch, int width, int slot0, int c0, int m,
+                                               float* __restrict__ trow, float* __restrict__ arow, float* __restrict__ grow, float lr,
+                                               int adagrad, int emit, int apply, int lane) {
+    const bool vec = ((width | pitch) & 3) == 0;
+    if (vec) {
+        for (int q = 4 * lane; q < width; q += 128) {
+            float4 x[LONG_WARP_MAX];
+            const float4 g0 = *reinterpret_cast<const float4*>(part + (size_t)slot0 * pitch + q);
+#pragma unroll
+            for (int u = 0; u < LONG_WARP_MAX; ++u)
+                x[u] = u < m ? *reinterpret_cast<const float4*>(part + (size_t)(2 * (c0 + 1 + u)) * pitch + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f), a = w;
+            if (apply) {
+                w = *reinterpret_cast<const float4*>(trow + q);
+                if (adagrad) a = *reinterpret_cast<const float4*>(arow + q);
+            }
+            float4 g = g0;
+#pragma unroll
+            for (int u = 0; u < LONG_WARP_MAX; ++u) { g.x += x[u].x; g.y += x[u].y; g.z += x[u].z; g.w += x[u].w; }
+            if (emit) *reinterpret_cast<float4*>(grow + q) = g;
+            if (apply) {
+                opt_apply4(w, a, g, lr, adagrad);
+                *reinterpret_cast<float4*>(trow + q) = w;
+                if (adagrad) *reinterpret_cast<float4*>(arow + q) = a;
+            }
+        }
+    } else {
+        for (int q = lane; q < width; q += 32) {
+            float g = part[(size_t)slot0 * pitch + q];
+            for (int u = 0; u < m; ++u) g += part[(size_t)(2 * (c0 + 1 + u)) * pitch + q];
+            if (emit) grow[q] = g;
+            if (apply) {
+                float w = trow[q];
+                if (adagrad) {
+                    float a = arow[q];
+                    adagrad_apply(w, a, g, lr);
+                    arow[q] = a;
+                } else {
+                    w -= lr * g;
+                }
+                trow[q] = w;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
     pdl_enter();
     extern __shared__ float red[];      // [8][K]
@@ -512,23 +568,26 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
     __shared__ uint32_t sh_row[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (p.n + 31) >> 5;
-    // a CTA looks at 8 consecutive chunks at a time, one per warp (long segments are rare once the two-chunk ones are
-    // absorbed by level 1: most CTAs find nothing and leave after one round of key probes)
     for (int cb = blockIdx.x * 8; cb < nchunks; cb += gridDim.x * 8) {
         {
             const int c = cb + warp;
             uint32_t row = 0;
             int slot0 = -1, m = 0;
-            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row);
+            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row, ROWS_ABSORB(0));
             if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
+            if (slot0 >= 0 && m <= LONG_WARP_MAX) {
+                const size_t ro = (size_t)row * p.K;
+                long2_warp_row(p.part, p.K, p.K, slot0, c, m, p.W + ro, p.accW + ro, p.gW_dense + ro, p.lr, p.adagrad, p.emit, p.apply, lane);
+                slot0 = -1;
+            }
             if (lane == 0) { sh_slot[warp] = slot0; sh_m[warp] = m; sh_row[warp] = row; }
         }
         __syncthreads();
         for (int ci = 0; ci < 8; ++ci) {
-        const int c0 = cb + ci;
-        const int slot0 = sh_slot[ci], m = sh_m[ci];
-        const uint32_t row = sh_row[ci];
-        if (slot0 >= 0) {
+            const int c0 = cb + ci;
+            const int slot0 = sh_slot[ci], m = sh_m[ci];
+            const uint32_t row = sh_row[ci];
+            if (slot0 < 0) continue;
             // warp w sums partial rows of chunks c0+1+w, c0+1+w+8, ...
             for (int k0 = 0; k0 < p.K; k0 += 32) {
                 const int k = k0 + lane;
@@ -567,7 +626,6 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
             }
             __syncthreads();        // `red` is reused by the CTA's next segment
         }
-        }
         __syncthreads();            // sh_* are rewritten by the next round
     }
 }
@@ -580,23 +638,42 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (p.n + 31) >> 5;
     const int PE = p.dp + 4;
-    // a CTA looks at 8 consecutive chunks at a time, one per warp (long segments are rare once the two-chunk ones are
-    // absorbed by level 1: most CTAs find nothing and leave after one round of key probes)
     for (int cb = blockIdx.x * 8; cb < nchunks; cb += gridDim.x * 8) {
         {
             const int c = cb + warp;
             uint32_t row = 0;
             int slot0 = -1, m = 0;
-            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row);
+            if (c < nchunks) slot0 = long_segment_start(p.keys_s, p.n, c, &row, ROWS_ABSORB(1));
             if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
+            if (slot0 >= 0 && m <= LONG_WARP_MAX) {
+                const size_t ro = (size_t)row * p.d;
+                long2_warp_row(p.part, PE, p.d, slot0, c, m, p.A + ro, p.accA + ro, p.gA_dense + ro, p.lr, p.adagrad, p.emit, p.apply, lane);
+                if (lane == 0) {        // bias partial at column dp
+                    float g = p.part[(size_t)slot0 * PE + p.dp];
+                    for (int u = 0; u < m; ++u) g += p.part[(size_t)(2 * (c + 1 + u)) * PE + p.dp];
+                    if (p.emit) p.gAb_dense[row] = g;
+                    if (p.apply) {
+                        float wv = p.Ab[row];
+                        if (p.adagrad) {
+                            float a = p.accAb[row];
+                            adagrad_apply(wv, a, g, p.lr);
+                            p.accAb[row] = a;
+                        } else {
+                            wv -= p.lr * g;
+                        }
+                        p.Ab[row] = wv;
+                    }
+                }
+                slot0 = -1;
+            }
             if (lane == 0) { sh_slot[warp] = slot0; sh_m[warp] = m; sh_row[warp] = row; }
         }
         __syncthreads();
         for (int ci = 0; ci < 8; ++ci) {
-        const int c0 = cb + ci;
-        const int slot0 = sh_slot[ci], m = sh_m[ci];
-        const uint32_t row = sh_row[ci];
-        if (slot0 >= 0) {
+            const int c0 = cb + ci;
+            const int slot0 = sh_slot[ci], m = sh_m[ci];
+            const uint32_t row = sh_row[ci];
+            if (slot0 < 0) continue;
             for (int j0 = 0; j0 <= p.dp; j0 += 32) {       // column dp holds the bias partial
                 const int j = j0 + lane;
                 float acc = 0.f;
@@ -637,7 +714,6 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
                 }
             }
             __syncthreads();        // `red` is reused by the CTA's next segment
-        }
         }
         __syncthreads();            // sh_* are rewritten by the next round
     }
@@ -849,7 +925,24 @@ size_t segwork_temp_bytes(int64_t n) {
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (int)n, 0, 32, (cudaStream_t)0);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, (cudaStream_t)0);
-    return (a > b ? a : b) + 256;
+    const size_t own = radix_sort_temp_bytes(n, 256);      // rae_sort.cu (any SM count up to 256)
+    return std::max(std::max(a, b), own) + 256;
+}
+
+// pairs up to this count go through the one-kernel cooperative sort (rae_sort.cu); device-wide sorts of more pairs than
+// that (bind-time sorts of a whole split, config 5's global batch on one GPU) are bandwidth-bound and stay with the
+// library's onesweep
+static bool own_sort(const rae_engine* h, int64_t n) { return h->coop_launch && n <= RAE_OWN_SORT_MAX; }
+
+int sort_entities(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2, int64_t neg_ld,
+                  cudaStream_t st) {
+    const int64_t n = (int64_t)(2 + 2 * h->S) * h->B;
+    if (own_sort(h, n))
+        return radix_sort_entities(h, a1, a2, neg1, neg2, neg_ld, h->ent.keys_s, h->ent.vals_s, h->ent.key_bits, st, h->ent_cub_tmp,
+                                   h->ent_cub_bytes);
+    int rc = build_entity_keys(h, a1, a2, neg1, neg2, neg_ld, st);
+    if (rc) return rc;
+    return sort_pairs(h, h->ent, n, st, h->ent_cub_tmp, h->ent_cub_bytes);
 }
 
 int build_entity_keys(rae_engine* h, const int32_t* a1, const int32_t* a2, const int32_t* neg1, const int32_t* neg2,
@@ -873,6 +966,7 @@ int build_feature_keys(rae_engine* h, const int32_t* indptr, const int32_t* indi
 int sort_pairs(rae_engine* h, SegWork& w, int64_t n, cudaStream_t st, void* tmp, size_t tmp_bytes) {
     if (n > w.capacity) return fail(h, RAE_EINVAL, "internal: sort workspace too small (%lld > %lld)", (long long)n, (long long)w.capacity);
     if (n <= 0) return RAE_OK;
+    if (own_sort(h, n)) return radix_sort_pairs(h, w.keys, w.vals, w.keys_s, w.vals_s, n, w.key_bits, st, tmp, tmp_bytes);
     size_t bytes = tmp_bytes;
     // LSD radix sort is stable: equal rows keep ascending occurrence order == np.argsort(kind='stable')
     RAE_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, bytes, w.keys, w.keys_s, w.vals, w.vals_s, (int)n, 0,
