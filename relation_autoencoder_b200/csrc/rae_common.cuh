@@ -62,6 +62,13 @@ __device__ __forceinline__ float sigmoidf(float x) {
 }
 
 __device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }
+// 16-byte read-only load that stays where it is written (volatile asm keeps program order): a run of these is issued back
+// to back, so the loads of a thread cost one memory latency instead of one each
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 // AdaGrad row rule, Optimizers.py:29-32: acc' = acc + g^2 ; p' = p - lr*g/(sqrt(acc') + 1e-6)
 // sqrt.approx / rcp.approx (1 ulp each, MUFU) instead of the IEEE sequences: the update kernels are instruction-bound and

@@ -275,6 +275,13 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
     return v;
 }
 
+// the same for data this kernel also writes (no read-only path)
+__device__ __forceinline__ float ldg_ordered(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // 16 bytes x 4 of one row -> 16 floats
 __device__ __forceinline__ void load16(const float* p, bool ok0, bool ok1, bool ok2, bool ok3, float (&x)[16]) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -864,14 +871,17 @@ __global__ void __launch_bounds__(256) k_tc_combine(const float* __restrict__ vT
             else v0 = vT[(size_t)((j >> 1) & 1) * plane + idx];
             const int np = DP == 128 ? ns : 2 * ns;                     // planes of wT that hold column j
             const int first = DP == 128 ? (j >> 6) : 0, step = DP == 128 ? 2 : 1;
+            // unconditional loads from clamped plane indices (volatile asm: issued back to back, one latency); planes beyond np
+            // re-read the last valid one and are dropped by the select.  (As conditional loads they compiled into a
+            // load - add chain through one register.)
             float wv[MAXP];
 #pragma unroll
-            for (int s = 0; s < MAXP; ++s) wv[s] = s < np ? wT[(size_t)(first + step * s) * plane + idx] : 0.f;
+            for (int s = 0; s < MAXP; ++s) wv[s] = ldg_stream(wT + (size_t)(first + step * min(s, np - 1)) * plane + idx);
             for (int s = MAXP; s < np; ++s) w += wT[(size_t)(first + step * s) * plane + idx];      // (more than 16 planes: tiny tiles only)
             if (spT != nullptr) { c1 = spT[idx]; c2 = spT[plane + idx]; }
             v = v0 + v1;
 #pragma unroll
-            for (int s = 0; s < MAXP; ++s) w += wv[s];
+            for (int s = 0; s < MAXP; ++s) w += s < np ? wv[s] : 0.f;
         }
         tv[r][tx] = v;
         tw[r][tx] = w;
@@ -1751,14 +1761,27 @@ __global__ void __launch_bounds__(1024) k_tc_bwd_finish(float* __restrict__ ev, 
     float* dzs = fin_smem + 32 * KS;       // [32][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b0 = blockIdx.x * 32;
+    // Every loop below is "4 strided elements per lane" (K, d <= 128): the loads of all four are issued before the first use
+    // (volatile asm, clamped addresses, results dropped by selects) - the kernel runs one 1024-thread CTA per SM, so a chain of
+    // dependent round trips is paid in full (18.7 us for 21 MB before, ncu long-scoreboard).
     {
         const int ns = tcs_nslots(sch_dq, b0 >> 7);
-        const int b = b0 + lane;
-        for (int k = warp; k < K; k += 32) {
+        const int b = b0 + lane, bb = min(b, B - 1);
+        float t[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+                t[u][sl] = ldg_stream(dqT + ((size_t)min(sl, ns - 1) * NK + min(warp + 32 * u, K - 1)) * B + bb);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = warp + 32 * u;
+            if (k >= K) continue;
             float v = 0.f;
-            if (b < B)
-                for (int s = 0; s < ns; ++s) v += dqT[((size_t)s * NK + k) * B + b];
-            sdq[lane * KS + k] = v;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) v += sl < ns ? t[u][sl] : 0.f;
+            for (int sl = 4; sl < ns; ++sl) v += dqT[((size_t)sl * NK + k) * B + bb];
+            sdq[lane * KS + k] = b < B ? v : 0.f;
         }
     }
     __syncthreads();
@@ -1767,25 +1790,51 @@ __global__ void __launch_bounds__(1024) k_tc_bwd_finish(float* __restrict__ ev, 
         const int b = b0 + e;
         if (b < B) {
             float* evb = ev + (size_t)b * E_NV * dp;
+            float lq[4], qq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = min(lane + 32 * u, K - 1);
+                lq[u] = ldg_stream(logq + (size_t)b * K + kk);
+                qq[u] = ldg_stream(q + (size_t)b * K + kk);
+            }
             if (hasSP) {
                 // d cost / d L = M c + SP term, d cost / d R = M^T a + SP term: k_tc_combine left M c and M^T a in E_GA1 / E_GA2
                 const float gp = sc[(size_t)b * SC_N + SC_GP], g1 = sc[(size_t)b * SC_N + SC_G1], g2 = sc[(size_t)b * SC_N + SC_G2];
-                for (int j = lane; j < d; j += 32) {
-                    evb[E_GA1 * dp + j] = fmaf(gp + g2, evb[E_C1 * dp + j], evb[E_GA1 * dp + j]);
-                    evb[E_GA2 * dp + j] = fmaf(gp + g1, evb[E_C2 * dp + j], evb[E_GA2 * dp + j]);
+                float x1[4], x2[4], y1[4], y2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = min(lane + 32 * u, d - 1);
+                    x1[u] = ldg_ordered(evb + E_GA1 * dp + jj); y1[u] = ldg_ordered(evb + E_C1 * dp + jj);
+                    x2[u] = ldg_ordered(evb + E_GA2 * dp + jj); y2[u] = ldg_ordered(evb + E_C2 * dp + jj);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = lane + 32 * u;
+                    if (j < d) {
+                        evb[E_GA1 * dp + j] = fmaf(gp + g2, y1[u], x1[u]);
+                        evb[E_GA2 * dp + j] = fmaf(gp + g1, y2[u], x2[u]);
+                    }
                 }
             }
-            float dot = 0.f;
-            for (int k = lane; k < K; k += 32) {
-                const float v = fmaf(ent_coef, logq[(size_t)b * K + k] + 1.f, sdq[e * KS + k]);
-                dzs[e * K + k] = v;
-                dot = fmaf(q[(size_t)b * K + k], v, dot);
+            float dot = 0.f, vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = lane + 32 * u;
+                vv[u] = 0.f;
+                if (k < K) {
+                    vv[u] = fmaf(ent_coef, lq[u] + 1.f, sdq[e * KS + k]);
+                    dot = fmaf(qq[u], vv[u], dot);
+                }
             }
             dot = warp_sum(dot);
-            for (int k = lane; k < K; k += 32) {
-                const float v = q[(size_t)b * K + k] * (dzs[e * K + k] - dot);
-                dzs[e * K + k] = v;
-                dz[(size_t)b * K + k] = v;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = lane + 32 * u;
+                if (k < K) {
+                    const float v = qq[u] * (vv[u] - dot);
+                    dzs[e * K + k] = v;
+                    dz[(size_t)b * K + k] = v;
+                }
             }
         } else {
             for (int k = lane; k < K; k += 32) dzs[e * K + k] = 0.f;
