@@ -409,6 +409,15 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
             eng.train_device((2 * (warmup + steps) + s) % nb, want_cost=False)
         dist_phase_ms = eng.phase_times_ms()
         eng.set_profiling(False)
+        if hasattr(eng, "set_timeline"):
+            eng.set_timeline(True)
+            tls = []
+            for r in range(5):
+                for s in range(6):
+                    eng.train_device((2 * (warmup + steps) + 20 + 6 * r + s) % nb, want_cost=False)
+                tls.append(eng.timeline())
+            eng.set_timeline(False)
+            timeline = [[tls[0][i][0], tls[0][i][1], round(float(np.median([t[i][2] for t in tls])), 1)] for i in range(len(tls[0]))]
     if with_phases and world == 1:
         eng.set_profiling(True)
         acc = {}

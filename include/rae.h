@@ -181,7 +181,8 @@ int rae_sparse_rows_apply(rae_engine* h, float* table, float* acc, int64_t width
  * gradient buffers, sum them in rank order (deterministic) and apply the optimiser once per row.  The routing (which
  * rows, which slots) depends only on the ids and is planned once per split / epoch by the host side. */
 #define RAE_MAX_PEERS 16
-#define RAE_FLAG_WORDS 32      /* a rank's flag buffer: RAE_MAX_PEERS barrier epochs, then its local cost (double), padding */
+#define RAE_FLAG_WORDS 64      /* a rank's flag buffer: RAE_MAX_PEERS barrier epochs, its local cost (double), padding to 32; a second
+                                * barrier sequence (the side stream's "A, Ab and dense parameters applied") in words [32, 32 + RAE_MAX_PEERS) */
 #define RAE_IPC_HANDLE_BYTES 64
 /* zero-initialised device allocation + its IPC handle (handle_out: RAE_IPC_HANDLE_BYTES bytes, may be NULL) */
 int rae_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out);
@@ -235,6 +236,15 @@ typedef struct rae_dist_step {
  * dense gradients straight from dense_bufs in rank order when given -> the three pulls -> barrier ("every owner has
  * applied").  The barrier is a one-warp kernel: release-store of the epoch into every peer's flag word, acquire-spin on the
  * own flags (bounded: a rank that never arrives sets the status word instead of hanging the GPU, see rae_peer_status). */
+/* Gradient push (optional, once after rae_create with RAE_FLAG_EMIT_ONLY): gw / ga / gab are HOST arrays of `world` device
+ * pointers to every rank's RECEIVE buffers, float [world][f_cap][K], [world][n_cap][d], [world][n_cap].  From then on the
+ * step's row-update kernels store the reduced gradient row of compact slot j (global row id = f_ids[j] / e_ids[j] of the
+ * rae_dist_step) into the buffer of rank id % world at region [rank][j] instead of this rank's own compact buffer, and the
+ * gw_bufs / ga_bufs / gab_bufs of rae_dist_step must then be the `world` regions of THIS rank's receive buffers (local
+ * pointers): rae_dist_step_end applies from local memory.  The remote traffic becomes posted stores issued beside the
+ * dense-gradient contraction instead of loads on the critical path behind the barrier. */
+int rae_bind_push_targets(rae_engine* h, const void* const* gw, const void* const* ga, const void* const* gab, int32_t world,
+                          int32_t rank, int64_t f_cap, int64_t n_cap);
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream);
 int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream);
 /* func['train'](batch_index, neg1, neg2) form of rae_dist_step_begin: this rank's HOST negatives int32[S,B] with row strides

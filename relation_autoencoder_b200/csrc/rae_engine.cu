@@ -98,7 +98,8 @@ static int run_step(rae_engine* h, const int32_t* indptr, const int32_t* indices
         if (h->profiling) RAE_CUDA(h, cudaEventRecord(h->ev_phase[phase], st));        \
         ++phase;                                                                       \
     } while (0)
-    h->tl_n = 0;
+    if (!h->tl_keep) h->tl_n = 0;
+    h->tl_keep = false;
 #define RAE_MARK(name, strm, sid)                                                          \
     do {                                                                                   \
         if (h->timeline && h->tl_n < RAE_TL_MAX) {                                         \
@@ -541,6 +542,7 @@ void rae_destroy(rae_engine* h) {
         for (int i = 0; i <= RAE_NUM_PHASES; ++i) cudaEventDestroy(h->ev_phase[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_upd[i]);
     }
+    cudaFree(h->push.w_dev);
     if (h->tl_created) {
         for (int i = 0; i < RAE_TL_MAX; ++i) cudaEventDestroy(h->tl_ev[i]);
     }

@@ -166,7 +166,7 @@ struct rae_engine {
     bool neg_staged;            // ev_neg has been recorded at least once (pinned_neg may still be in flight)
     bool neg_direct;            // the last host-negatives copy read the caller's page-locked arrays in place
     int stage_flip;             // which half of the double-buffered device staging the next host step fills
-    int barrier_epoch; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
+    int barrier_epoch, barrier_epoch1; int32_t* peer_err_dev;      // peer-flag barriers issued so far; device status word (timeouts)
     int32_t* peer_err_pinned;                      // page-locked copy of the status word: checked by every rae_dist_* call
     cudaEvent_t pending_wait;                      // if set: the step's main stream waits for it before the decoder reads A
     // explicit-step staging
@@ -178,6 +178,12 @@ struct rae_engine {
     bool profiling; cudaEvent_t ev_phase[RAE_NUM_PHASES + 1]; cudaEvent_t ev_upd[3]; bool ev_created;
     // timeline (rae_set_profiling(h, 2)): the step runs with its normal three-stream overlap and an event is recorded behind
     // every kernel group on the stream it ran on -> the real concurrent schedule (rae_get_timeline)
+    // row-sharded multi-GPU, gradient PUSH (rae_bind_push_targets): the emit-only row-update kernels store each reduced
+    // gradient row straight into its OWNER's receive buffer, region [rank][compact slot] (posted stores over NVLink,
+    // overlapping the dense contraction that runs beside them); the owner then applies from local memory
+    struct { float** w_dev; float** a_dev; float** ab_dev; int world, rank; int64_t f_cap, n_cap; bool on;
+             const int32_t* f_ids; const int32_t* e_ids; } push;
+    bool tl_keep;               // the next run_step appends to the marks recorded by rae_dist_step_begin instead of restarting
     bool timeline; int tl_n; cudaEvent_t tl_ev[RAE_TL_MAX]; const char* tl_name[RAE_TL_MAX]; int tl_stream[RAE_TL_MAX]; bool tl_created;
     const uint32_t* last_f_keys_s; int64_t last_f_n;   // sorted feature keys of the last step (statistics)
     int32_t* stat_dev;   // [2] device scratch for unique-row counts
@@ -261,8 +267,8 @@ int launch_fetch_rows(rae_engine* h, const void* const* tables, int world, int64
 int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const int32_t* rows_local, const int32_t* ent_off,
                       const int32_t* ent_src, const int32_t* ent_slot, int64_t n_rows, const void* const* grads, int world,
                       cudaStream_t st);
-int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st);
-int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st);
+int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st, int kind = 0);
+int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st, int part = 0);
 int launch_dense_finalize(rae_engine* h, cudaStream_t st, bool fuse_apply);  // sum partials -> dense_grad, or (fused) straight into the optimiser rule
 int launch_dense_apply(rae_engine* h, cudaStream_t st);     // AdaGrad/SGD on C,C1,C2,Wb (+ W when dense_w)
 int stage_host_negatives(rae_engine* h, const int32_t* neg1_host, int64_t ld1, const int32_t* neg2_host, int64_t ld2,

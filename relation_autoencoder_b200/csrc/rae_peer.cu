@@ -33,6 +33,7 @@ __device__ __forceinline__ float ld_cv(const float* p) { return __ldcv(p); }
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_fetch_rows(PeerPtrs tabs, int world, int width, const int32_t* __restrict__ ids, int n,
                                                     float* __restrict__ out) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) k_fetch_rows(PeerPtrs tabs, int world, in
 // width == 1 (bias table): one thread per row
 __global__ void __launch_bounds__(256) k_fetch_scalars(PeerPtrs tabs, int world, const int32_t* __restrict__ ids, int n,
                                                        float* __restrict__ out) {
+    pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int id = ids[i];
         out[i] = __ldg(tabs.p[id % world] + id / world);
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) k_pull_apply(float* __restrict__ table, f
                                                     const int32_t* __restrict__ rows_local, const int32_t* __restrict__ ent_off,
                                                     const int32_t* __restrict__ ent_src, const int32_t* __restrict__ ent_slot,
                                                     int n_rows, PeerPtrs grads, float lr, int adagrad, const int32_t* __restrict__ abort) {
+    pdl_enter();
     if (*abort != 0) return;      // a peer barrier of this handle timed out: the peers' gradient rows may be stale
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(256) k_pull_apply_scalars(float* __restrict__ 
                                                             const int32_t* __restrict__ ent_off, const int32_t* __restrict__ ent_src,
                                                             const int32_t* __restrict__ ent_slot, int n_rows, PeerPtrs grads,
                                                             float lr, int adagrad, const int32_t* __restrict__ abort) {
+    pdl_enter();
     if (*abort != 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
         float g = 0.f;
@@ -203,13 +207,14 @@ struct FlagPtrs {
 };
 
 __global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, int32_t* __restrict__ status,
-                               volatile int32_t* __restrict__ status_host) {
+                               volatile int32_t* __restrict__ status_host, int word0) {
+    pdl_enter();
     const int r = threadIdx.x;
     __threadfence_system();
     if (r < world && *status == 0) {
-        int32_t* dst = flags.p[r] + rank;
+        int32_t* dst = flags.p[r] + word0 + rank;
         asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
-        const int32_t* src = flags.p[rank] + r;
+        const int32_t* src = flags.p[rank] + word0 + r;
         const long long t0 = clock64();
         int32_t v;
         for (;;) {
@@ -229,6 +234,7 @@ __global__ void k_peer_barrier(FlagPtrs flags, int rank, int world, int epoch, i
 // global cost = sum of the ranks' local costs in rank order (the same double on every rank); each rank published its own
 // in its flag buffer (words [RAE_MAX_PEERS, RAE_MAX_PEERS+2)) before the "every rank has emitted" barrier
 __global__ void k_global_cost(FlagPtrs flags, int world, double* __restrict__ out_dev, double* __restrict__ out_mapped) {
+    pdl_enter();
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int r = 0; r < world; ++r) {
@@ -262,10 +268,43 @@ __global__ void __launch_bounds__(256) k_check_negatives(const int32_t* __restri
 struct DenseSeg { float* p; float* acc; size_t begin, end; };      // [begin, end) of the flat gradient
 struct DenseSegs { DenseSeg s[4]; int count; };
 
-__global__ void __launch_bounds__(256) k_dense_apply_peers(DenseSegs segs, PeerPtrs grads, int world, size_t n, float* __restrict__ sum_out,
-                                                           float lr, int adagrad, const int32_t* __restrict__ abort) {
+__global__ void __launch_bounds__(256) k_dense_apply_peers(DenseSegs segs, PeerPtrs grads, int world, size_t i_begin, size_t i_end,
+                                                           float* __restrict__ sum_out, float lr, int adagrad, int vec,
+                                                           const int32_t* __restrict__ abort) {
+    pdl_enter();
     if (*abort != 0) return;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (vec) {
+        // 16-byte path (every segment boundary, i_begin and the buffers are 16-byte aligned): 4 elements per thread, the
+        // peers' loads of all of them in flight together
+        for (size_t i = i_begin + 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < i_end; i += 4 * (size_t)gridDim.x * blockDim.x) {
+            float4 x[RAE_MAX_PEERS];
+#pragma unroll
+            for (int r = 0; r < RAE_MAX_PEERS; ++r)
+                x[r] = r < world ? ld_cv4(reinterpret_cast<const float4*>(grads.p[r] + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < RAE_MAX_PEERS; ++r) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
+            if (sum_out) *reinterpret_cast<float4*>(sum_out + i) = g;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < segs.count && i >= segs.s[k].begin && i < segs.s[k].end) {
+                    const size_t j = i - segs.s[k].begin;
+                    float4 w = *reinterpret_cast<const float4*>(segs.s[k].p + j);
+                    if (adagrad) {
+                        float4 a = *reinterpret_cast<const float4*>(segs.s[k].acc + j);
+                        adagrad_apply(w.x, a.x, g.x, lr); adagrad_apply(w.y, a.y, g.y, lr);
+                        adagrad_apply(w.z, a.z, g.z, lr); adagrad_apply(w.w, a.w, g.w, lr);
+                        *reinterpret_cast<float4*>(segs.s[k].acc + j) = a;
+                    } else {
+                        w.x -= lr * g.x; w.y -= lr * g.y; w.z -= lr * g.z; w.w -= lr * g.w;
+                    }
+                    *reinterpret_cast<float4*>(segs.s[k].p + j) = w;
+                }
+            }
+        }
+        return;
+    }
+    for (size_t i = i_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += (size_t)gridDim.x * blockDim.x) {
         float x[RAE_MAX_PEERS];
 #pragma unroll
         for (int r = 0; r < RAE_MAX_PEERS; ++r) x[r] = r < world ? ld_cv(grads.p[r] + i) : 0.f;
@@ -311,12 +350,12 @@ int launch_fetch_rows(rae_engine* h, const void* const* tables, int world, int64
     if (rc) return rc;
     if (width == 1) {
         const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 8);
-        k_fetch_scalars<<<blocks, 256, 0, st>>>(pp, world, ids, (int)n, out);
+        launch_pdl(k_fetch_scalars, dim3(blocks), dim3(256), 0, st, pp, world, ids, (int)n, out);
     } else {
         const int64_t warps = (n + 3) / 4;
         const int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->num_sms * 8);
-        if ((width & 3) == 0) k_fetch_rows<true><<<blocks, 256, 0, st>>>(pp, world, (int)width, ids, (int)n, out);
-        else k_fetch_rows<false><<<blocks, 256, 0, st>>>(pp, world, (int)width, ids, (int)n, out);
+        if ((width & 3) == 0) launch_pdl(k_fetch_rows<true>, dim3(blocks), dim3(256), 0, st, pp, world, (int)width, ids, (int)n, out);
+        else launch_pdl(k_fetch_rows<false>, dim3(blocks), dim3(256), 0, st, pp, world, (int)width, ids, (int)n, out);
     }
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
@@ -334,13 +373,13 @@ int launch_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, co
     const int adagrad = h->adagrad ? 1 : 0;
     if (width == 1) {
         const int blocks = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)h->num_sms * 8);
-        k_pull_apply_scalars<<<blocks, 256, 0, st>>>(table, acc, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
+        launch_pdl(k_pull_apply_scalars, dim3(blocks), dim3(256), 0, st, table, acc, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
     } else {
         const int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)h->num_sms * 16);
         if ((width & 3) == 0)
-            k_pull_apply<true><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
+            launch_pdl(k_pull_apply<true>, dim3(blocks), dim3(256), 0, st, table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
         else
-            k_pull_apply<false><<<blocks, 256, 0, st>>>(table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
+            launch_pdl(k_pull_apply<false>, dim3(blocks), dim3(256), 0, st, table, acc, (int)width, rows_local, ent_off, ent_src, ent_slot, (int)n_rows, pp, lr, adagrad, h->peer_err_dev);
     }
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
@@ -354,7 +393,9 @@ int peer_failed(rae_engine* h) {
                               "untouched from that step on - the run cannot continue");
 }
 
-int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st) {
+// kind 0: words [0, RAE_MAX_PEERS) of the flag buffers; kind 1: words [RAE_FLAG_WORDS / 2, + RAE_MAX_PEERS) - a second,
+// independent barrier sequence for the side stream (the ranks must issue the barriers of one kind in the same order)
+int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, int rank, cudaStream_t st, int kind) {
     if (world < 1 || world > RAE_MAX_PEERS || rank < 0 || rank >= world) return fail(h, RAE_EINVAL, "rae_peer_barrier: bad world / rank");
     FlagPtrs fp;
     memset(&fp, 0, sizeof(fp));
@@ -362,32 +403,43 @@ int launch_peer_barrier(rae_engine* h, const void* const* flag_bufs, int world, 
         if (!flag_bufs[r]) return fail(h, RAE_EINVAL, "rae_peer_barrier: null flag buffer for rank %d", r);
         fp.p[r] = static_cast<int32_t*>(const_cast<void*>(flag_bufs[r]));
     }
-    h->barrier_epoch += 1;
-    k_peer_barrier<<<1, 32, 0, st>>>(fp, rank, world, h->barrier_epoch, h->peer_err_dev, h->peer_err_pinned);
+    int& epoch = kind == 0 ? h->barrier_epoch : h->barrier_epoch1;
+    epoch += 1;
+    launch_pdl(k_peer_barrier, dim3(1), dim3(32), 0, st, fp, rank, world, epoch, h->peer_err_dev, h->peer_err_pinned,
+               kind == 0 ? 0 : RAE_FLAG_WORDS / 2);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
 }
 
-int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st) {
+// part 0: every dense tensor; 1: the decoder tensors C | C1 | C2 only; 2: the encoder bias Wb only (the split tail of the
+// sharded step applies Wb - read by the next step's encoder - on the main stream and the rest on a side stream)
+int launch_dense_apply_peers(rae_engine* h, const void* const* dense_bufs, int world, cudaStream_t st, int part) {
     PeerPtrs pp;
     int rc = fill_peers(h, dense_bufs, world, &pp, "rae_dist_step_end(dense_bufs)");
     if (rc) return rc;
     if (h->dense_w) return fail(h, RAE_EINVAL, "peer dense update does not support l1 / l2 != 0");
     DenseSegs segs{};
+    bool aligned = true;
     auto add = [&](int pid, int64_t begin, int64_t n) {
         if (n <= 0) return;
         DenseSeg& sg = segs.s[segs.count++];
         sg.p = h->P[pid]; sg.acc = h->ACC[pid]; sg.begin = (size_t)begin; sg.end = (size_t)(begin + n);
+        if ((begin & 3) || (n & 3) || (((uintptr_t)sg.p | (uintptr_t)sg.acc) & 15)) aligned = false;
     };
     const int64_t dd = h->hasM ? (int64_t)h->d * h->d * h->K : 0, dk = h->hasSP ? (int64_t)h->d * h->K : 0;
     add(RAE_P_C, h->off_gC, dd);
     add(RAE_P_C1, h->off_gC1, dk);
     add(RAE_P_C2, h->off_gC2, dk);
     add(RAE_P_WB, h->off_gWb, h->K);
-    const size_t n = (size_t)h->n_dense;
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 8);
-    k_dense_apply_peers<<<blocks, 256, 0, st>>>(segs, pp, world, n, nullptr, (float)h->cfg.lr, h->adagrad ? 1 : 0, h->peer_err_dev);
+    for (int r = 0; r < world; ++r)
+        if ((uintptr_t)pp.p[r] & 15) aligned = false;
+    const size_t i_begin = part == 2 ? (size_t)h->off_gWb : 0, i_end = part == 1 ? (size_t)h->off_gWb : (size_t)h->n_dense;
+    if (i_end <= i_begin) return RAE_OK;
+    const size_t n = i_end - i_begin, work = aligned ? (n + 3) / 4 : n;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)h->num_sms * 8);
+    launch_pdl(k_dense_apply_peers, dim3(blocks), dim3(256), 0, st, segs, pp, world, i_begin, i_end, nullptr, (float)h->cfg.lr,
+               h->adagrad ? 1 : 0, aligned ? 1 : 0, h->peer_err_dev);
     h->launches++;
     RAE_CUDA(h, cudaGetLastError());
     return RAE_OK;
@@ -464,6 +516,12 @@ int rae_pull_apply(rae_engine* h, float* table, float* acc, int64_t width, const
 }
 
 int rae_peer_barrier(rae_engine* h, const void* const* flag_bufs, int32_t world, int32_t rank, void* stream) {
+    // a stand-alone barrier orders EVERYTHING this handle has issued: the side streams' tails join the caller's stream first
+    if (h && h->s1 && h->s2) {
+        cudaStream_t st0 = (cudaStream_t)stream;
+        if (cudaEventRecord(h->ev_join1, h->s1) == cudaSuccess) cudaStreamWaitEvent(st0, h->ev_join1, 0);
+        if (cudaEventRecord(h->ev_join2, h->s2) == cudaSuccess) cudaStreamWaitEvent(st0, h->ev_join2, 0);
+    }
     if (!h || !flag_bufs) return fail(h, RAE_EINVAL, "rae_peer_barrier: null argument");
     return launch_peer_barrier(h, flag_bufs, world, rank, (cudaStream_t)stream);
 }
@@ -477,11 +535,48 @@ int rae_peer_status(rae_engine* h, void* stream) {
     return peer_failed(h);
 }
 
+#define RAE_DMARK(name, strm, sid)                                                         \
+    do {                                                                                   \
+        if (h->timeline && h->tl_n < RAE_TL_MAX) {                                         \
+            RAE_CUDA(h, cudaEventRecord(h->tl_ev[h->tl_n], strm));                         \
+            h->tl_name[h->tl_n] = name; h->tl_stream[h->tl_n] = sid; ++h->tl_n;            \
+        }                                                                                  \
+    } while (0)
+
+int rae_bind_push_targets(rae_engine* h, const void* const* gw, const void* const* ga, const void* const* gab, int32_t world,
+                          int32_t rank, int64_t f_cap, int64_t n_cap) {
+    if (!h || !gw || !ga || !gab) return fail(h, RAE_EINVAL, "rae_bind_push_targets: null argument");
+    if (!h->emit_only) return fail(h, RAE_EINVAL, "rae_bind_push_targets needs RAE_FLAG_EMIT_ONLY");
+    if (world < 1 || world > RAE_MAX_PEERS || rank < 0 || rank >= world || f_cap <= 0 || n_cap <= 0)
+        return fail(h, RAE_EINVAL, "rae_bind_push_targets: bad world / rank / capacity");
+    float* host[3][RAE_MAX_PEERS] = {};
+    for (int r = 0; r < world; ++r) {
+        if (!gw[r] || !ga[r] || !gab[r]) return fail(h, RAE_EINVAL, "rae_bind_push_targets: null receive buffer of rank %d", r);
+        host[0][r] = static_cast<float*>(const_cast<void*>(gw[r]));
+        host[1][r] = static_cast<float*>(const_cast<void*>(ga[r]));
+        host[2][r] = static_cast<float*>(const_cast<void*>(gab[r]));
+    }
+    if (h->push.w_dev == nullptr) {
+        float** blk = nullptr;
+        RAE_CUDA(h, cudaMalloc((void**)&blk, 3 * RAE_MAX_PEERS * sizeof(float*)));
+        h->push.w_dev = blk; h->push.a_dev = blk + RAE_MAX_PEERS; h->push.ab_dev = blk + 2 * RAE_MAX_PEERS;
+    }
+    RAE_CUDA(h, cudaMemcpy(h->push.w_dev, host, sizeof(host), cudaMemcpyHostToDevice));
+    h->push.world = world; h->push.rank = rank; h->push.f_cap = f_cap; h->push.n_cap = n_cap;
+    h->push.on = true;
+    return RAE_OK;
+}
+
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_begin: null argument");
     if (peer_failed(h)) return RAE_ECUDA;
+    h->push.f_ids = d->f_ids;
+    h->push.e_ids = d->e_ids;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    h->tl_n = 0;
+    h->tl_keep = true;
+    RAE_DMARK("dist_start", st, 0);
     const bool side = h->s1 != nullptr && !h->profiling;
     if (side) {
         // entity rows arrive on the side stream that sorts the entity occurrences next; the main stream (W rows ->
@@ -491,9 +586,11 @@ int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
         if ((rc = rae_fetch_rows(h, d->a_shards, d->world, h->d, d->e_ids, d->n_e, d->Ac, h->s1))) return rc;
         if ((rc = rae_fetch_rows(h, d->ab_shards, d->world, 1, d->e_ids, d->n_e, d->Abc, h->s1))) return rc;
         RAE_CUDA(h, cudaEventRecord(h->ev_dfetch, h->s1));
+        RAE_DMARK("fetch_entities", h->s1, 1);
         h->pending_wait = h->ev_dfetch;
     }
     if ((rc = rae_fetch_rows(h, d->w_shards, d->world, h->K, d->f_ids, d->n_f, d->Wc, stream))) return rc;
+    RAE_DMARK("fetch_w", st, 0);
     if (!side) {
         if ((rc = rae_fetch_rows(h, d->a_shards, d->world, h->d, d->e_ids, d->n_e, d->Ac, stream))) return rc;
         if ((rc = rae_fetch_rows(h, d->ab_shards, d->world, 1, d->e_ids, d->n_e, d->Abc, stream))) return rc;
@@ -548,10 +645,12 @@ int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
         if ((rc = rae_copy_cost(h, reinterpret_cast<double*>(fp.p[d->rank] + RAE_MAX_PEERS), stream))) return rc;
     }
     // (A) every rank has emitted its gradient rows and its dense gradient
-    if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
+    RAE_DMARK("local_step_done", st, 0);
+    if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st, 0))) return rc;
+    RAE_DMARK("barrier_emitted", st, 0);
     if (gcost) {
         // the caller gets the global cost here, while the pulls below still run (rae_dist_read_cost)
-        k_global_cost<<<1, 32, 0, st>>>(fp, d->world, d->cost_dev, h->gcost_pinned);
+        launch_pdl(k_global_cost, dim3(1), dim3(32), 0, st, fp, d->world, d->cost_dev, h->gcost_pinned);
         h->launches++;
         RAE_CUDA(h, cudaGetLastError());
         RAE_CUDA(h, cudaEventRecord(h->ev_gcost, st));
@@ -565,25 +664,55 @@ int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
         RAE_CUDA(h, cudaStreamWaitEvent(h->s2, h->ev_dfork, 0));
     }
     cudaStream_t sa = side ? h->s1 : st, sb = side ? h->s2 : st;
+    // three independent branches: entity rows on s1, the dense update (reads nothing the applies write) and the biases on
+    // s2, W rows here
+    const bool peer_dense = flags && d->dense_bufs != nullptr;
+    if (peer_dense) {
+        // Wb is read by the NEXT step's encoder on this stream: applied here (K elements); the decoder tensors are next read
+        // by the operand preparation, which runs on s2 itself
+        if (side) {
+            if ((rc = launch_dense_apply_peers(h, d->dense_bufs, d->world, st, 2))) return rc;
+            if ((rc = launch_dense_apply_peers(h, d->dense_bufs, d->world, sb, 1))) return rc;
+        } else if ((rc = launch_dense_apply_peers(h, d->dense_bufs, d->world, st, 0))) {
+            return rc;
+        }
+        RAE_DMARK("dense_apply_peers", sb, side ? 2 : 0);
+    }
     if (d->n_er > 0) {
         if ((rc = rae_pull_apply(h, d->A, d->accA, h->d, d->er_rows, d->er_off, d->e_src, d->e_slot, d->n_er, d->ga_bufs, d->world, sa))) return rc;
+        RAE_DMARK("apply_A", sa, side ? 1 : 0);
         if ((rc = rae_pull_apply(h, d->Ab, d->accAb, 1, d->er_rows, d->er_off, d->e_src, d->e_slot, d->n_er, d->gab_bufs, d->world, sb))) return rc;
+        RAE_DMARK("apply_Ab", sb, side ? 2 : 0);
     }
     if (d->n_fr > 0 && (rc = rae_pull_apply(h, d->W, d->accW, h->K, d->fr_rows, d->fr_off, d->f_src, d->f_slot, d->n_fr, d->gw_bufs,
                                             d->world, stream))) return rc;
-    if (flags && d->dense_bufs != nullptr) {
-        if ((rc = launch_dense_apply_peers(h, d->dense_bufs, d->world, st))) return rc;
-    } else if ((rc = rae_train_step_end(h, stream))) {
-        return rc;
-    }
-    if (side) {
-        RAE_CUDA(h, cudaEventRecord(h->ev_join1, h->s1));
+    RAE_DMARK("apply_W", st, 0);
+    if (!peer_dense && (rc = rae_train_step_end(h, stream))) return rc;
+    if (side && flags) {
+        // Split tail.  The next step's first consumers of the tables are the W fetch and the encoder on this stream: they
+        // need every owner's W apply only.  The entity rows are fetched on s1, so "every owner has applied A, Ab and the
+        // dense update" is a second barrier sequence (kind 1) on s1, behind which s1's next work (the entity fetch of
+        // the next step) is ordered by the stream itself; this stream meets it where the decoder first reads A
+        // (pending_wait).  The applies of A / Ab / the dense parameters thus run beside the next step's head.
         RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
-        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
-        RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
+        RAE_CUDA(h, cudaStreamWaitEvent(h->s1, h->ev_join2, 0));
+        if ((rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, h->s1, 1))) return rc;
+        RAE_DMARK("barrier_rest_applied", h->s1, 1);
+        if ((rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st, 0))) return rc;
+        RAE_DMARK("barrier_w_applied", st, 0);
+    } else {
+        if (side) {
+            RAE_CUDA(h, cudaEventRecord(h->ev_join1, h->s1));
+            RAE_CUDA(h, cudaEventRecord(h->ev_join2, h->s2));
+            RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join1, 0));
+            RAE_CUDA(h, cudaStreamWaitEvent(st, h->ev_join2, 0));
+        }
+        // (B) every owner has applied: the next step may fetch, the compact gradient buffers may be overwritten
+        if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st, 0))) return rc;
+        RAE_DMARK("barrier_applied", st, 0);
     }
-    // (B) every owner has applied: the next step may fetch, the compact gradient buffers may be overwritten
-    if (flags && (rc = launch_peer_barrier(h, d->flag_bufs, d->world, d->rank, st))) return rc;
+    h->push.f_ids = nullptr;        // valid for the step whose descriptor set them only
+    h->push.e_ids = nullptr;
     if (d->cost_dev && !gcost) return rae_copy_cost(h, d->cost_dev, stream);
     return RAE_OK;
 }

@@ -119,7 +119,19 @@ __global__ void k_count_heads(const uint32_t* __restrict__ keys_s, int n, int32_
 // in chunk order and applies the update.  Hot rows (Zipf) are thereby spread over many warps; the summation order is a
 // fixed function of the sorted layout -> bitwise reproducible.  No atomics.
 
+// where an emitted (reduced) gradient row goes: the local buffer, or - gradient push - the owner's receive buffer
+struct PushTo { float* const* base; float* const* bias; const int32_t* ids; int world; long long rowoff; };
+__device__ __forceinline__ float* emit_row(const PushTo& t, float* local, uint32_t row, int width) {
+    if (t.base == nullptr) return local + (size_t)row * width;
+    return t.base[t.ids[row] % t.world] + ((size_t)t.rowoff + row) * width;
+}
+__device__ __forceinline__ float* emit_bias(const PushTo& t, float* local, uint32_t row) {
+    if (t.bias == nullptr) return local + row;
+    return t.bias[t.ids[row] % t.world] + (size_t)t.rowoff + row;
+}
+
 struct EntArgs {
+    PushTo push;
     const uint32_t* keys_s; const uint32_t* vals_s;
     const float* ev; const float* sc; const float* gn1; const float* gn2;
     float* A; float* Ab; float* accA; float* accAb;
@@ -149,6 +161,7 @@ __device__ __forceinline__ int long_segment_start(const uint32_t* __restrict__ k
 }
 
 struct WArgs {
+    PushTo push;
     const uint32_t* keys_s; const uint32_t* vals_s;
     const float* dz;
     float* W; float* accW; float* gW_dense;
@@ -210,6 +223,7 @@ __device__ __forceinline__ void opt_apply4(float4& w, float4& a, const float4& g
 
 
 struct RowsArgs {
+    PushTo push;
     const uint32_t* keys_s; const uint32_t* vals_s; int n;
     const float* payload;      // W: dz [B,K] ; entity: ev
     int width;                 // floats per table row (K or d)
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
                 if (parked) {
                     p.part[(size_t)s.slot * p.pitch + p.dp] = gb;
                 } else {
-                    if (p.emit) p.gb_out[s.key] = gb;
+                    if (p.emit) *emit_bias(p.push, p.gb_out, s.key) = gb;
                     if (p.apply) {
                         float w = p.tableb[s.key];
                         if (p.adagrad) {
@@ -456,13 +470,14 @@ __global__ void __launch_bounds__(256) k_rows_chunk(RowsArgs p, int slab_cols) {
                     }
                     const size_t idx = (size_t)row[u] * p.width + q;
                     if (p.emit) {
+                        float* go = emit_row(p.push, p.g_out, row[u], p.width) + q;
                         if (VEC) {
-                            *reinterpret_cast<float4*>(p.g_out + idx) = g;
+                            *reinterpret_cast<float4*>(go) = g;
                         } else {
-                            p.g_out[idx] = g.x;
-                            if (q + 1 < p.width) p.g_out[idx + 1] = g.y;
-                            if (q + 2 < p.width) p.g_out[idx + 2] = g.z;
-                            if (q + 3 < p.width) p.g_out[idx + 3] = g.w;
+                            go[0] = g.x;
+                            if (q + 1 < p.width) go[1] = g.y;
+                            if (q + 2 < p.width) go[2] = g.z;
+                            if (q + 3 < p.width) go[3] = g.w;
                         }
                     }
                     if (p.apply) {
@@ -577,7 +592,7 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
             if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
             if (slot0 >= 0 && m <= LONG_WARP_MAX) {
                 const size_t ro = (size_t)row * p.K;
-                long2_warp_row(p.part, p.K, p.K, slot0, c, m, p.W + ro, p.accW + ro, p.gW_dense + ro, p.lr, p.adagrad, p.emit, p.apply, lane);
+                long2_warp_row(p.part, p.K, p.K, slot0, c, m, p.W + ro, p.accW + ro, emit_row(p.push, p.gW_dense, row, p.K), p.lr, p.adagrad, p.emit, p.apply, lane);
                 slot0 = -1;
             }
             if (lane == 0) { sh_slot[warp] = slot0; sh_m[warp] = m; sh_row[warp] = row; }
@@ -611,7 +626,7 @@ __global__ void __launch_bounds__(256) k_w_long2(WArgs p) {
 #pragma unroll
                 for (int w = 0; w < 8; ++w) g += red[w * p.K + k];
                 const size_t idx = (size_t)row * p.K + k;
-                if (p.emit) p.gW_dense[idx] = g;
+                if (p.emit) emit_row(p.push, p.gW_dense, row, p.K)[k] = g;
                 if (p.apply) {
                     float wv = p.W[idx];
                     if (p.adagrad) {
@@ -647,11 +662,11 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
             if (slot0 >= 0) m = long_extent<0>(p.keys_s, nchunks, c, row, lane);
             if (slot0 >= 0 && m <= LONG_WARP_MAX) {
                 const size_t ro = (size_t)row * p.d;
-                long2_warp_row(p.part, PE, p.d, slot0, c, m, p.A + ro, p.accA + ro, p.gA_dense + ro, p.lr, p.adagrad, p.emit, p.apply, lane);
+                long2_warp_row(p.part, PE, p.d, slot0, c, m, p.A + ro, p.accA + ro, emit_row(p.push, p.gA_dense, row, p.d), p.lr, p.adagrad, p.emit, p.apply, lane);
                 if (lane == 0) {        // bias partial at column dp
                     float g = p.part[(size_t)slot0 * PE + p.dp];
                     for (int u = 0; u < m; ++u) g += p.part[(size_t)(2 * (c + 1 + u)) * PE + p.dp];
-                    if (p.emit) p.gAb_dense[row] = g;
+                    if (p.emit) *emit_bias(p.push, p.gAb_dense, row) = g;
                     if (p.apply) {
                         float wv = p.Ab[row];
                         if (p.adagrad) {
@@ -699,7 +714,7 @@ __global__ void __launch_bounds__(256) k_entity_long2(EntArgs p) {
                 float* P = (j == p.dp) ? p.Ab + row : p.A + (size_t)row * p.d + j;
                 float* AC = (j == p.dp) ? p.accAb + row : p.accA + (size_t)row * p.d + j;
                 if (p.emit) {
-                    if (j == p.dp) p.gAb_dense[row] = g; else p.gA_dense[(size_t)row * p.d + j] = g;
+                    if (j == p.dp) *emit_bias(p.push, p.gAb_dense, row) = g; else emit_row(p.push, p.gA_dense, row, p.d)[j] = g;
                 }
                 if (p.apply) {
                     float wv = *P;
@@ -1038,6 +1053,8 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
     p.gA_dense = h->gA_dense; p.gAb_dense = h->gAb_dense;
     p.B = h->B; p.S = h->S; p.d = h->d; p.dp = h->dp; p.n = (int)n_occ;
     p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = emit_dense; p.apply = apply;
+    if (h->emit_only && h->push.on && h->push.e_ids != nullptr)
+        p.push = PushTo{h->push.a_dev, h->push.ab_dev, h->push.e_ids, h->push.world, (long long)h->push.rank * h->push.n_cap};
     const int64_t nchunks = (n_occ + 31) / 32;
     int rc = ensure_part(h, &h->ent_part, &h->ent_part_cap, (size_t)(2 * nchunks) * (h->dp + 4));
     if (rc) return rc;
@@ -1049,6 +1066,7 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
     r.lr = p.lr; r.adagrad = p.adagrad; r.emit = p.emit; r.apply = p.apply;
     r.B = h->B; r.S = h->S; r.dp = h->dp; r.sc = h->sc; r.gn1 = h->gn1; r.gn2 = h->gn2;
     r.tableb = p.Ab; r.accb = p.accAb; r.gb_out = p.gAb_dense;
+    r.push = p.push;
     if ((rc = launch_rows_chunk<1>(h, r, st))) return rc;
     const int blocks2 = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
     launch_pdl(k_entity_long2, dim3(blocks2), dim3(256), sizeof(float) * 8 * (h->dp + 4), st, p);
@@ -1060,9 +1078,11 @@ int launch_entity_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* 
 // feature rows (and the generic owner-side apply): table[row,:] updated with the sum of payload[val,:] over the row's
 // sorted occurrences
 static int rows_update(rae_engine* h, float* table, float* acc, float* g_out, int width, const uint32_t* keys_s,
-                       const uint32_t* vals_s, const float* payload, int64_t n, bool emit, bool apply, cudaStream_t st) {
+                       const uint32_t* vals_s, const float* payload, int64_t n, bool emit, bool apply, cudaStream_t st,
+                       const PushTo* push = nullptr) {
     if (n <= 0) return RAE_OK;
     WArgs p{};
+    if (push != nullptr) p.push = *push;
     p.keys_s = keys_s; p.vals_s = vals_s;
     p.dz = payload; p.W = table; p.accW = acc; p.gW_dense = g_out;
     p.K = width; p.n = (int)n; p.lr = (float)h->cfg.lr; p.adagrad = h->adagrad; p.emit = emit; p.apply = apply;
@@ -1075,6 +1095,7 @@ static int rows_update(rae_engine* h, float* table, float* acc, float* g_out, in
     r.payload = payload; r.width = width; r.pitch = width;
     r.table = table; r.acc = acc; r.g_out = g_out; r.part = p.part;
     r.lr = p.lr; r.adagrad = p.adagrad; r.emit = emit; r.apply = apply;
+    r.push = p.push;
     if ((rc = launch_rows_chunk<0>(h, r, st))) return rc;
     const int blocks2 = (int)std::min<int64_t>((nchunks + 7) / 8, (int64_t)h->num_sms * 8);
     launch_pdl(k_w_long2, dim3(blocks2), dim3(256), sizeof(float) * 8 * width, st, p);
@@ -1085,7 +1106,11 @@ static int rows_update(rae_engine* h, float* table, float* acc, float* g_out, in
 
 int launch_w_update(rae_engine* h, const uint32_t* keys_s, const uint32_t* vals_s, int64_t nnz, bool emit_dense,
                     bool apply, cudaStream_t st) {
-    return rows_update(h, h->P[RAE_P_W], h->ACC[RAE_P_W], h->gW_dense, h->K, keys_s, vals_s, h->dz, nnz, emit_dense, apply, st);
+    PushTo push{};
+    const bool pushing = h->emit_only && h->push.on && h->push.f_ids != nullptr;
+    if (pushing) push = PushTo{h->push.w_dev, nullptr, h->push.f_ids, h->push.world, (long long)h->push.rank * h->push.f_cap};
+    return rows_update(h, h->P[RAE_P_W], h->ACC[RAE_P_W], h->gW_dense, h->K, keys_s, vals_s, h->dz, nnz, emit_dense, apply, st,
+                       pushing ? &push : nullptr);
 }
 
 int build_row_keys(rae_engine* h, const int32_t* rows, int64_t n, cudaStream_t st) {

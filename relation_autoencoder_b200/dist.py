@@ -262,8 +262,13 @@ class CudaBackend(GranularStep):
         self.h = self.eng._h
         f32 = dict(dtype=torch.float32, device=self.device)
         self.compact = {"W": torch.zeros(f_cap, de.K, **f32), "A": torch.zeros(n_cap, de.d, **f32), "Ab": torch.zeros(n_cap, **f32)}
-        self.grad_buf = {"W": PeerBuffer(self.lib, (f_cap, de.K), self.device), "A": PeerBuffer(self.lib, (n_cap, de.d), self.device),
-                         "Ab": PeerBuffer(self.lib, (n_cap,), self.device)}
+        # gradient PUSH: every rank owns RECEIVE buffers with one region per source rank, [world][cap][width]; the emit-only
+        # row-update kernels of rank s store the reduced gradient row of compact slot j into region [s][j] of the row's
+        # owner (posted stores over NVLink beside the dense contraction), and the owner applies from local memory
+        self.f_cap, self.n_cap = int(f_cap), int(n_cap)
+        W_ = de.world
+        self.grad_buf = {"W": PeerBuffer(self.lib, (W_ * f_cap, de.K), self.device), "A": PeerBuffer(self.lib, (W_ * n_cap, de.d), self.device),
+                         "Ab": PeerBuffer(self.lib, (W_ * n_cap,), self.device)}
         # the flat dense gradient and the barrier flags are peer-visible too: with them the step needs NO collective
         n_dense = int(self.lib.rae_dense_grad_size(self.h))
         self.grad_buf["dense"] = PeerBuffer(self.lib, (n_dense,), self.device)
@@ -271,6 +276,15 @@ class CudaBackend(GranularStep):
         self._exchange(self.grad_buf)
         self.dense_grad = self.grad_buf["dense"].tensor
         self.peer_sync = True
+        gb = self.grad_buf
+        self.eng._check(self.lib.rae_bind_push_targets(self.h, gb["W"].peer_array(), gb["A"].peer_array(), gb["Ab"].peer_array(),
+                                                       de.world, de.rank, self.f_cap, self.n_cap), "rae_bind_push_targets")
+        # the owner-side apply reads the `world` regions of the OWN receive buffers
+        def regions(buf, cap, width):
+            base = buf.tensor.data_ptr()
+            return (C.c_void_p * de.world)(*[base + 4 * r * cap * width for r in range(de.world)])
+        self._recv_regions = {"W": regions(gb["W"], self.f_cap, de.K), "A": regions(gb["A"], self.n_cap, de.d),
+                              "Ab": regions(gb["Ab"], self.n_cap, 1)}
         # small dense gradients are summed straight from the peers' buffers inside the dense update; large ones (d = 128:
         # 6.6 MB) go through NCCL's all-reduce, which moves 2(n-1)/n of the bytes instead of (n-1)
         self.peer_dense = (de.world - 1) * n_dense * 4 <= (16 << 20)
@@ -310,7 +324,7 @@ class CudaBackend(GranularStep):
         if n_rows == 0:
             return
         self.eng._check(self.lib.rae_pull_apply(self.h, self._p(table), self._p(acc), width, self._p(rows_local), self._p(ent_off),
-                                                self._p(ent_src), self._p(ent_slot), n_rows, self.grad_buf[name].peer_array(),
+                                                self._p(ent_src), self._p(ent_slot), n_rows, self._recv_regions[name],
                                                 self.de.world, self._stream), "rae_pull_apply")
 
     def local_cost_tensor(self) -> torch.Tensor:
@@ -333,7 +347,7 @@ class CudaBackend(GranularStep):
             d = L.RaeDistStep()
             d.world = de.world
             d.w_shards, d.a_shards, d.ab_shards = vp(self._peer_arrays["W"]), vp(self._peer_arrays["A"]), vp(self._peer_arrays["Ab"])
-            d.gw_bufs, d.ga_bufs, d.gab_bufs = vp(self._grad_arrays["W"]), vp(self._grad_arrays["A"]), vp(self._grad_arrays["Ab"])
+            d.gw_bufs, d.ga_bufs, d.gab_bufs = (vp(self._recv_regions[k]) for k in ("W", "A", "Ab"))
             d.Wc, d.Ac, d.Abc = (self.compact[k].data_ptr() for k in ("W", "A", "Ab"))
             d.f_ids, d.n_f = el(fp.u_ids, fp.u_off[b]), fp.u_off[b + 1] - fp.u_off[b]
             d.e_ids, d.n_e = el(ep.u_ids, ep.u_off[b]), ep.u_off[b + 1] - ep.u_off[b]
@@ -606,6 +620,14 @@ class DistributedEngine:
         cost all-reduce / barrier).  Adds event records: never on for a timed run."""
         self._profiling = bool(on) and self.dev.type == "cuda"
         self._phase_log = []
+
+    def set_timeline(self, on: bool):
+        """Timeline mode of this rank's handle (rae_set_profiling(h, 2)): events behind every kernel group of the sharded
+        step on the stream it ran on, overlap kept."""
+        self.backend.eng.set_profiling(2 if on else 0)
+
+    def timeline(self):
+        return self.backend.eng.timeline()
 
     def phase_times_ms(self) -> Dict[str, float]:
         names = ("fetch_and_local_step", "dense_allreduce", "dense_apply_and_pull", "cost_allreduce_barrier")
