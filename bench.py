@@ -328,10 +328,11 @@ def _measure(args, wl, wl_name, rank, world, local_rank, dist, steps, warmup, mi
     if world > 1:
         from relation_autoencoder_b200.dist import DistributedEngine
         eng = DistributedEngine(wl["model"], wl["K"], wl["d"], wl["S"], B, wl["F"], wl["N"], wl["N_train"], lr=0.1,
-                                l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, rank=rank, world=world)
+                                l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, rank=rank, world=world,
+                                peer_dense_max_bytes=int(args.peer_dense_max_mb * (1 << 20)))
     else:
         eng = Engine(wl["model"], wl["K"], wl["d"], wl["S"], B, wl["F"], wl["N"], wl["N_train"], lr=0.1,
-                     l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, flags=128 if args.no_pdl else 0)
+                     l2=wl.get("l2", 0.0), alpha=wl.get("alpha", 1.0), device=local_rank, flags=(128 if args.no_pdl else 0) | args.engine_flags)
     eng.set_params_numpy(params)
     del params
 
@@ -632,6 +633,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra cfg2 record")
     ap.add_argument("--uniform", action="store_true", help="uniform instead of Zipf feature ids")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-dense-max-mb", type=float, default=16.0, help="N GPUs: remote dense-gradient bytes per rank up to which the "
+                    "dense update sums the peers' buffers itself; above it NCCL's all-reduce runs beside the sparse-row applies")
+    ap.add_argument("--engine-flags", type=int, default=0, help="extra RAE_FLAG_* bits for the 1-GPU engine (4 = force the SIMT contraction)")
     ap.add_argument("--no-pdl", action="store_true", help="RAE_FLAG_NO_PDL: plain stream-order launches (A/B of programmatic dependent launch)")
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU work allowed for the CPU legs")
     args = ap.parse_args()

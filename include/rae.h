@@ -245,6 +245,10 @@ typedef struct rae_dist_step {
  * dense-gradient contraction instead of loads on the critical path behind the barrier. */
 int rae_bind_push_targets(rae_engine* h, const void* const* gw, const void* const* ga, const void* const* gab, int32_t world,
                           int32_t rank, int64_t f_cap, int64_t n_cap);
+/* dense_bufs == NULL (the caller all-reduces the dense gradient): `event` (a cudaEvent_t recorded behind that all-reduce, on
+ * any stream) is waited for by the NEXT rae_dist_step_end right before its dense update - so the all-reduce may run beside
+ * the barrier and the sparse-row applies instead of in front of them.  Consumed by that call. */
+int rae_dist_set_dense_wait(rae_engine* h, void* event);
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream);
 int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream);
 /* func['train'](batch_index, neg1, neg2) form of rae_dist_step_begin: this rank's HOST negatives int32[S,B] with row strides

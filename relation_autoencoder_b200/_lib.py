@@ -98,6 +98,7 @@ _SIGNATURES = {
     "rae_dist_step_end": (C.c_int, [_P, C.POINTER(RaeDistStep), _P]),
     "rae_dist_step_begin_host": (C.c_int, [_P, C.POINTER(RaeDistStep), _P, C.c_int64, _P, C.c_int64, _P]),
     "rae_bind_push_targets": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
+    "rae_dist_set_dense_wait": (C.c_int, [_P, _P]),
     "rae_dist_read_cost": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "rae_peer_barrier": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "rae_peer_status": (C.c_int, [_P, _P]),

@@ -183,6 +183,7 @@ struct rae_engine {
     // overlapping the dense contraction that runs beside them); the owner then applies from local memory
     struct { float** w_dev; float** a_dev; float** ab_dev; int world, rank; int64_t f_cap, n_cap; bool on;
              const int32_t* f_ids; const int32_t* e_ids; } push;
+    void* dense_wait;           // cudaEvent_t the next rae_dist_step_end waits for before its dense update (caller's all-reduce)
     bool tl_keep;               // the next run_step appends to the marks recorded by rae_dist_step_begin instead of restarting
     bool timeline; int tl_n; cudaEvent_t tl_ev[RAE_TL_MAX]; const char* tl_name[RAE_TL_MAX]; int tl_stream[RAE_TL_MAX]; bool tl_created;
     const uint32_t* last_f_keys_s; int64_t last_f_n;   // sorted feature keys of the last step (statistics)

@@ -567,6 +567,12 @@ int rae_bind_push_targets(rae_engine* h, const void* const* gw, const void* cons
     return RAE_OK;
 }
 
+int rae_dist_set_dense_wait(rae_engine* h, void* event) {
+    if (!h) return RAE_EINVAL;
+    h->dense_wait = event;
+    return RAE_OK;
+}
+
 int rae_dist_step_begin(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (!h || !d) return fail(h, RAE_EINVAL, "rae_dist_step_begin: null argument");
     if (peer_failed(h)) return RAE_ECUDA;
@@ -687,7 +693,15 @@ int rae_dist_step_end(rae_engine* h, const rae_dist_step* d, void* stream) {
     if (d->n_fr > 0 && (rc = rae_pull_apply(h, d->W, d->accW, h->K, d->fr_rows, d->fr_off, d->f_src, d->f_slot, d->n_fr, d->gw_bufs,
                                             d->world, stream))) return rc;
     RAE_DMARK("apply_W", st, 0);
-    if (!peer_dense && (rc = rae_train_step_end(h, stream))) return rc;
+    if (!peer_dense) {
+        // the caller all-reduced the dense gradient itself - possibly on another stream, beside the barrier and the applies
+        // above (rae_dist_set_dense_wait): the dense update is the first thing here that needs the sum
+        if (h->dense_wait != nullptr) {
+            RAE_CUDA(h, cudaStreamWaitEvent(st, (cudaEvent_t)h->dense_wait, 0));
+            h->dense_wait = nullptr;
+        }
+        if ((rc = rae_train_step_end(h, stream))) return rc;
+    }
     if (side && flags) {
         // Split tail.  The next step's first consumers of the tables are the W fetch and the encoder on this stream: they
         // need every owner's W apply only.  The entity rows are fetched on s1, so "every owner has applied A, Ab and the

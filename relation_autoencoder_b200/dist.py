@@ -287,7 +287,7 @@ class CudaBackend(GranularStep):
                               "Ab": regions(gb["Ab"], self.n_cap, 1)}
         # small dense gradients are summed straight from the peers' buffers inside the dense update; large ones (d = 128:
         # 6.6 MB) go through NCCL's all-reduce, which moves 2(n-1)/n of the bytes instead of (n-1)
-        self.peer_dense = (de.world - 1) * n_dense * 4 <= (16 << 20)
+        self.peer_dense = (de.world - 1) * n_dense * 4 <= de.peer_dense_max_bytes
 
     def bind_dense(self, dense: Dict[str, torch.Tensor], dense_acc: Dict[str, torch.Tensor]):
         g = lambda m, n: self._p(m.get(n))
@@ -385,6 +385,17 @@ class CudaBackend(GranularStep):
         self.eng._check(self.lib.rae_dist_step_begin_host(self.h, C.byref(self.descs[b]), p1, ld1, p2, ld2, self._stream),
                         "rae_dist_step_begin_host")
 
+    def dense_allreduce_aside(self, group):
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_ar_stream", None) is None:
+            self._ar_stream = torch.cuda.Stream(device=self.device)
+            self._ar_event = torch.cuda.Event()
+        self._ar_stream.wait_stream(cur)
+        with torch.cuda.stream(self._ar_stream):
+            dist.all_reduce(self.dense_grad, group=group)
+            self._ar_event.record(self._ar_stream)
+        self.eng._check(self.lib.rae_dist_set_dense_wait(self.h, C.c_void_p(self._ar_event.cuda_event)), "rae_dist_set_dense_wait")
+
     def run_end(self, de, b):
         self.eng._check(self.lib.rae_dist_step_end(self.h, C.byref(self.descs[b]), self._stream), "rae_dist_step_end")
         return self.cost_t
@@ -421,7 +432,9 @@ class DistributedEngine:
 
     def __init__(self, model: str, K: int, d: int, S: int, B: int, F: int, N: int, n_train: int, lr: float = 0.1,
                  l1: float = 0.0, l2: float = 0.0, alpha: float = 1.0, optimizer: str = "adagrad", ext_reg: bool = True,
-                 device=0, rank: Optional[int] = None, world: Optional[int] = None, backend_factory=None, group=None):
+                 device=0, rank: Optional[int] = None, world: Optional[int] = None, backend_factory=None, group=None,
+                 peer_dense_max_bytes: int = 16 << 20):
+        self.peer_dense_max_bytes = int(peer_dense_max_bytes)
         if l1 != 0.0 or l2 != 0.0:
             raise NotImplementedError("row-sharded multi-GPU training supports l1 = l2 = 0 only (the regulariser makes dW dense)")
         from .engine import MODEL_IDS, MODEL_PARAMS
@@ -593,7 +606,12 @@ class DistributedEngine:
         if ev: ev[1].record()
         peer_sync = getattr(bk, "peer_sync", False)               # CUDA backend: flag barriers over peer memory inside run_end
         if self.world > 1 and not getattr(bk, "peer_dense", False):
-            dist.all_reduce(bk.dense_grad, group=self.group)      # sum of the ranks' dense gradients (C | C1 | C2 | Wb);
+            if peer_sync and hasattr(bk, "dense_allreduce_aside"):
+                # NCCL's all-reduce of the dense gradient runs on its own stream BESIDE the flag barrier and the sparse-row
+                # applies of run_end (they do not need the sum); the dense update inside run_end waits for its event
+                bk.dense_allreduce_aside(self.group)
+            else:
+                dist.all_reduce(bk.dense_grad, group=self.group)  # sum of the ranks' dense gradients (C | C1 | C2 | Wb);
         if ev: ev[2].record()                                     # without peer_sync it also orders "every rank has emitted"
         cost = bk.run_end(self, b)
         if ev: ev[3].record()

@@ -41,7 +41,8 @@ def main():
         loc_ip.append(len(loc_ix))
     de = DistributedEngine(model, K, d, S, B, F, N, n_train=Bg * nb, lr=0.1, alpha=0.7, rank=rank, world=world,
                            device=int(os.environ.get("LOCAL_RANK", "0")),
-                           backend_factory=None if cuda else NumpyBackend)
+                           backend_factory=None if cuda else NumpyBackend,
+                           peer_dense_max_bytes=int(os.environ.get("RAE_TEST_PEER_DENSE_MAX", str(16 << 20))))
     tol = 2e-5 if cuda else 1e-12
     de.set_params_numpy(p0)
     de.bind_split("train", np.asarray(loc_ip), np.asarray(loc_ix), pr["a1"][rows], pr["a2"][rows])

@@ -28,6 +28,18 @@ def test_sharded_step_matches_oracle(model, world):
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:]
 
 
+def test_sharded_step_with_nccl_dense_allreduce_aside():
+    """The dense gradient too large for the peer-read update (forced here: threshold 0) goes through NCCL's all-reduce on
+    its own stream, beside the flag barrier and the sparse-row applies; the dense update waits for its event."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py"), "rescal+sp", "cuda"]
+    env = dict(os.environ, RAE_TEST_PEER_DENSE_MAX="0")
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:]
+
+
 def test_peer_barrier_timeout_is_fatal_and_skips_the_pulls():
     """A rank that never arrives (here: world = 2 with nobody behind rank 1's flag word) makes the bounded barrier time
     out (~2 s).  From then on the handle is dead: the owner-side pull kernels leave the tables untouched (the peers'
