@@ -549,11 +549,11 @@ def _run_ours(args, wl, rank, world, local_rank):
 
 
 PHASE_KERNELS = {      # phase -> the kernel it times (rae.h: one phase = one kernel of the step plus small helpers)
-    "encoder_forward": "k_encoder_forward_v4", "entity_sort": "entity occurrence sort",
+    "encoder_forward": "k_encoder_forward_v4", "entity_sort": "k_radix_sort<1> (own cooperative radix sort)",
     "operand_prep": "k_tc_prep_c + k_tc_prep_qt", "contract_forward": "k_tc_bilinear (forward)", "score": "k_score",
     "entity_update": "k_rows_chunk<1> + k_entity_long2", "w_update": "k_rows_chunk<0> + k_w_long2",
     "contract_recompute": "k_tc_bilinear (recompute)", "contract_dq": "k_tc_transpose_al + k_tc_dq", "backward_finish": "k_tc_bwd_finish",
-    "contract_dc": "k_tc_dc", "dense_finalize": "k_dense_finalize", "cost": "k_cost", "dense_apply": "k_dense_apply",
+    "contract_dc": "k_tc_dc", "dense_finalize": "k_dense_finalize (+ fused optimiser rule)", "cost": "k_cost", "dense_apply": "k_dense_apply (regulariser path only)",
 }
 
 
