@@ -753,6 +753,23 @@ __device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
     return ds.tile_slots[n >> 7];
 }
 
+// sum of the `nsplit` partial slots of 4 consecutive elements, in slot order, 8 slots per round trip: the loads of a round
+// are issued back to back (volatile asm; slots beyond nsplit re-read the last valid one - a cache hit - and are dropped by
+// the select).  The C1 / C2 tiles of the one-tile dC kernel have 64 slots: read one after the other (a load - add chain)
+// they made 25 CTAs of this kernel run 40 us after the other 1700 had finished (ncu: SMs active 38 % of the duration).
+__device__ __forceinline__ float4 sum_slots(const float* __restrict__ part, size_t plane, size_t i0, int nsplit) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp0 = 0; sp0 < nsplit; sp0 += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = ldg_stream4(part + (size_t)min(sp0 + u, nsplit - 1) * plane + i0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (sp0 + u < nsplit) { s.x += x[u].x; s.y += x[u].y; s.z += x[u].z; s.w += x[u].w; }
+    }
+    return s;
+}
+
 // fused optimiser step (single-GPU production path): the summed gradient goes straight into the AdaGrad / SGD rule of its
 // element of C | C1 | C2 | Wb instead of through the flat gradient buffer and a second kernel (Optimizers.py:29-32,51).
 // Only taken when every tensor is 16-byte aligned and K % 4 == 0 (launch_dense_finalize checks).
@@ -783,19 +800,9 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
             // asm stays in program order): ONE memory latency per thread.  Written as conditional loads the compiler chained
             // them, load - add - load - add through one register (38 us for 46 MB, ncu).  Slots beyond nsplit re-read the last
             // valid one (a cache hit) and are dropped by the select.
-            float4 x[8];
-#pragma unroll
-            for (int sp = 0; sp < 8; ++sp) x[sp] = ldg_stream4(part + (size_t)max(min(sp, nsplit - 1), 0) * n_units_elems + i0);
             float4 w = *reinterpret_cast<const float4*>(pp);
             float4 a = fz.adagrad ? *reinterpret_cast<const float4*>(pa) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 s = nsplit > 0 ? x[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int sp = 1; sp < 8; ++sp)
-                if (sp < nsplit) { s.x += x[sp].x; s.y += x[sp].y; s.z += x[sp].z; s.w += x[sp].w; }
-            for (int sp = 8; sp < nsplit; ++sp) {
-                const float4 y = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
-                s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
-            }
+            const float4 s = sum_slots(part, n_units_elems, i0, nsplit);
             const bool reg = fz.r1 != 0.f || fz.r2 != 0.f;
             dense_rule(w.x, a.x, s.x, fz, reg); dense_rule(w.y, a.y, s.y, fz, reg);
             dense_rule(w.z, a.z, s.z, fz, reg); dense_rule(w.w, a.w, s.w, fz, reg);
@@ -806,17 +813,7 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
         if ((n_units_elems & 3) == 0 && (K & 3) == 0) {        // the 4 elements share a row
             const int nsplit = dense_slots_of(ds, i0);
             // all slot loads are issued before the first add (one memory latency, not one per slot); summed in slot order
-            float4 x[8];
-#pragma unroll
-            for (int sp = 0; sp < 8; ++sp) x[sp] = ldg_stream4(part + (size_t)max(min(sp, nsplit - 1), 0) * n_units_elems + i0);
-            float4 s = nsplit > 0 ? x[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int sp = 1; sp < 8; ++sp)
-                if (sp < nsplit) { s.x += x[sp].x; s.y += x[sp].y; s.z += x[sp].z; s.w += x[sp].w; }
-            for (int sp = 8; sp < nsplit; ++sp) {
-                const float4 y = *reinterpret_cast<const float4*>(part + (size_t)sp * n_units_elems + i0);
-                s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
-            }
+            const float4 s = sum_slots(part, n_units_elems, i0, nsplit);
             *reinterpret_cast<float4*>(out + i0) = s;
         } else {
             for (size_t i = i0; i < min(i0 + 4, n_units_elems); ++i) {

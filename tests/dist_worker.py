@@ -43,7 +43,7 @@ def main():
                            device=int(os.environ.get("LOCAL_RANK", "0")),
                            backend_factory=None if cuda else NumpyBackend,
                            peer_dense_max_bytes=int(os.environ.get("RAE_TEST_PEER_DENSE_MAX", str(16 << 20))))
-    tol = 2e-5 if cuda else 1e-12
+    tol = 1e-5 if cuda else 1e-12
     de.set_params_numpy(p0)
     de.bind_split("train", np.asarray(loc_ip), np.asarray(loc_ix), pr["a1"][rows], pr["a2"][rows])
     de.bind_epoch_negatives(pr["neg1"][:, rows], pr["neg2"][:, rows])
