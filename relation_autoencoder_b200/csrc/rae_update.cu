@@ -753,13 +753,22 @@ __device__ __forceinline__ int dense_slots_of(const DenseSlots& ds, size_t i0) {
     return ds.tile_slots[n >> 7];
 }
 
-// sum of the `nsplit` partial slots of 4 consecutive elements, in slot order, 8 slots per round trip: the loads of a round
+// sum of the `nsplit` partial slots of 4 consecutive elements, in slot order, 8 or 16 slots per round trip: the loads of a round
 // are issued back to back (volatile asm; slots beyond nsplit re-read the last valid one - a cache hit - and are dropped by
 // the select).  The C1 / C2 tiles of the one-tile dC kernel have 64 slots: read one after the other (a load - add chain)
 // they made 25 CTAs of this kernel run 40 us after the other 1700 had finished (ncu: SMs active 38 % of the duration).
 __device__ __forceinline__ float4 sum_slots(const float* __restrict__ part, size_t plane, size_t i0, int nsplit) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sp0 = 0; sp0 < nsplit; sp0 += 8) {
+    int sp0 = 0;
+    for (; sp0 + 8 < nsplit; sp0 += 16) {              // more than 8 slots left: 16 per round trip
+        float4 x[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x[u] = ldg_stream4(part + (size_t)min(sp0 + u, nsplit - 1) * plane + i0);
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (sp0 + u < nsplit) { s.x += x[u].x; s.y += x[u].y; s.z += x[u].z; s.w += x[u].w; }
+    }
+    for (; sp0 < nsplit; sp0 += 8) {
         float4 x[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) x[u] = ldg_stream4(part + (size_t)min(sp0 + u, nsplit - 1) * plane + i0);
@@ -788,7 +797,9 @@ __global__ void __launch_bounds__(256) k_dense_finalize(const float* __restrict_
                                                         float* __restrict__ out, size_t off_wb, int n_elem_blocks, DenseFuse fz) {
     pdl_enter();
     if ((int)blockIdx.x < n_elem_blocks) {
-        const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        // element blocks in REVERSE order: the C1 / C2 rows at the end of the flat layout have the most partial slots (64 at
+        // the target shape, several load round trips): their CTAs start in the first wave instead of the last
+        const size_t i0 = ((size_t)(n_elem_blocks - 1 - (int)blockIdx.x) * blockDim.x + threadIdx.x) * 4;
         if (i0 >= n_units_elems) return;
         if (fz.on) {
             const int t = i0 >= fz.off[2] ? 2 : (i0 >= fz.off[1] ? 1 : 0);
