@@ -66,8 +66,8 @@ extern "C" {
 #define RAE_FLAG_FORCE_SIMT 4u      /* never take the tcgen05 contraction path */
 #define RAE_FLAG_FORCE_TENSOR 8u    /* fail instead of falling back when the tcgen05 path does not support the shape */
 #define RAE_FLAG_NO_FEATURE_CACHE 16u /* re-sort the batch's (feature, example) pairs every step instead of once at bind */
-#define RAE_FLAG_CLUSTER_MULTICAST 64u /* tcgen05 path: thread-block clusters, streamed operand fetched once per cluster (multicast).
-                                         * Measured on B200: no gain (the kernels are not operand-traffic bound) -> off by default */
+#define RAE_FLAG_CLUSTER_MULTICAST 64u /* accepted and ignored: the cluster-multicast variant of the tcgen05 path measured no gain on
+                                         * B200 (the kernels are not operand-traffic bound) and was removed */
 #define RAE_FLAG_NO_PDL 128u        /* launch the step's kernels in plain stream order (no programmatic dependent launch): A/B measurements */
 #define RAE_FLAG_EMIT_ONLY 32u      /* row-sharded multi-GPU: W/A/Ab are per-step compact copies; emit per-row gradients, apply nothing */
 

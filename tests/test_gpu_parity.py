@@ -303,3 +303,47 @@ def test_errors_are_reported_not_thrown_across_the_abi():
     with pytest.raises(RuntimeError, match="unsupported sizes"):
         Engine("rescal+sp", 4, 300, 2, 8, 16, 16, 8)
     eng.close()
+
+
+def test_step_timeline_marks_follow_the_streams():
+    """rae_set_profiling(h, 2): the step keeps its three-stream overlap and records an event behind every kernel group on the
+    stream it ran on; per stream the marks are ordered in time, the step ends after all of them (bench.py: timeline_us)."""
+    sh = SHAPES["k100d128"]
+    pr = make_problem("AC", seed=21, **sh)
+    eng = _engine("AC", sh, flags=0)
+    eng.set_params_numpy(_to32(pr["p"]))
+    eng.set_profiling(2)
+    for _ in range(2):
+        eng.train_explicit(pr["indptr"], pr["indices"], pr["a1"], pr["a2"], pr["neg1"], pr["neg2"])
+    tl = eng.timeline()
+    eng.set_profiling(0)
+    names = [n for n, _, _ in tl]
+    assert names[0] == "start" and names[-1] == "end"
+    for want in ("encoder", "contract_forward", "score", "contract_dq", "backward_finish", "contract_dc", "dense_finalize",
+                 "entity_sort", "entity_update", "w_update"):
+        assert want in names, (want, names)
+    for stream in (0, 1, 2):
+        t = [us for _, s, us in tl if s == stream]
+        assert all(b >= a for a, b in zip(t, t[1:])), (stream, tl)
+    assert tl[-1][2] >= max(us for _, _, us in tl) - 1e-3
+    assert int(eng.stats()["tensor_path"]) == 1
+    eng.close()
+
+
+@pytest.mark.parametrize("model", O.MODELS)
+def test_programmatic_dependent_launch_changes_no_bit(model):
+    """The step's kernels are launched with programmatic stream serialization (griddepcontrol.wait before their first global
+    access); RAE_FLAG_NO_PDL launches them in plain stream order.  Same data dependencies, so the same bits."""
+    sh = SHAPES["b512d128"]
+    pr = make_problem(model, seed=22, dup_heavy=True, **sh)
+    outs = []
+    for flags in (0, 128):
+        eng = _engine(model, sh, flags=flags)
+        eng.set_params_numpy(_to32(pr["p"]))
+        costs = [eng.train_explicit(pr["indptr"], pr["indices"], pr["a1"], pr["a2"], pr["neg1"], pr["neg2"]) for _ in range(3)]
+        outs.append((costs, eng.get_params_numpy(), eng.get_acc_numpy()))
+        eng.close()
+    assert outs[0][0] == outs[1][0]
+    for n in outs[0][1]:
+        assert np.array_equal(outs[0][1][n], outs[1][1][n]), n
+        assert np.array_equal(outs[0][2][n], outs[1][2][n]), n
