@@ -282,17 +282,6 @@ __device__ __forceinline__ float ldg_ordered(const float* p) {
     return v;
 }
 
-// 16 bytes x 4 of one row -> 16 floats
-__device__ __forceinline__ void load16(const float* p, bool ok0, bool ok1, bool ok2, bool ok3, float (&x)[16]) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 a = ok0 ? *reinterpret_cast<const float4*>(p) : z;
-    const float4 b = ok1 ? *reinterpret_cast<const float4*>(p + 4) : z;
-    const float4 c = ok2 ? *reinterpret_cast<const float4*>(p + 8) : z;
-    const float4 d = ok3 ? *reinterpret_cast<const float4*>(p + 12) : z;
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-    x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w; x[12] = d.x; x[13] = d.y; x[14] = d.z; x[15] = d.w;
-}
-
 // segments of a CTA's range under the balanced schedule (rae_internal.h)
 struct TcSeg { int tile, u0, u1, slot; };
 struct TcSegIter {
