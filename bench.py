@@ -529,6 +529,10 @@ def _run_ours(args, wl, rank, world, local_rank):
         line["tf32_peak_tflops_measured"] = tf32_peak
     if phase_ms is not None:
         line["roofline"] = _roofline(wl, st, phase_ms, pk, args.workload, frag["step_roofline"], tf32_peak)
+        try:
+            line["tensor_kernels"] = _tensor_kernels(wl, st, phase_ms, pk, tf32_peak)
+        except Exception as e:          # a reporting extra must never cost the bench line
+            line["tensor_kernels"] = {"error": repr(e)}
     if extra:
         line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
@@ -569,6 +573,29 @@ def _traffic(workload, phase):
         except Exception:
             continue
     return None
+
+
+def _tensor_kernels(wl, st, phase_ms, pk, tf32_peak):
+    """Tensor roofline of the four contraction phases (always reported, whichever kernel dominates the step): algorithmic
+    2*B*(d+2)*d*K flop of one contraction / the phase's device time (the phase includes the small transposed-view / combine
+    helpers beside the tcgen05 kernel, so the kernel itself is slightly faster) against the TF32 cuBLAS GEMM measured in
+    this run (`frac`).  The kernels ISSUE 3x the algorithmic flops as kind::f16 MMAs (hi.hi + hi.lo + lo.hi on FP16 pairs),
+    whose rate is the bf16 one: `issued_frac` = 3 x achieved / the measured bf16 burst peak (MEASURED_PEAKS.json)."""
+    if not int(st.get("tensor_path", 0)):
+        return None
+    K, d, B = wl["K"], wl["d"], wl["B"]
+    units = (d if wl["model"] in ("rescal", "rescal+sp") else 0) + (2 if wl["model"] in ("sp", "rescal+sp") else 0)
+    gemm = 2.0 * B * units * d * K
+    peak = tf32_peak if tf32_peak else pk["bf16_burst"] / 2.0
+    out = {"issued_peak_tflops": pk["bf16_burst"], "peak_tflops": peak, "peak_is": "TF32 cuBLAS GEMM 8192^3 measured in this run" if tf32_peak else "bf16 burst / 2 (fallback)",
+           "algorithmic_flops_per_launch": gemm}
+    for ph in ("contract_forward", "contract_recompute", "contract_dq", "contract_dc"):
+        ms = phase_ms.get(ph)
+        if ms and ms > 0:
+            ach = gemm / (ms * 1e-3) / 1e12
+            out[ph] = {"ms": round(ms, 5), "tflops": round(ach, 1), "frac": round(ach / peak, 4),
+                       "issued_frac": round(3.0 * ach / pk["bf16_burst"], 4)}
+    return out
 
 
 def _roofline(wl, st, phase_ms, pk, workload, step_roofline, tf32_peak):

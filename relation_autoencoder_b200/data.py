@@ -191,11 +191,11 @@ def unpickle_objects(a_file, verbose=False):
         feats, lex, data, gold = _load_all(raw, 'utf-8')
     except UnicodeDecodeError:
         feats, lex, data, gold = _load_all(raw, 'latin-1')
-    assert type(feats) == list
-    assert isinstance(lex, FeatureLexicon), \
-        "Expected an instance of FeatureLexicon as the 2nd object to be pickled. Got '{}' instead".format(type(lex))
-    assert type(data) == dict
-    assert type(gold) == dict
+    # the four objects of a dataset file, in file order (validated like pickle_objects validates what it writes)
+    for pos, obj, want in ((1, feats, list), (2, lex, FeatureLexicon), (3, data, dict), (4, gold, dict)):
+        if not isinstance(obj, want):
+            raise AssertionError('%s: object %d of the dataset file is a %s, expected %s'
+                                 % (a_file, pos, type(obj).__name__, want.__name__))
     if verbose:
         print('  loaded feature extractors:', ', '.join("'" + str(getattr(_, '__name__', _)) + "'" for _ in feats))
         print('  loaded dataset with {} splits'.format(', '.join("'" + _ + "'" for _ in data.keys())))
