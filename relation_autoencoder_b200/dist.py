@@ -70,6 +70,26 @@ def _excl_cumsum(cnt: torch.Tensor) -> torch.Tensor:
     return off
 
 
+def _owned_entries(keys: List[torch.Tensor], nb: int, stride: int, rank: int, world: int):
+    """Owner-side view of every rank's distinct (batch, row) keys: for the rows this rank owns, (batch, local row, source rank,
+    compact slot of the row in that source's batch list).  One vectorised pass over the concatenated keys (no per-source
+    loop, no host synchronisation): a key's slot is its position inside its source's list minus the number of that
+    source's keys in earlier batches."""
+    dev = keys[0].device
+    sizes = torch.tensor([k.numel() for k in keys], dtype=torch.int64, device=dev)
+    allk = torch.cat(keys)
+    src = torch.repeat_interleave(torch.arange(world, dtype=torch.int64, device=dev), sizes)
+    b = torch.div(allk, stride, rounding_mode="floor")
+    idd = allk - b * stride
+    start_of_src = _excl_cumsum(sizes)[:-1]
+    pos = torch.arange(allk.numel(), dtype=torch.int64, device=dev) - start_of_src[src]
+    cnt = torch.bincount(src * nb + b, minlength=world * nb).reshape(world, nb)
+    off = torch.cumsum(cnt, 1) - cnt                       # [world, nb] keys of the source in earlier batches
+    slot = pos - off.reshape(-1)[src * nb + b]
+    own = (idd % world) == rank
+    return b[own], torch.div(idd[own], world, rounding_mode="floor"), src[own], slot[own]
+
+
 def build_epoch_plan(ids: torch.Tensor, batch_of: torch.Tensor, nb: int, n_rows_total: int, rank: int, world: int,
                      group=None) -> EpochPlan:
     """Collective.  ``ids`` int64 [n]: global row id of every occurrence this rank has in the epoch; ``batch_of`` int64 [n]:
@@ -97,19 +117,7 @@ def build_epoch_plan(ids: torch.Tensor, batch_of: torch.Tensor, nb: int, n_rows_
         keys = [gathered[s][: sizes[s]] for s in range(world)]
     else:
         keys = [ukey]
-    eb, erow, esrc, eslot = [], [], [], []
-    for s in range(world):
-        k = keys[s]
-        b = torch.div(k, stride, rounding_mode="floor")
-        idd = k - b * stride
-        off = _excl_cumsum(torch.bincount(b, minlength=nb))
-        slot = torch.arange(k.numel(), device=dev, dtype=torch.int64) - off[b]
-        own = (idd % world) == rank
-        eb.append(b[own])
-        erow.append(torch.div(idd[own], world, rounding_mode="floor"))
-        eslot.append(slot[own])
-        esrc.append(torch.full((int(own.sum().item()),), s, dtype=torch.int64, device=dev))
-    eb, erow, esrc, eslot = torch.cat(eb), torch.cat(erow), torch.cat(esrc), torch.cat(eslot)
+    eb, erow, esrc, eslot = _owned_entries(keys, nb, stride, rank, world)
     key2 = (eb * n_local + erow) * world + esrc            # distinct by construction: any sort gives the same order
     order = torch.argsort(key2)
     rowkey = torch.div(key2[order], world, rounding_mode="floor")
